@@ -1,0 +1,238 @@
+"""ctypes binding of include/dsrt.h (libdsrt.so).  No CPU fallback: a missing library raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+EXPORTED_SYMBOLS = [
+    "dsrt_create", "dsrt_destroy", "dsrt_last_error", "dsrt_version", "dsrt_set_scene", "dsrt_set_bvh",
+    "dsrt_set_camera", "dsrt_set_params", "dsrt_set_option", "dsrt_build_bvh2", "dsrt_build_accel",
+    "dsrt_accel_info", "dsrt_render", "dsrt_render_device", "dsrt_resolve_device", "dsrt_sync",
+    "dsrt_collect_stats", "dsrt_primary_hits", "dsrt_trace_closest", "dsrt_trace_any", "dsrt_tonemap",
+]
+
+
+class DsrtError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libdsrt.so")
+
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise DsrtError(f"{p} is missing: build it with `make -C dsgpuraytracing_b200/csrc` "
+                            "(or __graft_entry__.build()); there is no CPU fallback")
+        _lib = C.CDLL(p)
+        _lib.dsrt_last_error.restype = C.c_char_p
+        _lib.dsrt_version.restype = C.c_char_p
+    return _lib
+
+
+class _Scene(C.Structure):
+    _fields_ = [("n_prims", C.c_int32), ("prim_type", C.c_void_p), ("prim_bsdf", C.c_void_p),
+                ("tri_pos", C.c_void_p), ("tri_nrm", C.c_void_p), ("sphere", C.c_void_p),
+                ("n_bsdf", C.c_int32), ("bsdf_type", C.c_void_p), ("bsdf_param", C.c_void_p),
+                ("n_lights", C.c_int32), ("light_type", C.c_void_p), ("light_param", C.c_void_p)]
+
+
+class _Bvh2(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("node_bbox", C.c_void_p), ("node_start", C.c_void_p),
+                ("node_range", C.c_void_p), ("node_left", C.c_void_p), ("node_right", C.c_void_p),
+                ("prim_order", C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("camera_samples", C.c_uint64), ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64), ("gpu_seconds", C.c_double),
+                ("extend_seconds", C.c_double), ("connect_seconds", C.c_double), ("shade_seconds", C.c_double),
+                ("kernel_launches", C.c_uint32), ("batches", C.c_uint32)]
+
+    @property
+    def segments(self):
+        return self.extend_rays + self.shadow_rays
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def _scene_struct(arr, keep):
+    s = _Scene()
+    pt = _c(arr["prim_type"], np.int32); pb = _c(arr["prim_bsdf"], np.int32)
+    tp = _c(arr["tri_pos"], np.float64); tn = _c(arr["tri_nrm"], np.float64); sp = _c(arr["sphere"], np.float64)
+    bt = _c(arr["bsdf_type"], np.int32); bp = _c(arr["bsdf_param"], np.float32)
+    lt = _c(arr["light_type"], np.int32); lp = _c(arr["light_param"], np.float64)
+    keep.extend([pt, pb, tp, tn, sp, bt, bp, lt, lp])
+    s.n_prims = len(pt); s.prim_type = pt.ctypes.data; s.prim_bsdf = pb.ctypes.data
+    s.tri_pos = tp.ctypes.data; s.tri_nrm = tn.ctypes.data; s.sphere = sp.ctypes.data
+    s.n_bsdf = len(bt); s.bsdf_type = bt.ctypes.data; s.bsdf_param = bp.ctypes.data
+    s.n_lights = len(lt); s.light_type = lt.ctypes.data; s.light_param = lp.ctypes.data
+    return s
+
+
+def build_bvh2(arr):
+    """Host SAH builder (dsrt_build_bvh2).  Returns the dict of BVH arrays; needs no GPU."""
+    L = load_library()
+    keep = []
+    s = _scene_struct(arr, keep)
+    n = max(s.n_prims, 1)
+    bbox = np.zeros((2 * n, 6)); st = np.zeros(2 * n, np.int32); rg = np.zeros(2 * n, np.int32)
+    le = np.zeros(2 * n, np.int32); ri = np.zeros(2 * n, np.int32); order = np.zeros(n, np.int32)
+    m = C.c_int32(0)
+    rc = L.dsrt_build_bvh2(C.byref(s), *[C.c_void_p(x.ctypes.data) for x in (bbox, st, rg, le, ri, order)], C.byref(m))
+    if rc:
+        raise DsrtError(f"dsrt_build_bvh2 failed ({rc})")
+    m = m.value
+    return {"node_bbox": bbox[:m].copy(), "node_start": st[:m].copy(), "node_range": rg[:m].copy(),
+            "node_left": le[:m].copy(), "node_right": ri[:m].copy(), "prim_order": order[:s.n_prims].copy()}
+
+
+class Core:
+    """One dsrt context = one GPU.  Mirrors the call order of CUDAPathTracer::init (cuda_src/setup.cu:181-201)."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        self.ctx = C.c_void_p()
+        rc = self.L.dsrt_create(int(device), C.byref(self.ctx))
+        if rc:
+            msg = self.L.dsrt_last_error(self.ctx).decode() if self.ctx else "no context"
+            if self.ctx:
+                self.L.dsrt_destroy(self.ctx)
+            self.ctx = None
+            raise DsrtError(f"dsrt_create failed ({rc}): {msg}")
+        self.width = self.height = 0
+        self.ns_aa = 1
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.L.dsrt_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc:
+            raise DsrtError(f"{what} failed ({rc}): {self.L.dsrt_last_error(self.ctx).decode()}")
+
+    def set_scene(self, arr):
+        keep = []
+        s = _scene_struct(arr, keep)
+        self._ck(self.L.dsrt_set_scene(self.ctx, C.byref(s)), "dsrt_set_scene")
+        self.n_prims = s.n_prims
+
+    def set_bvh(self, b):
+        keep = [_c(b["node_bbox"], np.float64), _c(b["node_start"], np.int32), _c(b["node_range"], np.int32),
+                _c(b["node_left"], np.int32), _c(b["node_right"], np.int32), _c(b["prim_order"], np.int32)]
+        s = _Bvh2()
+        s.n_nodes = len(keep[1])
+        (s.node_bbox, s.node_start, s.node_range, s.node_left, s.node_right, s.prim_order) = [k.ctypes.data for k in keep]
+        self._ck(self.L.dsrt_set_bvh(self.ctx, C.byref(s)), "dsrt_set_bvh")
+
+    def set_camera(self, cam):
+        """cam: the 17-double camera vector (pos[3], c2w[9] column-major, W, H, screenDist, hFov, vFov)."""
+        cam = _c(cam, np.float64)
+        pos = cam[0:3].copy(); c2w = cam[3:12].copy()
+        self.width, self.height = int(cam[12]), int(cam[13])
+        self._ck(self.L.dsrt_set_camera(self.ctx, C.c_void_p(pos.ctypes.data), C.c_void_p(c2w.ctypes.data),
+                                        self.width, self.height, C.c_double(float(cam[14]))), "dsrt_set_camera")
+
+    def set_params(self, ns_aa, ns_area_light, max_depth, seed=0):
+        self.ns_aa = int(ns_aa)
+        self._ck(self.L.dsrt_set_params(self.ctx, int(ns_aa), int(ns_area_light), int(max_depth), C.c_uint32(seed)),
+                 "dsrt_set_params")
+
+    def set_option(self, name, value):
+        self._ck(self.L.dsrt_set_option(self.ctx, name.encode(), C.c_int64(int(value))), "dsrt_set_option")
+
+    def build_accel(self):
+        self._ck(self.L.dsrt_build_accel(self.ctx), "dsrt_build_accel")
+
+    def accel_info(self):
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        self._ck(self.L.dsrt_accel_info(self.ctx, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "dsrt_accel_info")
+        return {"wide_nodes": a.value, "node_bytes": b.value, "prim_bytes": c.value, "max_depth": d.value}
+
+    def load(self, arr, camera=None, bvh=None):
+        """set_scene + (host SAH build | given BVH) + build_accel (+ camera)."""
+        self.set_scene(arr)
+        self.set_bvh(bvh if bvh is not None else build_bvh2(arr))
+        self.build_accel()
+        if camera is not None:
+            self.set_camera(camera)
+
+    def render(self, spp_begin=0, spp_count=None, spp_stride=1, out=None):
+        """Host-buffer render (H2D of nothing, D2H of the frame): returns (rgb[H,W,3], Stats)."""
+        if spp_count is None:
+            spp_count = self.ns_aa
+        rgb = out if out is not None else np.zeros((self.height, self.width, 3), np.float32)
+        st = Stats()
+        self._ck(self.L.dsrt_render(self.ctx, int(spp_begin), int(spp_count), int(spp_stride),
+                                    C.c_void_p(rgb.ctypes.data), C.byref(st)), "dsrt_render")
+        return rgb, st
+
+    def render_device(self, d_accum_ptr, spp_begin, spp_count, spp_stride=1, stream=0, collect=False):
+        st = Stats() if collect else None
+        self._ck(self.L.dsrt_render_device(self.ctx, int(spp_begin), int(spp_count), int(spp_stride),
+                                           C.c_void_p(d_accum_ptr), C.c_void_p(stream),
+                                           C.byref(st) if collect else None), "dsrt_render_device")
+        return st
+
+    def resolve_device(self, d_accum_ptr, d_rgb_ptr=0, d_rgba8_ptr=0, stream=0):
+        self._ck(self.L.dsrt_resolve_device(self.ctx, C.c_void_p(d_accum_ptr), C.c_void_p(d_rgb_ptr),
+                                            C.c_void_p(d_rgba8_ptr), C.c_void_p(stream)), "dsrt_resolve_device")
+
+    def collect_stats(self):
+        st = Stats()
+        self._ck(self.L.dsrt_collect_stats(self.ctx, C.byref(st)), "dsrt_collect_stats")
+        return st
+
+    def sync(self):
+        self._ck(self.L.dsrt_sync(self.ctx), "dsrt_sync")
+
+    def primary_hits(self, mode=1):
+        ids = np.zeros((self.height, self.width), np.int32); ts = np.zeros((self.height, self.width))
+        self._ck(self.L.dsrt_primary_hits(self.ctx, int(mode), C.c_void_p(ids.ctypes.data), C.c_void_p(ts.ctypes.data)),
+                 "dsrt_primary_hits")
+        return ids, ts
+
+    def trace_closest(self, o, d, tmax=None):
+        o = _c(o, np.float32).reshape(-1, 3); d = _c(d, np.float32).reshape(-1, 3); n = len(o)
+        tm = _c(tmax, np.float32) if tmax is not None else None
+        ids = np.zeros(n, np.int32); ts = np.zeros(n, np.float32)
+        self._ck(self.L.dsrt_trace_closest(self.ctx, C.c_int64(n), C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data),
+                                           C.c_void_p(tm.ctypes.data) if tm is not None else None,
+                                           C.c_void_p(ids.ctypes.data), C.c_void_p(ts.ctypes.data)), "dsrt_trace_closest")
+        return ids, ts
+
+    def trace_any(self, o, d, tmax=None):
+        o = _c(o, np.float32).reshape(-1, 3); d = _c(d, np.float32).reshape(-1, 3); n = len(o)
+        tm = _c(tmax, np.float32) if tmax is not None else None
+        hit = np.zeros(n, np.int32)
+        self._ck(self.L.dsrt_trace_any(self.ctx, C.c_int64(n), C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data),
+                                       C.c_void_p(tm.ctypes.data) if tm is not None else None,
+                                       C.c_void_p(hit.ctypes.data)), "dsrt_trace_any")
+        return hit
+
+    def tonemap(self, rgb):
+        rgb = _c(rgb, np.float32); n = rgb.size // 3
+        out = np.zeros(n, np.uint32)
+        self._ck(self.L.dsrt_tonemap(self.ctx, C.c_void_p(rgb.ctypes.data), C.c_int64(n), C.c_void_p(out.ctypes.data)),
+                 "dsrt_tonemap")
+        return out.reshape(rgb.shape[:-1])

@@ -1,0 +1,857 @@
+// dsrt_api.cu -- the C ABI (include/dsrt.h) and the sm_100a wavefront kernels behind it.
+//
+// Wavefront per batch of camera samples:
+//   k_generate : Camera::generate_ray + pixel jitter                       (pathtracer.cpp:571-577, camera.cpp:113-129)
+//   k_extend   : closest hit, persistent warps + dynamic ray fetch         (bvh.cpp:343-363)
+//   k_shade    : emission, light sampling -> shadow queue, BSDF::sample_f,
+//                Russian roulette -> next extend queue                     (pathtracer.cpp:435-552)
+//   k_connect  : any hit for shadow rays, accumulate unoccluded light      (pathtracer.cpp:501-519, bvh.cpp:331-341)
+//   k_resolve  : 1/ns_aa scale + HDRImageBuffer::toColor                   (pathtracer.cpp:579, image.h:174-189)
+// Queues are appended with warp-aggregated atomics; all queue sizes live in device memory, so a whole frame
+// is enqueued without a host round trip.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dsrt.h"
+#include "layout.h"
+#include "rng.cuh"
+#include "shade.cuh"
+#include "traverse.cuh"
+#include "wide_bvh.h"
+
+namespace dsrt {
+
+constexpr int kTraceThreads = 128;        // 4 warps per CTA
+constexpr int kMaxDepthSlots = 64;        // queue-size slots per batch (depth 0..63)
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------ device state
+struct PathState {
+  float4* ray_o;     // o.xyz, tmax
+  float4* ray_d;     // d.xyz, src_slot (int bits)
+  float4* hit;       // t, u, v, slot (int bits)
+  float4* thr;       // throughput rgb, (depth | includeLe << 8) (int bits)
+  uint32_t* pixel;   // y*W+x
+  uint32_t* sample;  // camera-sample index
+};
+struct ShadowQueue { float4* a; float4* b; float4* c; };   // (o, tmax) (d, src_slot) (contribution rgb, pixel)
+
+struct RenderParams {
+  Camera cam;
+  uint32_t seed;
+  int max_depth;
+  int spp_begin, spp_stride;
+  int batch_first_sample;   // index (within this call) of the first sample of the batch
+  int n_pix_padded, blocks_x;
+  int skip_null_shadow;
+};
+
+struct Counters {             // one block per batch, zeroed with a single memset
+  uint32_t q_count[kMaxDepthSlots];       // extend-queue size per depth
+  uint32_t s_count[kMaxDepthSlots];       // shadow-queue size per depth
+  uint32_t work_extend[kMaxDepthSlots];   // persistent-kernel fetch counters
+  uint32_t work_connect[kMaxDepthSlots];
+};
+struct Totals { unsigned long long camera, extend, shadow, nodes, prims; };
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void k_generate(PathState ps, RenderParams rp, int n_paths, uint32_t* queue, uint32_t* q_count, int aligned) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_paths) return;
+  if (aligned && i == 0) *q_count = (uint32_t)n_paths;   // identity queue
+  const int s_local = i / rp.n_pix_padded, rank = i - s_local * rp.n_pix_padded;
+  const int blk = rank >> 5, lane = rank & 31;
+  const int bx = blk % rp.blocks_x, by = blk / rp.blocks_x;
+  const int x = bx * 8 + (lane & 7), y = by * 4 + (lane >> 3);
+  const bool valid = x < rp.cam.width && y < rp.cam.height;
+  if (valid) {
+    const uint32_t pix = (uint32_t)(y * rp.cam.width + x);
+    const uint32_t smp = (uint32_t)(rp.spp_begin + (rp.batch_first_sample + s_local) * rp.spp_stride);
+    const float4 u = rng_block(rp.seed, pix, smp, 0u, kBlockCamera);
+    V3 o, d;
+    generate_ray(rp.cam, ((float)x + u.x) / (float)rp.cam.width, ((float)y + u.y) / (float)rp.cam.height, &o, &d);
+    ps.ray_o[i] = make_float4(o.x, o.y, o.z, kInfF);
+    ps.ray_d[i] = make_float4(d.x, d.y, d.z, __int_as_float(-1));
+    ps.thr[i] = make_float4(1.f, 1.f, 1.f, __int_as_float(0 | (1 << 8)));
+    ps.pixel[i] = pix;
+    ps.sample[i] = smp;
+  }
+  if (!aligned) {   // ragged frame: compact the valid paths into the depth-0 queue
+    const unsigned m = __ballot_sync(__activemask(), valid);
+    if (valid) {
+      const int lane_id = threadIdx.x & 31;
+      const int leader = __ffs(m) - 1;
+      uint32_t base = 0;
+      if (lane_id == leader) base = atomicAdd(q_count, (uint32_t)__popc(m));
+      base = __shfl_sync(m, base, leader);
+      queue[base + __popc(m & ((1u << lane_id) - 1u))] = (uint32_t)i;
+    }
+  }
+}
+
+// pixel-centre camera rays for dsrt_primary_hits(mode 0)
+__global__ void k_generate_centres(PathState ps, RenderParams rp, int n_paths) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_paths) return;
+  const int x = i % rp.cam.width, y = i / rp.cam.width;
+  V3 o, d;
+  generate_ray(rp.cam, ((float)x + 0.5f) / (float)rp.cam.width, ((float)y + 0.5f) / (float)rp.cam.height, &o, &d);
+  ps.ray_o[i] = make_float4(o.x, o.y, o.z, kInfF);
+  ps.ray_d[i] = make_float4(d.x, d.y, d.z, __int_as_float(-1));
+}
+
+// Persistent warps; a lane whose ray has finished waits until at most kRefill lanes of its warp are still
+// busy, then the warp fetches new rays for all idle lanes with one aggregated atomic (ballot + popc + shfl).
+constexpr int kRefillBusyLanes = 20;
+
+template <bool ANY, bool COUNT>
+__global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+                                                         const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
+                                                         uint32_t* work, float4* hit_out, const float4* __restrict__ contrib,
+                                                         float* accum, Totals* totals) {
+  extern __shared__ uint2 smem_stack[];
+  uint2* stack = smem_stack + threadIdx.x;
+  const int stride = blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const uint32_t n = *n_ptr;
+  TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
+
+  // per-lane traversal state (kept across refills)
+  bool busy = false, exhausted = false;
+  uint32_t item = 0;
+  TraceRay ray; NodeFrame fr; WatertightRay wr;
+  float tbest = 0.f; TraceHit hit; int sp = 0;
+  uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
+  hit.slot = -1; hit.t = 0.f; hit.u = 0.f; hit.v = 0.f;
+
+  while (true) {
+    // ---- refill idle lanes
+    const unsigned idle = __ballot_sync(kFull, !busy);
+    if (idle && !exhausted) {
+      uint32_t base = 0;
+      const int leader = __ffs(idle) - 1;
+      if (lane == leader) base = atomicAdd(work, (uint32_t)__popc(idle));
+      base = __shfl_sync(kFull, base, leader);
+      if (!busy) {
+        const uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
+        if (k < n) {
+          item = queue ? queue[k] : k;
+          const float4 o = ray_o[item], d = ray_d[item];
+          ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.tmax = o.w;
+          ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.src_slot = __float_as_int(d.w);
+          fr = make_frame(ray); wr = make_watertight(ray);
+          tbest = ray.tmax; hit.slot = -1; hit.t = ray.tmax; hit.u = 0.f; hit.v = 0.f;
+          sp = 0; ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
+          busy = true;
+        }
+      }
+      if (base + (uint32_t)__popc(idle) >= n) exhausted = true;
+    }
+    if (!__any_sync(kFull, busy)) break;
+
+    // ---- traverse until the warp is due for a refill
+    while (true) {
+      if (busy) {
+        bool done = false;
+        if (ngroup.y > 0x00ffffffu) {
+          const uint32_t bit = 31u - (uint32_t)__clz(ngroup.y);
+          ngroup.y &= ~(1u << bit);
+          if (ngroup.y > 0x00ffffffu) { stack[sp * stride] = ngroup; sp++; }
+          const uint32_t slot = (bit - 24u) ^ fr.octinv;
+          const uint32_t rel = __popc(ngroup.y & 0xffu & ((1u << slot) - 1u));
+          const uint4* np = A.nodes + (size_t)(ngroup.x + rel) * 5;
+          const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+          if (COUNT) cnt.nodes++;
+          const uint32_t m = test_children<false>(ray, fr, n0, n1, n2, n3, n4, tbest, 0.f);
+          ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
+          tgroup = make_uint2(n1.y, m & 0x00ffffffu);
+        } else {
+          tgroup = make_uint2(0u, 0u);
+        }
+        while (tgroup.y) {
+          const uint32_t k = 31u - (uint32_t)__clz(tgroup.y);
+          tgroup.y &= ~(1u << k);
+          const int slot = (int)(tgroup.x + k);
+          if (COUNT) cnt.prims++;
+          const float4* pp = A.prims + (size_t)slot * 3;
+          const float4 a = __ldg(pp), b = __ldg(pp + 1);
+          float t, u = 0.f, v = 0.f; bool h;
+          if (b.w != 0.0f) {
+            const float4 c = __ldg(pp + 2);
+            h = (slot != ray.src_slot) && hit_triangle(ray, wr, a, b, c, tbest, t, u, v);
+          } else {
+            h = hit_sphere(ray, a, b, slot == ray.src_slot, ANY, tbest, t);
+          }
+          if (h) {
+            tbest = t; hit.slot = slot; hit.t = t; hit.u = u; hit.v = v;
+            if (ANY) { done = true; break; }
+          }
+        }
+        if (!done && ngroup.y <= 0x00ffffffu) {
+          if (sp == 0) done = true;
+          else { sp--; ngroup = stack[sp * stride]; }
+        }
+        if (done) {
+          busy = false;
+          if (ANY) {
+            if (hit_out) hit_out[item] = make_float4(hit.t, 0.f, 0.f, __int_as_float(hit.slot));
+            if (accum && hit.slot < 0) {       // unoccluded: add this light sample's contribution
+              const float4 c = contrib[item];
+              float* px = accum + 3 * (size_t)__float_as_uint(c.w);
+              if (c.x != 0.f) atomicAdd(px, c.x);
+              if (c.y != 0.f) atomicAdd(px + 1, c.y);
+              if (c.z != 0.f) atomicAdd(px + 2, c.z);
+            }
+          } else {
+            hit_out[item] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.slot));
+          }
+        }
+      }
+      const int nbusy = __popc(__ballot_sync(kFull, busy));
+      if (nbusy == 0 || (!exhausted && nbusy <= kRefillBusyLanes)) break;
+    }
+  }
+  if (COUNT) {
+    unsigned long long a = cnt.nodes, b = cnt.prims;
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(kFull, a, o); b += __shfl_xor_sync(kFull, b, o); }
+    if (lane == 0) { atomicAdd(&totals->nodes, a); atomicAdd(&totals->prims, b); }
+  }
+}
+
+// parity kernel: one thread per pixel, double-precision rays supplied by the host (bit-identical to the
+// reference's Camera::generate_ray), production traversal with conservative slabs + fp64 leaf tests
+__global__ void __launch_bounds__(kTraceThreads) k_primary_parity(Accel A, const double* __restrict__ rays, int n, int32_t* slot_out,
+                                                                  double* t_out) {
+  extern __shared__ uint2 smem_stack[];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Ray64 r64; r64.ox = rays[6 * i]; r64.oy = rays[6 * i + 1]; r64.oz = rays[6 * i + 2];
+  r64.dx = rays[6 * i + 3]; r64.dy = rays[6 * i + 4]; r64.dz = rays[6 * i + 5];
+  TraceRay r; r.ox = (float)r64.ox; r.oy = (float)r64.oy; r.oz = (float)r64.oz;
+  r.dx = (float)r64.dx; r.dy = (float)r64.dy; r.dz = (float)r64.dz; r.tmax = kInfF; r.src_slot = -1;
+  TraceHit hit; double t64 = 0;
+  trace_ray<false, true, false>(A, r, &r64, smem_stack + threadIdx.x, blockDim.x, hit, &t64, nullptr);
+  slot_out[i] = hit.slot;
+  t_out[i] = hit.slot >= 0 ? t64 : (double)kInfF;
+}
+
+__device__ __forceinline__ void add_rgb(float* accum, uint32_t pix, V3 c) {
+  float* px = accum + 3 * (size_t)pix;
+  if (c.x != 0.f) atomicAdd(px, c.x);
+  if (c.y != 0.f) atomicAdd(px + 1, c.y);
+  if (c.z != 0.f) atomicAdd(px + 2, c.z);
+}
+
+// One thread per queued path: PathTracer::trace_ray after the closest-hit query (shade_path, shade.cuh)
+struct QueueSink {
+  ShadowQueue sq; uint32_t base; int nh, rank;
+  __device__ __forceinline__ void shadow(int j, float4 a, float4 b, float4 c) {
+    const uint32_t e = base + (uint32_t)(j * nh + rank);     // sample-major within the warp's block
+    sq.a[e] = a; sq.b[e] = b; sq.c[e] = c;
+  }
+};
+
+__global__ void __launch_bounds__(128) k_shade(PathState ps, const float4* __restrict__ prims, SceneDev sc, RenderParams rp,
+                                               const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
+                                               uint32_t* next_queue, uint32_t* next_count, ShadowQueue sq, uint32_t* s_count,
+                                               float* accum, int depth) {
+  const uint32_t n = *n_ptr;
+  const int lane = threadIdx.x & 31;
+  for (uint32_t kb = blockIdx.x * blockDim.x; kb < n; kb += gridDim.x * blockDim.x) {
+    const uint32_t k = kb + threadIdx.x;
+    const bool live = k < n;
+    uint32_t p = 0;
+    PathIn in; in.hit = make_float4(0, 0, 0, __int_as_float(-1));
+    if (live) { p = queue ? queue[k] : k; in.hit = ps.hit[p]; }
+    const bool hitp = live && __float_as_int(in.hit.w) >= 0;     // miss: no environment light from the CLI
+    const unsigned hm = __ballot_sync(kFull, hitp);
+    QueueSink sink; sink.sq = sq; sink.base = 0; sink.nh = __popc(hm); sink.rank = __popc(hm & ((1u << lane) - 1u));
+    if (hm && sc.n_light_samples > 0) {
+      const int leader = __ffs(hm) - 1;
+      if (lane == leader) sink.base = atomicAdd(s_count, (uint32_t)(sink.nh * sc.n_light_samples));
+      sink.base = __shfl_sync(kFull, sink.base, leader);
+    }
+    PathOut out; out.cont = false;
+    if (hitp) {
+      in.ray_o = ps.ray_o[p]; in.ray_d = ps.ray_d[p]; in.thr = ps.thr[p]; in.pix = ps.pixel[p]; in.smp = ps.sample[p];
+      shade_path(in, prims, sc, rp.seed, rp.max_depth, depth, out, sink);
+      if (out.has_emission) add_rgb(accum, in.pix, out.emission);
+    }
+    const unsigned cm = __ballot_sync(kFull, out.cont);
+    if (cm) {
+      uint32_t base = 0;
+      const int leader = __ffs(cm) - 1;
+      if (lane == leader) base = atomicAdd(next_count, (uint32_t)__popc(cm));
+      base = __shfl_sync(kFull, base, leader);
+      if (out.cont) {
+        next_queue[base + __popc(cm & ((1u << lane) - 1u))] = p;
+        ps.ray_o[p] = out.new_o; ps.ray_d[p] = out.new_d; ps.thr[p] = out.new_thr;
+      }
+    }
+  }
+}
+
+__global__ void k_tally(const Counters* c, Totals* t, uint32_t camera) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long e = 0, s = 0;
+    for (int d = 0; d < kMaxDepthSlots; d++) { e += c->q_count[d]; s += c->s_count[d]; }
+    t->camera += camera; t->extend += e; t->shadow += s;
+  }
+}
+__global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
+
+// sampleBuffer = accum / ns_aa (pathtracer.cpp:579); optional toColor (image.h:174-189, 49-58)
+__global__ void k_resolve(const float* __restrict__ accum, float* rgb, uint32_t* rgba8, int n_pix, float inv_spp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pix) return;
+  const float r = accum[3 * i] * inv_spp, g = accum[3 * i + 1] * inv_spp, b = accum[3 * i + 2] * inv_spp;
+  if (rgb) { rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b; }
+  if (rgba8) {
+    const float exposure = sqrtf(2.0f), og = 1.0f / 2.2f;
+    const float cr = fminf(1.0f, powf(r * exposure, og)), cg = fminf(1.0f, powf(g * exposure, og)), cb = fminf(1.0f, powf(b * exposure, og));
+    rgba8[i] = (uint32_t)(cr * 255.f) | ((uint32_t)(cg * 255.f) << 8) | ((uint32_t)(cb * 255.f) << 16) | (255u << 24);
+  }
+}
+
+}  // namespace dsrt
+
+// ================================================================================================ host side
+using namespace dsrt;
+
+struct dsrt_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+  // host copies of the inputs
+  bool have_scene = false, have_bvh = false, have_cam = false, have_accel = false;
+  int n_prims = 0;
+  std::vector<int32_t> prim_type, prim_bsdf;
+  std::vector<double> tri_pos, tri_nrm, sphere;
+  std::vector<Bsdf> bsdfs;
+  std::vector<int32_t> light_type;
+  std::vector<double> light_param;
+  std::vector<double> node_bbox;
+  std::vector<int32_t> node_start, node_range, node_left, node_right, prim_order;
+  Camera cam{};
+  int ns_aa = 1, ns_area_light = 4, max_depth = 1;
+  uint32_t seed = 0;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0;
+  // accel
+  WideBVH wide;
+  double scene_diag = 1.0;
+  void* d_nodes = nullptr; void* d_prims = nullptr; void* d_shade = nullptr; void* d_prims64 = nullptr;
+  void* d_bsdf = nullptr; void* d_lights = nullptr;
+  int n_lights = 0, n_light_samples = 0;
+  // wavefront buffers
+  size_t cap_paths = 0, cap_shadow = 0;
+  PathState ps{}; ShadowQueue sq{}; float4* s_hit = nullptr;
+  uint32_t* queue[2] = {nullptr, nullptr};
+  Counters* d_counters = nullptr; int n_counter_blocks = 0;
+  Totals* d_totals = nullptr;
+  float* d_accum_own = nullptr; size_t accum_pixels = 0;
+  // timing
+  std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  struct Span { size_t e0, e1; int kind; };
+  std::vector<Span> spans;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  uint32_t launches = 0, batches = 0;
+};
+
+namespace {
+
+int fail(dsrt_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, DSRT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+template <typename T> int dev_alloc(dsrt_ctx* ctx, T** p, size_t n) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (n == 0) n = 1;
+  CK(cudaMalloc((void**)p, n * sizeof(T)));
+  return DSRT_OK;
+}
+void dev_free(void* p) { if (p) cudaFree(p); }
+
+cudaEvent_t next_event(dsrt_ctx* ctx) {
+  if (ctx->ev_used == ctx->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+  return ctx->ev_pool[ctx->ev_used++];
+}
+
+Accel make_accel(const dsrt_ctx* ctx, bool parity) {
+  Accel A;
+  A.nodes = (const uint4*)ctx->d_nodes; A.prims = (const float4*)ctx->d_prims;
+  A.prims64 = (const double*)ctx->d_prims64;
+  A.pad = parity ? (float)(1e-5 * ctx->scene_diag) : 0.f;
+  return A;
+}
+
+int trace_grid(const dsrt_ctx* ctx) { return ctx->sm_count * 8; }   // persistent: 8 CTAs of 4 warps per SM
+size_t stack_bytes() { return (size_t)kStackEntries * kTraceThreads * sizeof(uint2); }
+
+int ensure_wavefront(dsrt_ctx* ctx, size_t paths, size_t shadow) {
+  if (paths > ctx->cap_paths) {
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->ps.ray_o, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->ps.ray_d, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->ps.hit, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->ps.thr, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->ps.pixel, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->ps.sample, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->queue[0], paths))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->queue[1], paths))) return rc;
+    ctx->cap_paths = paths;
+  }
+  if (shadow > ctx->cap_shadow) {
+    int rc;
+    if ((rc = dev_alloc(ctx, &ctx->sq.a, shadow))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->sq.b, shadow))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->sq.c, shadow))) return rc;
+    ctx->cap_shadow = shadow;
+  }
+  return DSRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dsrt_version(void) { return "dsrt 0.1 (sm_100a wavefront path tracer)"; }
+
+int dsrt_create(int device, dsrt_ctx** out) {
+  if (!out) return DSRT_ERR_INVALID;
+  *out = nullptr;
+  dsrt_ctx* ctx = new dsrt_ctx();
+  ctx->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) {
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  }
+  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_totals, sizeof(Totals));
+  if (e == cudaSuccess) { cudaEventCreate(&ctx->ev_begin); cudaEventCreate(&ctx->ev_end); }
+  if (e != cudaSuccess) {
+    // the context is still returned so the caller can read the message; every later call fails loudly
+    ctx->err = std::string("dsrt_create: ") + cudaGetErrorString(e);
+    *out = ctx;
+    return DSRT_ERR_CUDA;
+  }
+  *out = ctx;
+  return DSRT_OK;
+}
+
+int dsrt_destroy(dsrt_ctx* ctx) {
+  if (!ctx) return DSRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx->d_nodes); dev_free(ctx->d_prims); dev_free(ctx->d_shade); dev_free(ctx->d_prims64);
+  dev_free(ctx->d_bsdf); dev_free(ctx->d_lights);
+  dev_free(ctx->ps.ray_o); dev_free(ctx->ps.ray_d); dev_free(ctx->ps.hit); dev_free(ctx->ps.thr);
+  dev_free(ctx->ps.pixel); dev_free(ctx->ps.sample); dev_free(ctx->queue[0]); dev_free(ctx->queue[1]);
+  dev_free(ctx->sq.a); dev_free(ctx->sq.b); dev_free(ctx->sq.c); dev_free(ctx->s_hit);
+  dev_free(ctx->d_counters); dev_free(ctx->d_totals); dev_free(ctx->d_accum_own);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+  if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return DSRT_OK;
+}
+
+const char* dsrt_last_error(const dsrt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int dsrt_set_scene(dsrt_ctx* ctx, const dsrt_scene* s) {
+  if (!ctx || !s) return DSRT_ERR_INVALID;
+  if (s->n_prims < 0 || s->n_bsdf < 0 || s->n_lights < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: negative count");
+  if (s->n_prims > 0 && (!s->prim_type || !s->prim_bsdf || !s->tri_pos || !s->tri_nrm || !s->sphere))
+    return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: null primitive array");
+  const size_t n = (size_t)s->n_prims;
+  for (size_t i = 0; i < n; i++) {
+    if (s->prim_bsdf[i] < 0 || s->prim_bsdf[i] >= s->n_bsdf) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: prim_bsdf out of range");
+    if (s->prim_type[i] != 0 && s->prim_type[i] != 1) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: prim_type must be 0 or 1");
+  }
+  ctx->n_prims = s->n_prims;
+  ctx->prim_type.assign(s->prim_type, s->prim_type + n);
+  ctx->prim_bsdf.assign(s->prim_bsdf, s->prim_bsdf + n);
+  ctx->tri_pos.assign(s->tri_pos, s->tri_pos + 9 * n);
+  ctx->tri_nrm.assign(s->tri_nrm, s->tri_nrm + 9 * n);
+  ctx->sphere.assign(s->sphere, s->sphere + 4 * n);
+  ctx->bsdfs.resize(s->n_bsdf);
+  for (int i = 0; i < s->n_bsdf; i++) {
+    Bsdf& b = ctx->bsdfs[i]; const float* q = s->bsdf_param + 8 * i;
+    for (int k = 0; k < 3; k++) { b.a[k] = q[k]; b.b[k] = q[3 + k]; }
+    b.ior = q[6]; b.type = s->bsdf_type[i];
+    if (b.type < 0 || b.type > 4) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: unknown BSDF type");
+  }
+  ctx->light_type.assign(s->light_type, s->light_type + s->n_lights);
+  ctx->light_param.assign(s->light_param, s->light_param + 28 * (size_t)s->n_lights);
+  for (int i = 0; i < s->n_lights; i++)
+    if (s->light_type[i] < 0 || s->light_type[i] > 3) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: unsupported light type (spot/sphere/mesh lights are empty stubs in the reference, light.cpp:61-115)");
+  ctx->have_scene = true; ctx->have_bvh = false; ctx->have_accel = false;
+  return DSRT_OK;
+}
+
+int dsrt_set_bvh(dsrt_ctx* ctx, const dsrt_bvh2* b) {
+  if (!ctx || !b) return DSRT_ERR_INVALID;
+  if (!ctx->have_scene) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_bvh: call dsrt_set_scene first");
+  if (b->n_nodes < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_bvh: negative node count");
+  const size_t m = (size_t)b->n_nodes;
+  ctx->node_bbox.assign(b->node_bbox, b->node_bbox + 6 * m);
+  ctx->node_start.assign(b->node_start, b->node_start + m);
+  ctx->node_range.assign(b->node_range, b->node_range + m);
+  ctx->node_left.assign(b->node_left, b->node_left + m);
+  ctx->node_right.assign(b->node_right, b->node_right + m);
+  ctx->prim_order.assign(b->prim_order, b->prim_order + ctx->n_prims);
+  std::vector<char> seen(ctx->n_prims, 0);
+  for (int i = 0; i < ctx->n_prims; i++) {
+    int p = ctx->prim_order[i];
+    if (p < 0 || p >= ctx->n_prims || seen[p]) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_bvh: prim_order is not a permutation");
+    seen[p] = 1;
+  }
+  ctx->have_bvh = true; ctx->have_accel = false;
+  return DSRT_OK;
+}
+
+int dsrt_set_camera(dsrt_ctx* ctx, const double* pos, const double* c2w, int32_t width, int32_t height, double screen_dist) {
+  if (!ctx || !pos || !c2w) return DSRT_ERR_INVALID;
+  if (width <= 0 || height <= 0 || !(screen_dist > 0)) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_camera: bad frame size / screenDist");
+  Camera& c = ctx->cam;
+  for (int k = 0; k < 3; k++) { c.pos[k] = (float)pos[k]; c.pos64[k] = pos[k]; }
+  for (int k = 0; k < 9; k++) { c.c2w[k] = (float)c2w[k]; c.c2w64[k] = c2w[k]; }
+  c.width = width; c.height = height;
+  c.W64 = width; c.H64 = height; c.dist64 = screen_dist;
+  c.w_over_dist = (float)(width / screen_dist); c.h_over_dist = (float)(height / screen_dist);
+  ctx->have_cam = true;
+  return DSRT_OK;
+}
+
+int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t max_ray_depth, uint32_t seed) {
+  if (!ctx) return DSRT_ERR_INVALID;
+  if (ns_aa < 1 || ns_area_light < 1 || max_ray_depth < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_params: ns_aa/ns_area_light must be >= 1, max_ray_depth >= 0");
+  if (max_ray_depth + 1 >= kMaxDepthSlots) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_set_params: max_ray_depth too large");
+  if (ns_area_light != ctx->ns_area_light) ctx->have_accel = false;   // light sample layout is baked at build_accel
+  ctx->ns_aa = ns_aa; ctx->ns_area_light = ns_area_light; ctx->max_depth = max_ray_depth; ctx->seed = seed;
+  return DSRT_OK;
+}
+
+int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
+  if (!ctx || !name) return DSRT_ERR_INVALID;
+  std::string n(name);
+  if (n == "count_traversal") ctx->opt_count = value;
+  else if (n == "batch_spp") ctx->opt_batch_spp = value;
+  else if (n == "stage_timing") ctx->opt_stage_timing = value;
+  else if (n == "skip_null_shadow") ctx->opt_skip_null = value;
+  else return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_option: unknown option " + n);
+  return DSRT_OK;
+}
+
+int dsrt_build_accel(dsrt_ctx* ctx) {
+  if (!ctx) return DSRT_ERR_INVALID;
+  if (!ctx->have_scene || !ctx->have_bvh) return fail(ctx, DSRT_ERR_INVALID, "dsrt_build_accel: scene and BVH must be set first");
+  CK(cudaSetDevice(ctx->device));
+  dsrt_scene s{}; s.n_prims = ctx->n_prims; s.prim_type = ctx->prim_type.data(); s.prim_bsdf = ctx->prim_bsdf.data();
+  s.tri_pos = ctx->tri_pos.data(); s.tri_nrm = ctx->tri_nrm.data(); s.sphere = ctx->sphere.data();
+  std::vector<Box3> pbox; primitive_boxes(&s, pbox);
+  dsrt_bvh2 b{}; b.n_nodes = (int)ctx->node_start.size(); b.node_bbox = ctx->node_bbox.data(); b.node_start = ctx->node_start.data();
+  b.node_range = ctx->node_range.data(); b.node_left = ctx->node_left.data(); b.node_right = ctx->node_right.data();
+  b.prim_order = ctx->prim_order.data();
+  std::string err;
+  int rc = build_wide_bvh(b, pbox, ctx->n_prims, ctx->wide, err);
+  if (rc) return fail(ctx, rc, err);
+  if (ctx->wide.max_depth > kStackEntries) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel: wide BVH deeper than the traversal stack");
+  Box3 all; all.reset(); for (const Box3& p : pbox) all.grow(p);
+  double dg = 0; for (int k = 0; k < 3; k++) { double e = ctx->n_prims ? all.hi[k] - all.lo[k] : 0; double m = ctx->n_prims ? std::fmax(std::fabs(all.lo[k]), std::fabs(all.hi[k])) : 0; dg += (e + m) * (e + m); }
+  ctx->scene_diag = std::sqrt(dg) + 1.0;
+
+  const size_t n = ctx->wide.slot_prim.size();
+  std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
+  flatten_records(s, ctx->wide, recs, shd, r64);
+  ctx->n_light_samples = flatten_lights((int)ctx->light_type.size(), ctx->light_type.data(), ctx->light_param.data(), ctx->ns_area_light, lights);
+  ctx->n_lights = (int)lights.size();
+
+  dev_free(ctx->d_nodes); dev_free(ctx->d_prims); dev_free(ctx->d_shade); dev_free(ctx->d_prims64); dev_free(ctx->d_bsdf); dev_free(ctx->d_lights);
+  ctx->d_nodes = ctx->d_prims = ctx->d_shade = ctx->d_prims64 = ctx->d_bsdf = ctx->d_lights = nullptr;
+  auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
+    if (e == cudaSuccess && bytes) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    return e;
+  };
+  CK(up(&ctx->d_nodes, ctx->wide.nodes.data(), ctx->wide.nodes.size() * sizeof(WideNode)));
+  CK(up(&ctx->d_prims, recs.data(), n * sizeof(PrimRecord)));
+  CK(up(&ctx->d_shade, shd.data(), n * sizeof(ShadeRecord)));
+  CK(up(&ctx->d_prims64, r64.data(), n * sizeof(PrimRecord64)));
+  CK(up(&ctx->d_bsdf, ctx->bsdfs.data(), ctx->bsdfs.size() * sizeof(Bsdf)));
+  CK(up(&ctx->d_lights, lights.data(), lights.size() * sizeof(Light)));
+  ctx->have_accel = true;
+  return DSRT_OK;
+}
+
+int dsrt_accel_info(const dsrt_ctx* ctx, int64_t* n_wide_nodes, int64_t* node_bytes, int64_t* prim_bytes, int32_t* max_depth) {
+  if (!ctx || !ctx->have_accel) return DSRT_ERR_INVALID;
+  if (n_wide_nodes) *n_wide_nodes = (int64_t)ctx->wide.nodes.size();
+  if (node_bytes) *node_bytes = (int64_t)(ctx->wide.nodes.size() * sizeof(WideNode));
+  if (prim_bytes) *prim_bytes = (int64_t)(ctx->wide.slot_prim.size() * sizeof(PrimRecord));
+  if (max_depth) *max_depth = ctx->wide.max_depth;
+  return DSRT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ rendering
+static int render_impl(dsrt_ctx* ctx, int spp_begin, int spp_count, int spp_stride, float* d_accum, cudaStream_t st) {
+  if (!ctx->have_accel || !ctx->have_cam) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: call dsrt_build_accel and dsrt_set_camera first");
+  if (spp_count < 0 || spp_stride < 1 || spp_begin < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: bad sample range");
+  CK(cudaSetDevice(ctx->device));
+  const int W = ctx->cam.width, H = ctx->cam.height;
+  const int blocks_x = (W + 7) / 8, blocks_y = (H + 3) / 4;
+  const int npp = blocks_x * blocks_y * 32;
+  const int aligned = (W % 8 == 0 && H % 4 == 0) ? 1 : 0;
+  int batch_spp = (int)ctx->opt_batch_spp;
+  if (batch_spp <= 0) batch_spp = std::max(1, (int)((4u << 20) / (unsigned)npp));   // ~4M paths per batch
+  batch_spp = std::min(batch_spp, std::max(1, spp_count));
+  const size_t P = (size_t)npp * batch_spp;
+  const int nls = ctx->n_light_samples;
+  int rc = ensure_wavefront(ctx, P, P * (size_t)std::max(nls, 1));
+  if (rc) return rc;
+  const int n_batches = (spp_count + batch_spp - 1) / batch_spp;
+  if (n_batches > ctx->n_counter_blocks) {
+    if ((rc = dev_alloc(ctx, &ctx->d_counters, (size_t)n_batches))) return rc;
+    ctx->n_counter_blocks = n_batches;
+  }
+  CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters) * (size_t)n_batches, st));
+  CK(cudaMemsetAsync(ctx->d_totals, 0, sizeof(Totals), st));
+  ctx->ev_used = 0; ctx->spans.clear(); ctx->launches = 0; ctx->batches = (uint32_t)n_batches;
+  CK(cudaEventRecord(ctx->ev_begin, st));
+
+  SceneDev sc; sc.bsdf = (const Bsdf*)ctx->d_bsdf; sc.lights = (const Light*)ctx->d_lights; sc.shade = (const float4*)ctx->d_shade;
+  sc.n_lights = ctx->n_lights; sc.n_light_samples = nls;
+  RenderParams rp; rp.cam = ctx->cam; rp.seed = ctx->seed; rp.max_depth = ctx->max_depth; rp.spp_begin = spp_begin; rp.spp_stride = spp_stride;
+  rp.n_pix_padded = npp; rp.blocks_x = blocks_x; rp.skip_null_shadow = (int)ctx->opt_skip_null; rp.batch_first_sample = 0;
+  const Accel A = make_accel(ctx, false);
+  const bool count = ctx->opt_count != 0, timing = ctx->opt_stage_timing != 0;
+  const int tgrid = trace_grid(ctx);
+  const size_t sbytes = stack_bytes();
+
+  auto span_begin = [&](int kind) { if (timing) { dsrt_ctx::Span s; s.kind = kind; s.e0 = ctx->ev_used; cudaEventRecord(next_event(ctx), st); s.e1 = 0; ctx->spans.push_back(s); } };
+  auto span_end = [&]() { if (timing) { ctx->spans.back().e1 = ctx->ev_used; cudaEventRecord(next_event(ctx), st); } };
+
+  for (int bi = 0; bi < n_batches; bi++) {
+    const int s0 = bi * batch_spp, ns = std::min(batch_spp, spp_count - s0);
+    const int n_paths = npp * ns;
+    Counters* C = ctx->d_counters + bi;
+    rp.batch_first_sample = s0;
+    span_begin(2);
+    k_generate<<<(n_paths + 255) / 256, 256, 0, st>>>(ctx->ps, rp, n_paths, ctx->queue[0], &C->q_count[0], aligned);
+    span_end();
+    ctx->launches++;
+    int cur = 0;
+    for (int d = 0; d <= ctx->max_depth; d++) {
+      const uint32_t* q = (d == 0 && aligned) ? nullptr : ctx->queue[cur];
+      span_begin(0);
+      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ctx->ps.ray_o, ctx->ps.ray_d, q, &C->q_count[d], &C->work_extend[d], ctx->ps.hit, nullptr, nullptr, ctx->d_totals);
+      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ctx->ps.ray_o, ctx->ps.ray_d, q, &C->q_count[d], &C->work_extend[d], ctx->ps.hit, nullptr, nullptr, ctx->d_totals);
+      span_end();
+      // upper bound of this depth's queue: depth 0 = all paths; deeper levels can only shrink
+      const int bound = d == 0 ? n_paths : std::min(n_paths, ctx->sm_count * 16 * 128);
+      span_begin(2);
+      k_shade<<<(bound + 127) / 128, 128, 0, st>>>(ctx->ps, (const float4*)ctx->d_prims, sc, rp, q, &C->q_count[d], ctx->queue[cur ^ 1], &C->q_count[d + 1],
+                                                   ctx->sq, &C->s_count[d], d_accum, d);
+      span_end();
+      if (nls > 0) {
+        span_begin(1);
+        if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ctx->sq.a, ctx->sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, ctx->sq.c, d_accum, ctx->d_totals);
+        else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ctx->sq.a, ctx->sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, ctx->sq.c, d_accum, ctx->d_totals);
+        span_end();
+        ctx->launches++;
+      }
+      ctx->launches += 2;
+      cur ^= 1;
+    }
+    k_tally<<<1, 32, 0, st>>>(C, ctx->d_totals, (uint32_t)((size_t)W * H * ns));
+    ctx->launches++;
+  }
+  CK(cudaEventRecord(ctx->ev_end, st));
+  CK(cudaGetLastError());
+  return DSRT_OK;
+}
+
+int dsrt_collect_stats(dsrt_ctx* ctx, dsrt_stats* stats) {
+  if (!ctx) return DSRT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->ev_end));
+  if (!stats) return DSRT_OK;
+  std::memset(stats, 0, sizeof(*stats));
+  Totals t;
+  CK(cudaMemcpy(&t, ctx->d_totals, sizeof(t), cudaMemcpyDeviceToHost));
+  stats->camera_samples = t.camera; stats->extend_rays = t.extend; stats->shadow_rays = t.shadow;
+  stats->nodes_visited = t.nodes; stats->prims_tested = t.prims;
+  float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+  stats->gpu_seconds = ms * 1e-3;
+  for (const auto& s : ctx->spans) {
+    float m = 0; cudaEventElapsedTime(&m, ctx->ev_pool[s.e0], ctx->ev_pool[s.e1]);
+    if (s.kind == 0) stats->extend_seconds += m * 1e-3; else if (s.kind == 1) stats->connect_seconds += m * 1e-3; else stats->shade_seconds += m * 1e-3;
+  }
+  stats->kernel_launches = ctx->launches; stats->batches = ctx->batches;
+  return DSRT_OK;
+}
+
+int dsrt_render_device(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp_stride, float* d_accum, void* stream, dsrt_stats* stats) {
+  if (!ctx || !d_accum) return DSRT_ERR_INVALID;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  int rc = render_impl(ctx, spp_begin, spp_count, spp_stride, d_accum, st);
+  if (rc) return rc;
+  if (stats) return dsrt_collect_stats(ctx, stats);
+  return DSRT_OK;
+}
+
+int dsrt_resolve_device(dsrt_ctx* ctx, const float* d_accum, float* d_rgb, uint32_t* d_rgba8, void* stream) {
+  if (!ctx || !d_accum || !ctx->have_cam) return DSRT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const int n = ctx->cam.width * ctx->cam.height;
+  k_resolve<<<(n + 255) / 256, 256, 0, st>>>(d_accum, d_rgb, d_rgba8, n, 1.0f / (float)ctx->ns_aa);
+  CK(cudaGetLastError());
+  return DSRT_OK;
+}
+
+int dsrt_sync(dsrt_ctx* ctx) {
+  if (!ctx) return DSRT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return DSRT_OK;
+}
+
+int dsrt_render(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp_stride, float* rgb_out, dsrt_stats* stats) {
+  if (!ctx || !rgb_out) return DSRT_ERR_INVALID;
+  if (!ctx->have_cam) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: call dsrt_set_camera first");
+  CK(cudaSetDevice(ctx->device));
+  const size_t npix = (size_t)ctx->cam.width * ctx->cam.height;
+  if (npix > ctx->accum_pixels) { int rc = dev_alloc(ctx, &ctx->d_accum_own, npix * 3); if (rc) return rc; ctx->accum_pixels = npix; }
+  CK(cudaMemsetAsync(ctx->d_accum_own, 0, npix * 3 * sizeof(float), ctx->stream));
+  int rc = render_impl(ctx, spp_begin, spp_count, spp_stride, ctx->d_accum_own, ctx->stream);
+  if (rc) return rc;
+  k_resolve<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_accum_own, ctx->d_accum_own, nullptr, (int)npix, 1.0f / (float)ctx->ns_aa);
+  CK(cudaMemcpyAsync(rgb_out, ctx->d_accum_own, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (stats) return dsrt_collect_stats(ctx, stats);
+  return DSRT_OK;
+}
+
+// Camera::generate_ray in double, exactly the reference's operation order (camera.cpp:113-129 with
+// Matrix3x3::operator*, matrix3x3.cpp:138-142, and Vector3D::normalize, vector3D.h:95-131).  Host code is
+// compiled without FMA contraction (see Makefile), so these rays are bit-identical to the reference's.
+static void host_generate_ray64(const Camera& c, double x, double y, double* out6) {
+  const double sp[3] = {-(x - 0.5) * c.W64 / c.dist64, -(y - 0.5) * c.H64 / c.dist64, 1.0};
+  double w[3], dir[3];
+  for (int k = 0; k < 3; k++) {
+    w[k] = (sp[0] * c.c2w64[k] + sp[1] * c.c2w64[3 + k]) + sp[2] * c.c2w64[6 + k];
+    dir[k] = ((-sp[0]) * c.c2w64[k] + (-sp[1]) * c.c2w64[3 + k]) + (-sp[2]) * c.c2w64[6 + k];
+  }
+  const double inv = 1. / std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+  for (int k = 0; k < 3; k++) { out6[k] = w[k] + c.pos64[k]; out6[3 + k] = dir[k] * inv; }
+}
+
+int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) {
+  if (!ctx || !prim_id) return DSRT_ERR_INVALID;
+  if (!ctx->have_accel || !ctx->have_cam) return fail(ctx, DSRT_ERR_INVALID, "dsrt_primary_hits: call dsrt_build_accel and dsrt_set_camera first");
+  CK(cudaSetDevice(ctx->device));
+  const int W = ctx->cam.width, H = ctx->cam.height, n = W * H;
+  std::vector<int32_t> slots(n); std::vector<double> ts(n);
+  cudaStream_t st = ctx->stream;
+  if (mode == 1) {
+    std::vector<double> rays((size_t)n * 6);
+    for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) host_generate_ray64(ctx->cam, (x + 0.5) / W, (y + 0.5) / H, &rays[6 * ((size_t)y * W + x)]);
+    double* d_rays = nullptr; int32_t* d_slot = nullptr; double* d_t = nullptr;
+    CK(cudaMalloc((void**)&d_rays, rays.size() * sizeof(double)));
+    CK(cudaMalloc((void**)&d_slot, n * sizeof(int32_t)));
+    CK(cudaMalloc((void**)&d_t, n * sizeof(double)));
+    CK(cudaMemcpyAsync(d_rays, rays.data(), rays.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_primary_parity<<<(n + kTraceThreads - 1) / kTraceThreads, kTraceThreads, stack_bytes(), st>>>(make_accel(ctx, true), d_rays, n, d_slot, d_t);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(slots.data(), d_slot, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ts.data(), d_t, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_rays); cudaFree(d_slot); cudaFree(d_t);
+  } else {
+    int rc = ensure_wavefront(ctx, (size_t)n, 1);
+    if (rc) return rc;
+    if (ctx->n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &ctx->d_counters, (size_t)1))) return rc; ctx->n_counter_blocks = 1; }
+    CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), st));
+    RenderParams rp; std::memset(&rp, 0, sizeof(rp)); rp.cam = ctx->cam;
+    k_generate_centres<<<(n + 255) / 256, 256, 0, st>>>(ctx->ps, rp, n);
+    k_set_u32<<<1, 1, 0, st>>>(&ctx->d_counters->q_count[0], (uint32_t)n);
+    k_trace<false, false><<<trace_grid(ctx), kTraceThreads, stack_bytes(), st>>>(make_accel(ctx, false), ctx->ps.ray_o, ctx->ps.ray_d, nullptr, &ctx->d_counters->q_count[0],
+                                                                             &ctx->d_counters->work_extend[0], ctx->ps.hit, nullptr, nullptr, ctx->d_totals);
+    CK(cudaGetLastError());
+    std::vector<float4> hits(n);
+    CK(cudaMemcpyAsync(hits.data(), ctx->ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n; i++) { int sl; std::memcpy(&sl, &hits[i].w, 4); slots[i] = sl; ts[i] = sl >= 0 ? (double)hits[i].x : (double)INFINITY; }
+  }
+  for (int i = 0; i < n; i++) { prim_id[i] = slots[i] >= 0 ? ctx->wide.slot_prim[slots[i]] : -1; if (t) t[i] = ts[i]; }
+  return DSRT_OK;
+}
+
+static int trace_batch(dsrt_ctx* ctx, bool any, int64_t n, const float* o, const float* d, const float* tmax, int32_t* out_id, float* out_t) {
+  if (!ctx->have_accel) return fail(ctx, DSRT_ERR_INVALID, "dsrt_trace: call dsrt_build_accel first");
+  if (n < 0 || (n > 0 && (!o || !d))) return DSRT_ERR_INVALID;
+  if (n == 0) return DSRT_OK;
+  CK(cudaSetDevice(ctx->device));
+  int rc = ensure_wavefront(ctx, (size_t)n, 1);
+  if (rc) return rc;
+  if (ctx->n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &ctx->d_counters, (size_t)1))) return rc; ctx->n_counter_blocks = 1; }
+  cudaStream_t st = ctx->stream;
+  std::vector<float4> ho(n), hd(n);
+  for (int64_t i = 0; i < n; i++) {
+    ho[i] = make_float4(o[3 * i], o[3 * i + 1], o[3 * i + 2], tmax ? tmax[i] : INFINITY);
+    int m1 = -1; float f; std::memcpy(&f, &m1, 4);
+    hd[i] = make_float4(d[3 * i], d[3 * i + 1], d[3 * i + 2], f);
+  }
+  CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), st));
+  CK(cudaMemsetAsync(ctx->d_totals, 0, sizeof(Totals), st));
+  CK(cudaMemcpyAsync(ctx->ps.ray_o, ho.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->ps.ray_d, hd.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
+  k_set_u32<<<1, 1, 0, st>>>(&ctx->d_counters->q_count[0], (uint32_t)n);
+  const Accel A = make_accel(ctx, false);
+  if (any) k_trace<true, true><<<trace_grid(ctx), kTraceThreads, stack_bytes(), st>>>(A, ctx->ps.ray_o, ctx->ps.ray_d, nullptr, &ctx->d_counters->q_count[0], &ctx->d_counters->work_extend[0], ctx->ps.hit, nullptr, nullptr, ctx->d_totals);
+  else k_trace<false, true><<<trace_grid(ctx), kTraceThreads, stack_bytes(), st>>>(A, ctx->ps.ray_o, ctx->ps.ray_d, nullptr, &ctx->d_counters->q_count[0], &ctx->d_counters->work_extend[0], ctx->ps.hit, nullptr, nullptr, ctx->d_totals);
+  CK(cudaGetLastError());
+  std::vector<float4> hits(n);
+  CK(cudaMemcpyAsync(hits.data(), ctx->ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int64_t i = 0; i < n; i++) {
+    int sl; std::memcpy(&sl, &hits[i].w, 4);
+    if (any) out_id[i] = sl >= 0 ? 1 : 0;
+    else { out_id[i] = sl >= 0 ? ctx->wide.slot_prim[sl] : -1; if (out_t) out_t[i] = sl >= 0 ? hits[i].x : INFINITY; }
+  }
+  return DSRT_OK;
+}
+
+int dsrt_trace_closest(dsrt_ctx* ctx, int64_t n, const float* o, const float* d, const float* tmax, int32_t* prim_id, float* t) {
+  if (!ctx || !prim_id) return DSRT_ERR_INVALID;
+  return trace_batch(ctx, false, n, o, d, tmax, prim_id, t);
+}
+int dsrt_trace_any(dsrt_ctx* ctx, int64_t n, const float* o, const float* d, const float* tmax, int32_t* hit) {
+  if (!ctx || !hit) return DSRT_ERR_INVALID;
+  return trace_batch(ctx, true, n, o, d, tmax, hit, nullptr);
+}
+
+int dsrt_tonemap(dsrt_ctx* ctx, const float* rgb, int64_t n_pixels, uint32_t* rgba8) {
+  if (!ctx || !rgb || !rgba8 || n_pixels < 0) return DSRT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  float* d_in = nullptr; uint32_t* d_out = nullptr;
+  CK(cudaMalloc((void**)&d_in, (size_t)n_pixels * 3 * sizeof(float) + 16));
+  CK(cudaMalloc((void**)&d_out, (size_t)n_pixels * sizeof(uint32_t) + 16));
+  CK(cudaMemcpyAsync(d_in, rgb, (size_t)n_pixels * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  k_resolve<<<(unsigned)((n_pixels + 255) / 256), 256, 0, ctx->stream>>>(d_in, nullptr, d_out, (int)n_pixels, 1.0f);
+  CK(cudaMemcpyAsync(rgba8, d_out, (size_t)n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_in); cudaFree(d_out);
+  return DSRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// layout.h -- HBM data layout shared by the host flattening code and the sm_100a kernels.
+//
+// Wide node: 8-wide BVH node, 80 bytes = five 128-bit loads (compressed wide-BVH layout after
+// Ylitie, Karras, Laine 2017).  Child boxes are quantised to 8 bits per plane relative to the node's
+// own box: lo = origin + qlo * 2^(e-127), hi = origin + qhi * 2^(e-127), rounded OUTWARDS so every
+// quantised box encloses the exact double-precision box of the reference's binary SAH tree.
+// Internal children are stored contiguously from child_base in slot order; the primitives of all
+// leaf children are stored contiguously from prim_base (leaf-contiguous primitive order).
+//   meta[i] == 0            empty slot
+//   meta[i] = 001 sssss     internal child, sssss = 24 + slot
+//   meta[i] = ccc ooooo     leaf child, ccc = unary primitive count (001, 011, 111), ooooo = offset from prim_base
+// so (meta >> 5) << (meta & 31) is the child's contribution to the 32-bit hit mask
+// (bits 31..24 internal children, bits 23..0 primitives).
+#pragma once
+#include <stdint.h>
+
+namespace dsrt {
+
+constexpr float kInfF = __builtin_huge_valf();
+
+struct alignas(16) WideNode {
+  float ox, oy, oz;
+  uint8_t ex, ey, ez, imask;
+  uint32_t child_base;
+  uint32_t prim_base;
+  uint8_t meta[8];
+  uint8_t qlox[8], qloy[8];
+  uint8_t qloz[8], qhix[8];
+  uint8_t qhiy[8], qhiz[8];
+};
+static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
+
+// Primitive record in leaf-contiguous order, 48 bytes = three 128-bit loads.
+//   triangle: a = (p1.xyz, prim_id bits)  b = (p2.xyz, 1.0f)      c = (p3.xyz, bsdf bits)
+//   sphere:   a = (centre.xyz, prim_id)   b = (r, r*r, 0, 0.0f)   c = (0,0,0, bsdf bits)
+struct alignas(16) PrimRecord {
+  float ax, ay, az; int32_t prim_id;
+  float bx, by, bz; float is_tri;
+  float cx, cy, cz; int32_t bsdf;
+};
+static_assert(sizeof(PrimRecord) == 48, "PrimRecord must be 48 bytes");
+
+// Shading record indexed by SLOT (same order as PrimRecord): vertex normals, 48 bytes.
+struct alignas(16) ShadeRecord {
+  float n1x, n1y, n1z, pad0;
+  float n2x, n2y, n2z, pad1;
+  float n3x, n3y, n3z, pad2;
+};
+static_assert(sizeof(ShadeRecord) == 48, "ShadeRecord must be 48 bytes");
+
+// fp64 primitive record for the parity kernel (reference arithmetic), by slot: 9 doubles + 3 spare
+struct alignas(16) PrimRecord64 {
+  double p[9];      // triangle: p1,p2,p3   sphere: centre, r, r2(computed as r*r in double), 0...
+  double pad[3];
+};
+static_assert(sizeof(PrimRecord64) == 96, "PrimRecord64 must be 96 bytes");
+
+struct Bsdf {       // 32 bytes
+  float a[3];       // albedo | reflectance | radiance
+  float b[3];       // transmittance
+  float ior;
+  int32_t type;     // 0 diffuse 1 mirror 2 refraction 3 glass 4 emission
+};
+
+struct Light {      // float restatement of light_param
+  float radiance[3];
+  float v0[3];      // dirToLight | position
+  float dir[3];
+  float dim_x[3];
+  float dim_y[3];
+  float area;
+  float s2w[9];     // column-major
+  int32_t type;     // 0 directional 1 hemisphere 2 point 3 area
+  int32_t is_delta;
+  int32_t sample_base;  // first flat light-sample index j of this light
+  int32_t n_samples;
+};
+
+struct Camera {
+  float pos[3];
+  float c2w[9];     // column-major
+  float w_over_dist, h_over_dist;
+  double pos64[3], c2w64[9], W64, H64, dist64;
+  int32_t width, height;
+};
+
+}  // namespace dsrt

@@ -1,0 +1,301 @@
+// traverse.cuh -- per-lane traversal of the compressed 8-wide BVH (layout.h) for sm_100a.
+//
+// Replaces BVHAccel::intersect closest / any (reference src/bvh.cpp:227-363) and Triangle/Sphere::intersect
+// (src/static_scene/triangle.cpp:25-104, sphere.cpp:10-77); the reference GPU fork's counterpart is
+// cuda_src/traversal.cu:3-222 + intersect.cu (pointer-linked binary tree, 64-entry local-memory stack).
+//
+// Node fetch = five 128-bit loads (80 B), primitive fetch = three 128-bit loads (48 B), both through the
+// read-only path.  The traversal stack holds node GROUPS (child_base, pending-children mask): one entry per
+// tree level, kept in shared memory (entry-major, so a warp's accesses are conflict free).
+//
+// Production mode: float slabs + watertight ray/triangle test (Woop, Benthin, Wald 2013: shear to ray space,
+// antisymmetric edge functions, double-precision fallback on exact zeros).
+// PARITY mode (template flag): identical traversal, but boxes are padded conservatively and the leaf tests run
+// in fp64 with the reference's exact operation order and no FMA contraction, so primary-hit ids are bit-exact
+// against the reference's double-precision Moller-Trumbore (gate 1 of SURVEY.md 8d).
+#pragma once
+#include <stdint.h>
+
+#include "hd.h"
+#include "layout.h"
+
+namespace dsrt {
+
+constexpr int kStackEntries = 32;    // >= levels of wide nodes (checked at dsrt_build_accel)
+
+
+struct TraceRay {
+  float ox, oy, oz, dx, dy, dz;
+  float tmax;
+  int src_slot;   // primitive slot the ray starts on, -1 for camera rays (see hit-point note in shade.cuh)
+};
+struct TraceHit {
+  float t, u, v;  // u,v = barycentric weights of p2,p3 (the reference's u,v, triangle.cpp:69-70)
+  int slot;       // -1 = miss
+};
+struct TraceCounters { uint32_t nodes, prims; };
+
+// double-precision ray for the parity kernel
+struct Ray64 { double ox, oy, oz, dx, dy, dz; };
+
+DSRT_HD float sel3(int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); }
+
+// ---- production primitive tests -------------------------------------------------------------------------
+struct WatertightRay { int kx, ky, kz; float Sx, Sy, Sz; };
+
+DSRT_HD WatertightRay make_watertight(const TraceRay& r) {
+  WatertightRay w;
+  const float ax = fabsf(r.dx), ay = fabsf(r.dy), az = fabsf(r.dz);
+  w.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+  w.kx = w.kz + 1; if (w.kx == 3) w.kx = 0;
+  w.ky = w.kx + 1; if (w.ky == 3) w.ky = 0;
+  const float dz = sel3(w.kz, r.dx, r.dy, r.dz);
+  if (dz < 0.0f) { int t = w.kx; w.kx = w.ky; w.ky = t; }   // preserve winding
+  const float dx = sel3(w.kx, r.dx, r.dy, r.dz), dy = sel3(w.ky, r.dx, r.dy, r.dz);
+  w.Sz = 1.0f / dz;
+  w.Sx = dx * w.Sz;
+  w.Sy = dy * w.Sz;
+  return w;
+}
+
+// returns true and updates (t,u,v) when the triangle is hit in (0, tmax)
+DSRT_HD bool hit_triangle(const TraceRay& r, const WatertightRay& w, const float4 a, const float4 b,
+                                             const float4 c, float tmax, float& t_out, float& u_out, float& v_out) {
+  const float Ax0 = a.x - r.ox, Ay0 = a.y - r.oy, Az0 = a.z - r.oz;
+  const float Bx0 = b.x - r.ox, By0 = b.y - r.oy, Bz0 = b.z - r.oz;
+  const float Cx0 = c.x - r.ox, Cy0 = c.y - r.oy, Cz0 = c.z - r.oz;
+  const float Akz = sel3(w.kz, Ax0, Ay0, Az0), Bkz = sel3(w.kz, Bx0, By0, Bz0), Ckz = sel3(w.kz, Cx0, Cy0, Cz0);
+  const float Ax = hd_fma(-w.Sx, Akz, sel3(w.kx, Ax0, Ay0, Az0)), Ay = hd_fma(-w.Sy, Akz, sel3(w.ky, Ax0, Ay0, Az0));
+  const float Bx = hd_fma(-w.Sx, Bkz, sel3(w.kx, Bx0, By0, Bz0)), By = hd_fma(-w.Sy, Bkz, sel3(w.ky, Bx0, By0, Bz0));
+  const float Cx = hd_fma(-w.Sx, Ckz, sel3(w.kx, Cx0, Cy0, Cz0)), Cy = hd_fma(-w.Sy, Ckz, sel3(w.ky, Cx0, Cy0, Cz0));
+  // edge functions: products rounded separately, so swapping the two vertices of a shared edge negates the
+  // value exactly (no cracks between adjacent triangles)
+  float U = hd_sub(hd_mul(Cx, By), hd_mul(Cy, Bx));
+  float V = hd_sub(hd_mul(Ax, Cy), hd_mul(Ay, Cx));
+  float W = hd_sub(hd_mul(Bx, Ay), hd_mul(By, Ax));
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    U = (float)hd_dsub(hd_dmul((double)Cx, (double)By), hd_dmul((double)Cy, (double)Bx));
+    V = (float)hd_dsub(hd_dmul((double)Ax, (double)Cy), hd_dmul((double)Ay, (double)Cx));
+    W = (float)hd_dsub(hd_dmul((double)Bx, (double)Ay), hd_dmul((double)By, (double)Ax));
+  }
+  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  const float det = U + V + W;
+  if (det == 0.0f) return false;
+  const float Az = w.Sz * Akz, Bz = w.Sz * Bkz, Cz = w.Sz * Ckz;
+  const float T = U * Az + V * Bz + W * Cz;
+  const float rdet = 1.0f / det;
+  const float t = T * rdet;
+  if (!(t > 0.0f && t < tmax)) return false;
+  t_out = t; u_out = V * rdet; v_out = W * rdet;
+  return true;
+}
+
+// Sphere::test / intersect semantics (sphere.cpp:10-77) in float.  A ray that STARTS on this sphere (src)
+// has one root at ~0: the reference rejects it with t > min_t thanks to its 1e-11 origin offset; in float
+// that root is resolved analytically (inward -> far root 2b, outward -> miss).
+DSRT_HD bool hit_sphere(const TraceRay& r, const float4 a, const float4 b, bool is_src, bool any_hit,
+                                           float tmax, float& t_out) {
+  const float mx = a.x - r.ox, my = a.y - r.oy, mz = a.z - r.oz;
+  const float bq = mx * r.dx + my * r.dy + mz * r.dz;
+  if (is_src) {
+    const float t2 = 2.0f * bq;
+    if (!(t2 > 0.0f && t2 < tmax)) return false;
+    t_out = t2;
+    return true;
+  }
+  const float cq = mx * mx + my * my + mz * mz - b.y;
+  const float delta = bq * bq - cq;
+  if (delta < 0.0f) return false;
+  const float sq = sqrtf(delta);
+  const float t1 = bq - sq, t2 = bq + sq;
+  if (any_hit) {                       // sphere.cpp:42-44: both roots alias the far root
+    return !(t2 >= tmax || t2 <= 0.0f);
+  }
+  if (t1 >= tmax || t2 <= 0.0f) return false;
+  const float t = (t1 <= 0.0f) ? t2 : t1;
+  if (!(t < tmax)) return false;       // closest-hit semantics (the reference omits this test, sphere.cpp:64-72)
+  t_out = t;
+  return true;
+}
+
+// ---- parity (fp64, reference operation order, no FMA) ------------------------------------------------------
+DSRT_HD double dm(double a, double b) { return hd_dmul(a, b); }
+DSRT_HD double da(double a, double b) { return hd_dadd(a, b); }
+DSRT_HD double ds(double a, double b) { return hd_dsub(a, b); }
+DSRT_HD double ddot(double ax, double ay, double az, double bx, double by, double bz) {
+  return da(da(dm(ax, bx), dm(ay, by)), dm(az, bz));
+}
+// Triangle::intersect(r, i), triangle.cpp:62-84
+DSRT_HD bool hit_triangle64(const Ray64& r, const double* __restrict__ p, double tmax, double& t_out,
+                                               double& u_out, double& v_out) {
+  const double e1x = ds(p[3], p[0]), e1y = ds(p[4], p[1]), e1z = ds(p[5], p[2]);
+  const double e2x = ds(p[6], p[0]), e2y = ds(p[7], p[1]), e2z = ds(p[8], p[2]);
+  const double sx = ds(r.ox, p[0]), sy = ds(r.oy, p[1]), sz = ds(r.oz, p[2]);
+  // cross(e1, d)
+  const double c1x = ds(dm(e1y, r.dz), dm(e1z, r.dy)), c1y = ds(dm(e1z, r.dx), dm(e1x, r.dz)), c1z = ds(dm(e1x, r.dy), dm(e1y, r.dx));
+  const double f = ddot(c1x, c1y, c1z, e2x, e2y, e2z);
+  if (f == 0) return false;
+  // cross(s, d)
+  const double c2x = ds(dm(sy, r.dz), dm(sz, r.dy)), c2y = ds(dm(sz, r.dx), dm(sx, r.dz)), c2z = ds(dm(sx, r.dy), dm(sy, r.dx));
+  const double u = hd_ddiv(ddot(c2x, c2y, c2z, e2x, e2y, e2z), f);
+  const double v = hd_ddiv(ddot(c1x, c1y, c1z, sx, sy, sz), f);
+  // cross(e1, -s)
+  const double nsx = -sx, nsy = -sy, nsz = -sz;
+  const double c3x = ds(dm(e1y, nsz), dm(e1z, nsy)), c3y = ds(dm(e1z, nsx), dm(e1x, nsz)), c3z = ds(dm(e1x, nsy), dm(e1y, nsx));
+  const double t = hd_ddiv(ddot(c3x, c3y, c3z, e2x, e2y, e2z), f);
+  if (!(u >= 0 && v >= 0 && da(u, v) <= 1 && t > 0.0 && t < tmax)) return false;
+  t_out = t; u_out = u; v_out = v;
+  return true;
+}
+// Sphere::intersect(r, i), sphere.cpp:10-77 (no t < i->t test: the hit is overwritten)
+DSRT_HD bool hit_sphere64(const Ray64& r, const double* __restrict__ p, double tmax, double& t_out) {
+  const double mx = ds(p[0], r.ox), my = ds(p[1], r.oy), mz = ds(p[2], r.oz);
+  const double b = ddot(mx, my, mz, r.dx, r.dy, r.dz);
+  const double c = ds(ddot(mx, my, mz, mx, my, mz), p[4]);
+  const double delta = ds(dm(b, b), c);
+  if (delta < 0) return false;
+  const double sq = hd_dsqrt(delta);
+  const double t1 = ds(b, sq), t2 = da(b, sq);
+  if (t1 >= tmax || t2 <= 0.0) return false;
+  t_out = (t1 <= 0.0) ? t2 : t1;
+  return true;
+}
+
+// ---- node test -----------------------------------------------------------------------------------------------
+struct NodeFrame {   // per-ray constants
+  float idx, idy, idz;   // reciprocal direction (clamped away from 0)
+  uint32_t octinv;       // 7 - octant, replicated in the low 3 bits
+};
+
+DSRT_HD NodeFrame make_frame(const TraceRay& r) {
+  NodeFrame f;
+  const float eps = 1.0e-24f;
+  const float dx = fabsf(r.dx) > eps ? r.dx : copysignf(eps, r.dx);
+  const float dy = fabsf(r.dy) > eps ? r.dy : copysignf(eps, r.dy);
+  const float dz = fabsf(r.dz) > eps ? r.dz : copysignf(eps, r.dz);
+  f.idx = 1.0f / dx; f.idy = 1.0f / dy; f.idz = 1.0f / dz;
+  const uint32_t oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+  f.octinv = 7u - oct;
+  return f;
+}
+
+DSRT_HD float byte_f(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+
+// Tests the 8 quantised child boxes of one node; returns the 32-bit hit mask (31..24 internal children in
+// visiting priority, 23..0 primitives).  pad > 0 only in parity mode.
+template <bool PARITY>
+DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uint4 n0, const uint4 n1,
+                                                  const uint4 n2, const uint4 n3, const uint4 n4, float tmax, float pad) {
+  const float ox = hd_u2f(n0.x), oy = hd_u2f(n0.y), oz = hd_u2f(n0.z);
+  const float sx = hd_u2f((n0.w & 0xffu) << 23) * fr.idx;
+  const float sy = hd_u2f(((n0.w >> 8) & 0xffu) << 23) * fr.idy;
+  const float sz = hd_u2f(((n0.w >> 16) & 0xffu) << 23) * fr.idz;
+  float blx, bly, blz, bhx, bhy, bhz;
+  if (PARITY) {
+    blx = (ox - pad - r.ox) * fr.idx; bhx = (ox + pad - r.ox) * fr.idx;
+    bly = (oy - pad - r.oy) * fr.idy; bhy = (oy + pad - r.oy) * fr.idy;
+    blz = (oz - pad - r.oz) * fr.idz; bhz = (oz + pad - r.oz) * fr.idz;
+  } else {
+    blx = bhx = (ox - r.ox) * fr.idx; bly = bhy = (oy - r.oy) * fr.idy; blz = bhz = (oz - r.oz) * fr.idz;
+  }
+  uint32_t mask = 0;
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const uint32_t meta4 = half ? n1.w : n1.z;
+    const uint32_t qlx = half ? n2.y : n2.x, qly = half ? n2.w : n2.z;
+    const uint32_t qlz = half ? n3.y : n3.x, qhx = half ? n3.w : n3.z;
+    const uint32_t qhy = half ? n4.y : n4.x, qhz = half ? n4.w : n4.z;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t meta = (meta4 >> (8 * i)) & 0xffu;
+      const float ax = hd_fma(byte_f(qlx, i), sx, blx), bx = hd_fma(byte_f(qhx, i), sx, bhx);
+      const float ay = hd_fma(byte_f(qly, i), sy, bly), by = hd_fma(byte_f(qhy, i), sy, bhy);
+      const float az = hd_fma(byte_f(qlz, i), sz, blz), bz = hd_fma(byte_f(qhz, i), sz, bhz);
+      const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+      float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+      tf = PARITY ? tf * 1.0001f + pad : tf * 1.0000004f;   // conservative against float rounding
+      if (meta != 0u && tn <= tf) {
+        const bool inner = (meta & 0xe0u) == 0x20u && (meta & 0x18u) == 0x18u;
+        const uint32_t bit = inner ? ((meta & 31u) ^ fr.octinv) : (meta & 31u);
+        mask |= (meta >> 5) << bit;
+      }
+    }
+  }
+  return mask;
+}
+
+// ---- the traversal loop --------------------------------------------------------------------------------------
+// One lane = one ray.  `stack` points at this thread's column of the shared-memory stack; entry e lives at
+// stack[e * stride].
+struct Accel {
+  const uint4* __restrict__ nodes;         // 5 uint4 per node
+  const float4* __restrict__ prims;        // 3 float4 per slot
+  const double* __restrict__ prims64;      // 12 doubles per slot (parity only)
+  float pad;                               // parity slab padding
+};
+
+template <bool ANY, bool PARITY, bool COUNT>
+DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, uint2* stack, int stride,
+                                          TraceHit& hit, double* t64_out, TraceCounters* cnt) {
+  const NodeFrame fr = make_frame(ray);
+  const WatertightRay wr = make_watertight(ray);
+  float tbest = ray.tmax;
+  double tbest64 = PARITY ? (double)ray.tmax : 0.0;
+  hit.slot = -1; hit.t = ray.tmax; hit.u = 0.f; hit.v = 0.f;
+  int sp = 0;
+  uint2 ngroup = make_uint2(0u, 0x80000000u);
+  uint2 tgroup = make_uint2(0u, 0u);
+  while (true) {
+    if (ngroup.y > 0x00ffffffu) {
+      const uint32_t bit = 31u - (uint32_t)hd_clz(ngroup.y);
+      ngroup.y &= ~(1u << bit);
+      if (ngroup.y > 0x00ffffffu) { stack[sp * stride] = ngroup; sp++; }
+      const uint32_t slot = (bit - 24u) ^ fr.octinv;
+      const uint32_t rel = hd_popc(ngroup.y & 0xffu & ((1u << slot) - 1u));
+      const uint4* np = A.nodes + (size_t)(ngroup.x + rel) * 5;
+      const uint4 n0 = hd_ldg(np), n1 = hd_ldg(np + 1), n2 = hd_ldg(np + 2), n3 = hd_ldg(np + 3), n4 = hd_ldg(np + 4);
+      if (COUNT) cnt->nodes++;
+      const uint32_t m = test_children<PARITY>(ray, fr, n0, n1, n2, n3, n4, tbest, A.pad);
+      ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
+      tgroup = make_uint2(n1.y, m & 0x00ffffffu);
+    } else {
+      tgroup = make_uint2(0u, 0u);
+    }
+    while (tgroup.y) {
+      const uint32_t k = 31u - (uint32_t)hd_clz(tgroup.y);
+      tgroup.y &= ~(1u << k);
+      const int slot = (int)(tgroup.x + k);
+      if (COUNT) cnt->prims++;
+      if (PARITY) {
+        const double* p = A.prims64 + (size_t)slot * 12;
+        double t, u = 0, v = 0; bool h;
+        const bool tri = p[11] != 0.0;
+        if (tri) h = hit_triangle64(*ray64, p, tbest64, t, u, v);
+        else h = hit_sphere64(*ray64, p, tbest64, t);
+        if (h) { tbest64 = t; tbest = hd_d2f_ru(t); hit.slot = slot; hit.t = (float)t; hit.u = (float)u; hit.v = (float)v; }
+      } else {
+        const float4* pp = A.prims + (size_t)slot * 3;
+        const float4 a = hd_ldg(pp), b = hd_ldg(pp + 1);
+        float t, u = 0.f, v = 0.f; bool h;
+        if (b.w != 0.0f) {
+          const float4 c = hd_ldg(pp + 2);
+          h = (slot != ray.src_slot) && hit_triangle(ray, wr, a, b, c, tbest, t, u, v);
+        } else {
+          h = hit_sphere(ray, a, b, slot == ray.src_slot, ANY, tbest, t);
+        }
+        if (h) {
+          if (ANY) { hit.slot = slot; hit.t = t; return; }
+          tbest = t; hit.slot = slot; hit.t = t; hit.u = u; hit.v = v;
+        }
+      }
+    }
+    if (ngroup.y <= 0x00ffffffu) {
+      if (sp == 0) break;
+      sp--;
+      ngroup = stack[sp * stride];
+    }
+  }
+  if (PARITY && t64_out) *t64_out = tbest64;
+}
+
+}  // namespace dsrt

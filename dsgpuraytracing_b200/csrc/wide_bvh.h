@@ -1,0 +1,25 @@
+// wide_bvh.h -- host-side flattening of the binary SAH BVH into the compressed 8-wide layout (layout.h).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "host_util.h"
+#include "layout.h"
+
+namespace dsrt {
+
+struct WideBVH {
+  std::vector<WideNode> nodes;      // node 0 = root, breadth-first
+  std::vector<int32_t> slot_prim;   // leaf-contiguous slot -> primitive id
+  int max_depth = 0;                // levels of wide nodes (bounds the traversal stack)
+};
+
+// primitive / shading / fp64 records in leaf-contiguous slot order (layout.h)
+void flatten_records(const dsrt_scene& sc, const WideBVH& wide, std::vector<PrimRecord>& recs, std::vector<ShadeRecord>& shd,
+                     std::vector<PrimRecord64>& r64);
+// float light table; returns the number of light samples per path vertex (pathtracer.cpp:474)
+int flatten_lights(int n_lights, const int32_t* light_type, const double* light_param, int ns_area_light, std::vector<Light>& out);
+
+int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err);
+
+}  // namespace dsrt

@@ -1,0 +1,145 @@
+/* dsrt.h -- C ABI of the B200-native path-tracing core (libdsrt.so).
+ *
+ * This is the drop-in boundary for the reference's GPU render path: it replaces the C++ class
+ * CUDAPathTracer of libGPUAccel.so (reference cuda_src/setup.h:90-148), which is driven from
+ * Application::startGPURayTracing (reference src/application.cpp:766-786).  Plain pointers and sizes
+ * only; every call returns a status code (DSRT_OK == 0) and never terminates the process (the reference
+ * prints and exit()s, cuda_src/setup.cu:139-143).  The message for the last failure of a context is
+ * available from dsrt_last_error().
+ *
+ * Call order for one render (mirrors CUDAPathTracer::init, cuda_src/setup.cu:181-201):
+ *   dsrt_create -> dsrt_set_scene -> dsrt_set_bvh (or dsrt_build_bvh2 + dsrt_set_bvh) -> dsrt_set_camera
+ *   -> dsrt_set_params -> dsrt_build_accel -> dsrt_render / dsrt_render_device -> dsrt_destroy
+ *
+ * Ownership: the caller owns every host array for the duration of the call only (the library copies);
+ * the library owns all device memory; output buffers are caller-allocated.  No cudaDeviceReset, no
+ * process-global state: contexts are independent (the reference keeps scene state in __constant__
+ * globals, cuda_src/kernel.cu:16-20, and is limited to 20 lights / 20 BSDFs, kernel.cu:3-4).
+ * One context is used by one host thread at a time.
+ */
+#ifndef DSRT_H
+#define DSRT_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSRT_OK 0
+#define DSRT_ERR_INVALID 1   /* bad argument / call order */
+#define DSRT_ERR_CUDA 2      /* CUDA runtime failure (no device, out of memory, launch failure, ...) */
+#define DSRT_ERR_LIMIT 3     /* scene exceeds an internal limit */
+
+typedef struct dsrt_ctx dsrt_ctx;
+
+/* Flattened static scene = what CUDAPathTracer::loadPrimitives / loadLights read out of
+ * PathTracer::primitives, Primitive::get_bsdf() and scene->lights (cuda_src/setup.cu:249-402, 689-774).
+ * Primitive i is PathTracer::primitives[i] (object order, src/pathtracer.cpp:230-234) -- that index is
+ * the primitive id reported by dsrt_primary_hits. */
+typedef struct {
+  int32_t n_prims;
+  const int32_t* prim_type;   /* 1 triangle, 0 sphere (triangle.h:74, sphere.h:85) */
+  const int32_t* prim_bsdf;   /* index into the BSDF table */
+  const double* tri_pos;      /* 9 per prim: p1,p2,p3 world space (Triangle v1,v2,v3; object.cpp:36-41) */
+  const double* tri_nrm;      /* 9 per prim: vertex normals n1,n2,n3 (halfEdgeMesh.h:492-515) */
+  const double* sphere;       /* 4 per prim: centre xyz, radius (sphere.h:98-99) */
+  int32_t n_bsdf;
+  const int32_t* bsdf_type;   /* 0 diffuse 1 mirror 2 refraction 3 glass 4 emission (bsdf.h:123-236) */
+  const float* bsdf_param;    /* 8 per BSDF: a[3] albedo|reflectance|radiance, b[3] transmittance, ior, 0 */
+  int32_t n_lights;
+  const int32_t* light_type;  /* 0 directional 1 infinite hemisphere 2 point 3 area (light.h:24-99) */
+  const double* light_param;  /* 28 per light: radiance[3], dirToLight|position[3], direction[3], dim_x[3],
+                                 dim_y[3], area, sampleToWorld[9] column-major at offset 16 */
+} dsrt_scene;
+
+/* Host-built binary SAH BVH (BVHAccel, src/bvh.cpp:21-202), flattened; node 0 is the root. */
+typedef struct {
+  int32_t n_nodes;
+  const double* node_bbox;    /* 6 per node: min xyz, max xyz */
+  const int32_t* node_start;  /* first slot in prim_order */
+  const int32_t* node_range;  /* number of slots */
+  const int32_t* node_left;   /* -1 when absent */
+  const int32_t* node_right;
+  const int32_t* prim_order;  /* n_prims: BVH slot -> primitive id (BVHAccel::primitives after the build) */
+} dsrt_bvh2;
+
+/* Counters of one render call (device-side atomics; the metric unit is the path SEGMENT = one BVH query). */
+typedef struct {
+  uint64_t camera_samples;    /* camera rays generated */
+  uint64_t extend_rays;       /* closest-hit queries (BVHAccel::intersect(ray, isect) calls) */
+  uint64_t shadow_rays;       /* any-hit queries (BVHAccel::intersect(ray) calls) */
+  uint64_t nodes_visited;     /* wide-BVH nodes fetched (only when dsrt_set_option("count_traversal",1)) */
+  uint64_t prims_tested;      /* primitive records fetched (same) */
+  double gpu_seconds;         /* CUDA-event time of the whole call on the render stream */
+  double extend_seconds;      /* summed CUDA-event time of the extend (closest-hit) launches */
+  double connect_seconds;     /* summed CUDA-event time of the connect (any-hit) launches */
+  double shade_seconds;       /* summed CUDA-event time of generate + shade launches */
+  uint32_t kernel_launches;   /* kernels launched by this call */
+  uint32_t batches;
+} dsrt_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------ */
+int dsrt_create(int device, dsrt_ctx** out);          /* replaces new CUDAPathTracer + init(), setup.cu:77-95,181-201 */
+int dsrt_destroy(dsrt_ctx* ctx);                      /* replaces ~CUDAPathTracer, setup.cu:97-115 */
+const char* dsrt_last_error(const dsrt_ctx* ctx);     /* never NULL */
+const char* dsrt_version(void);
+
+/* ---- scene upload -------------------------------------------------------------------------------- */
+int dsrt_set_scene(dsrt_ctx* ctx, const dsrt_scene* scene);   /* loadPrimitives + loadLights, setup.cu:249-402,689-774 */
+int dsrt_set_bvh(dsrt_ctx* ctx, const dsrt_bvh2* bvh);        /* loadBVH, setup.cu:415-476 */
+/* pos[3], c2w[9] column-major, frame size, screenDist -- Camera::generate_ray inputs (camera.cpp:113-129);
+ * replaces loadCamera, setup.cu:221-247 */
+int dsrt_set_camera(dsrt_ctx* ctx, const double* pos, const double* c2w, int32_t width, int32_t height,
+                    double screen_dist);
+/* ns_aa (-s), ns_area_light (-l), max_ray_depth (-m); replaces loadParameters, setup.cu:777-811 */
+int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t max_ray_depth, uint32_t seed);
+/* named knobs: "count_traversal" (0/1), "batch_spp" (camera samples per pixel per wavefront batch),
+ * "stage_timing" (0/1: per-stage CUDA events) */
+int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value);
+
+/* Host SAH builder = BVHAccel::BVHAccel + buildBVH (src/bvh.cpp:21-202: 32 buckets, max leaf 4, with the
+ * bucket-index clamp).  Arrays must hold 2*n_prims nodes / n_prims slots; returns the node count in *n_nodes. */
+int dsrt_build_bvh2(const dsrt_scene* scene, double* node_bbox, int32_t* node_start, int32_t* node_range,
+                    int32_t* node_left, int32_t* node_right, int32_t* prim_order, int32_t* n_nodes);
+
+/* Collapse the binary BVH into the compressed 8-wide SoA BVH, reorder primitives leaf-contiguously,
+ * upload.  Outputs sizes for the roofline accounting (may be NULL). */
+int dsrt_build_accel(dsrt_ctx* ctx);
+int dsrt_accel_info(const dsrt_ctx* ctx, int64_t* n_wide_nodes, int64_t* node_bytes, int64_t* prim_bytes,
+                    int32_t* max_depth);
+
+/* ---- rendering ----------------------------------------------------------------------------------- */
+/* Renders camera samples spp_begin, spp_begin+spp_stride, ... (spp_count of them) of every pixel and writes
+ * the radiance SUM scaled by 1/ns_aa (so a full render with spp_count == ns_aa equals the reference's
+ * sampleBuffer, src/pathtracer.cpp:571-581).  rgb_out: host, width*height*3 floats, row 0 = bottom
+ * (image.h:113-117).  Replaces startRayTracingPT + updateHostSampleBuffer, setup.cu:147-179, 813-827. */
+int dsrt_render(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp_stride, float* rgb_out,
+                dsrt_stats* stats);
+/* Same, but ADDS un-normalised radiance sums into a DEVICE buffer (width*height*3 floats) on the given
+ * cudaStream_t (NULL = the context's stream) without synchronising: the multi-GPU path reduces these
+ * partial sums with one NCCL reduce and then calls dsrt_resolve_device. */
+int dsrt_render_device(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp_stride,
+                       float* d_accum, void* stream, dsrt_stats* stats);
+/* d_rgb = d_accum / ns_aa; optional RGBA8 tone map (HDRImageBuffer::toColor, image.h:174-189) when d_rgba8 != NULL */
+int dsrt_resolve_device(dsrt_ctx* ctx, const float* d_accum, float* d_rgb, uint32_t* d_rgba8, void* stream);
+int dsrt_sync(dsrt_ctx* ctx);
+/* Fills *stats from the counters/events of the last dsrt_render_device call (synchronises). */
+int dsrt_collect_stats(dsrt_ctx* ctx, dsrt_stats* stats);
+
+/* Primary closest hits at pixel centres (px=(x+.5)/w): primitive id (-1 miss) and t.  mode 0 = production
+ * float kernel; mode 1 = parity kernel (same wide-BVH traversal, conservative box tests, fp64 leaf tests in the
+ * reference's operation order: triangle.cpp:55-104, sphere.cpp:10-77) -- bit-exact vs BVHAccel::intersect. */
+int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t);
+
+/* Arbitrary ray batches through the production kernels (tests / roofline counting):
+ * o,d: n*3 floats; tmax: n floats (NULL = inf).  closest: prim_id (-1 miss), t, u, v.  any: hit 0/1. */
+int dsrt_trace_closest(dsrt_ctx* ctx, int64_t n, const float* o, const float* d, const float* tmax,
+                       int32_t* prim_id, float* t);
+int dsrt_trace_any(dsrt_ctx* ctx, int64_t n, const float* o, const float* d, const float* tmax, int32_t* hit);
+
+/* HDRImageBuffer::toColor + ImageBuffer::update_pixel on the host result (image.h:49-58,174-189). */
+int dsrt_tonemap(dsrt_ctx* ctx, const float* rgb, int64_t n_pixels, uint32_t* rgba8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSRT_H */

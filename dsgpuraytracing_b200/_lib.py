@@ -53,13 +53,22 @@ class _Bvh2(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("camera_samples", C.c_uint64), ("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
-                ("nodes_visited", C.c_uint64), ("prims_tested", C.c_uint64), ("gpu_seconds", C.c_double),
+                ("extend_nodes", C.c_uint64), ("extend_prims", C.c_uint64),
+                ("connect_nodes", C.c_uint64), ("connect_prims", C.c_uint64), ("gpu_seconds", C.c_double),
                 ("extend_seconds", C.c_double), ("connect_seconds", C.c_double), ("shade_seconds", C.c_double),
                 ("kernel_launches", C.c_uint32), ("batches", C.c_uint32)]
 
     @property
     def segments(self):
         return self.extend_rays + self.shadow_rays
+
+    @property
+    def nodes_visited(self):
+        return self.extend_nodes + self.connect_nodes
+
+    @property
+    def prims_tested(self):
+        return self.extend_prims + self.connect_prims
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

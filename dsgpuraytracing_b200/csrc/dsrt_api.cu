@@ -58,7 +58,7 @@ struct Counters {             // one block per batch, zeroed with a single memse
   uint32_t work_extend[kMaxDepthSlots];   // persistent-kernel fetch counters
   uint32_t work_connect[kMaxDepthSlots];
 };
-struct Totals { unsigned long long camera, extend, shadow, nodes, prims; };
+struct Totals { unsigned long long camera, extend, shadow, nodes[2], prims[2]; };   // [0] extend, [1] connect
 
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void k_generate(PathState ps, RenderParams rp, int n_paths, uint32_t* queue, uint32_t* q_count, int aligned) {
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
   if (COUNT) {
     unsigned long long a = cnt.nodes, b = cnt.prims;
     for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(kFull, a, o); b += __shfl_xor_sync(kFull, b, o); }
-    if (lane == 0) { atomicAdd(&totals->nodes, a); atomicAdd(&totals->prims, b); }
+    if (lane == 0) { atomicAdd(&totals->nodes[ANY ? 1 : 0], a); atomicAdd(&totals->prims[ANY ? 1 : 0], b); }
   }
 }
 
@@ -688,7 +688,7 @@ int dsrt_collect_stats(dsrt_ctx* ctx, dsrt_stats* stats) {
   Totals t;
   CK(cudaMemcpy(&t, ctx->d_totals, sizeof(t), cudaMemcpyDeviceToHost));
   stats->camera_samples = t.camera; stats->extend_rays = t.extend; stats->shadow_rays = t.shadow;
-  stats->nodes_visited = t.nodes; stats->prims_tested = t.prims;
+  stats->extend_nodes = t.nodes[0]; stats->extend_prims = t.prims[0]; stats->connect_nodes = t.nodes[1]; stats->connect_prims = t.prims[1];
   float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
   stats->gpu_seconds = ms * 1e-3;
   for (const auto& s : ctx->spans) {

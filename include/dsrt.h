@@ -67,8 +67,10 @@ typedef struct {
   uint64_t camera_samples;    /* camera rays generated */
   uint64_t extend_rays;       /* closest-hit queries (BVHAccel::intersect(ray, isect) calls) */
   uint64_t shadow_rays;       /* any-hit queries (BVHAccel::intersect(ray) calls) */
-  uint64_t nodes_visited;     /* wide-BVH nodes fetched (only when dsrt_set_option("count_traversal",1)) */
-  uint64_t prims_tested;      /* primitive records fetched (same) */
+  /* fetch counters, only filled when dsrt_set_option("count_traversal", 1): wide-BVH nodes (80 B) and primitive
+   * records (48 B) fetched by the extend (closest-hit) and connect (any-hit) kernels */
+  uint64_t extend_nodes, extend_prims;
+  uint64_t connect_nodes, connect_prims;
   double gpu_seconds;         /* CUDA-event time of the whole call on the render stream */
   double extend_seconds;      /* summed CUDA-event time of the extend (closest-hit) launches */
   double connect_seconds;     /* summed CUDA-event time of the connect (any-hit) launches */

@@ -138,7 +138,8 @@ def test_empty_scene_and_errors(core):
     assert (ids == -1).all()
     # errors are status codes + messages, never exit() (the reference exits, cuda_src/setup.cu:139-143)
     c2 = D.Core(0)
-    with pytest.raises(D.DsrtError, match="dsrt_build_accel"):
+    with pytest.raises(D.DsrtError, match="dsrt_set_camera|dsrt_build_accel"):
+        c2.width = c2.height = 4
         c2.render()
     with pytest.raises(D.DsrtError, match="prim_bsdf"):
         bad = dict(base, prim_type=np.ones(1, np.int32), prim_bsdf=np.array([5], np.int32), tri_pos=np.zeros((1, 9)),

@@ -7,7 +7,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 EXPORTED_SYMBOLS = [
-    "dsrt_create", "dsrt_destroy", "dsrt_last_error", "dsrt_version", "dsrt_set_scene", "dsrt_set_bvh",
+    "dsrt_create", "dsrt_create_multi", "dsrt_device_count", "dsrt_destroy", "dsrt_last_error", "dsrt_version", "dsrt_set_scene", "dsrt_set_bvh",
     "dsrt_set_camera", "dsrt_set_params", "dsrt_set_option", "dsrt_build_bvh2", "dsrt_build_accel",
     "dsrt_accel_info", "dsrt_render", "dsrt_render_device", "dsrt_resolve_device", "dsrt_sync",
     "dsrt_collect_stats", "dsrt_primary_hits", "dsrt_trace_closest", "dsrt_trace_any", "dsrt_tonemap",
@@ -112,10 +112,14 @@ def build_bvh2(arr):
 class Core:
     """One dsrt context = one GPU.  Mirrors the call order of CUDAPathTracer::init (cuda_src/setup.cu:181-201)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
         self.L = load_library()
         self.ctx = C.c_void_p()
-        rc = self.L.dsrt_create(int(device), C.byref(self.ctx))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.L.dsrt_create_multi(len(devices), arr, C.byref(self.ctx))
+        else:
+            rc = self.L.dsrt_create(int(device), C.byref(self.ctx))
         if rc:
             msg = self.L.dsrt_last_error(self.ctx).decode() if self.ctx else "no context"
             if self.ctx:
@@ -245,3 +249,62 @@ class Core:
         self._ck(self.L.dsrt_tonemap(self.ctx, C.c_void_p(rgb.ctypes.data), C.c_int64(n), C.c_void_p(out.ctypes.data)),
                  "dsrt_tonemap")
         return out.reshape(rgb.shape[:-1])
+
+
+# ---- host side (libdsrt_host.so): COLLADA import + the PathTracer mirror -------------------------------------------
+HOST_EXPORTED_SYMBOLS = ["dsrth_load_dae", "dsrth_free", "dsrth_get_scene", "dsrth_get_camera", "dsrth_render_file"]
+_hostlib = None
+
+
+def load_host_library():
+    global _hostlib
+    if _hostlib is None:
+        load_library()
+        p = os.path.join(_HERE, "libdsrt_host.so")
+        if not os.path.exists(p):
+            raise DsrtError(f"{p} is missing: build it with `make -C dsgpuraytracing_b200/csrc all`")
+        _hostlib = C.CDLL(p)
+    return _hostlib
+
+
+def load_dae(path, width, height, cam_info=None):
+    """ColladaParser::load + Application::load (+ loadCamera): returns (scene arrays dict, camera[17])."""
+    H = load_host_library()
+    h = C.c_void_p(); err = C.create_string_buffer(512)
+    rc = H.dsrth_load_dae(path.encode(), int(width), int(height), cam_info.encode() if cam_info else None, C.byref(h), err, 512)
+    if rc:
+        raise DsrtError(f"dsrth_load_dae({path}) failed: {err.value.decode()}")
+    try:
+        s = _Scene()
+        H.dsrth_get_scene(h, C.byref(s))
+        n, nb, nl = s.n_prims, s.n_bsdf, s.n_lights
+
+        def arr(ptr, dt, shape):
+            cnt = int(np.prod(shape))
+            if cnt == 0:
+                return np.zeros(shape, dt)
+            buf = (C.c_char * (cnt * np.dtype(dt).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dt).reshape(shape).copy()
+        out = {"prim_type": arr(s.prim_type, np.int32, (n,)), "prim_bsdf": arr(s.prim_bsdf, np.int32, (n,)),
+               "tri_pos": arr(s.tri_pos, np.float64, (n, 9)), "tri_nrm": arr(s.tri_nrm, np.float64, (n, 9)),
+               "sphere": arr(s.sphere, np.float64, (n, 4)), "bsdf_type": arr(s.bsdf_type, np.int32, (nb,)),
+               "bsdf_param": arr(s.bsdf_param, np.float32, (nb, 8)), "light_type": arr(s.light_type, np.int32, (nl,)),
+               "light_param": arr(s.light_param, np.float64, (nl, 28))}
+        cam = np.zeros(17)
+        H.dsrth_get_camera(h, C.c_void_p(cam.ctypes.data))
+        return out, cam
+    finally:
+        H.dsrth_free(h)
+
+
+def render_file(path, width, height, spp, ns_area_light, max_depth, cam_info=None, n_gpus=1, seed=0, png=None):
+    """main.cpp's headless GPU path through the C++ PathTracer class.  Returns (rgb[H,W,3], Stats, seconds dict)."""
+    H = load_host_library()
+    rgb = np.zeros((height, width, 3), np.float32); st = Stats(); err = C.create_string_buffer(512)
+    tb, tr = C.c_double(), C.c_double()
+    rc = H.dsrth_render_file(path.encode(), cam_info.encode() if cam_info else None, int(width), int(height), int(spp),
+                             int(ns_area_light), int(max_depth), int(n_gpus), C.c_uint32(seed), C.c_void_p(rgb.ctypes.data),
+                             png.encode() if png else None, C.byref(st), C.byref(tb), C.byref(tr), err, 512)
+    if rc:
+        raise DsrtError(f"dsrth_render_file failed ({rc}): {err.value.decode()}")
+    return rgb, st, {"bvh_build": tb.value, "render": tr.value}

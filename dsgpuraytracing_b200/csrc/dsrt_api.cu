@@ -319,16 +319,55 @@ __global__ void k_resolve(const float* __restrict__ accum, float* rgb, uint32_t*
   }
 }
 
+// Fused reduce + resolve for the single-process multi-GPU path: device 0 reads every GPU's partial radiance sums
+// straight from peer memory over NVLink (P2P loads; staged copies when peer access is unavailable), adds them,
+// scales by 1/ns_aa and tone-maps -- one kernel, no separate collective pass.
+struct PeerPtrs { const float* p[16]; int n; };
+__global__ void k_resolve_peers(PeerPtrs src, float* rgb, uint32_t* rgba8, int n_pix, float inv_spp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pix) return;
+  float r = 0.f, g = 0.f, b = 0.f;
+  for (int k = 0; k < src.n; k++) { const float* a = src.p[k]; r += a[3 * i]; g += a[3 * i + 1]; b += a[3 * i + 2]; }
+  r *= inv_spp; g *= inv_spp; b *= inv_spp;
+  if (rgb) { rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b; }
+  if (rgba8) {
+    const float exposure = sqrtf(2.0f), og = 1.0f / 2.2f;
+    const float cr = fminf(1.0f, powf(r * exposure, og)), cg = fminf(1.0f, powf(g * exposure, og)), cb = fminf(1.0f, powf(b * exposure, og));
+    rgba8[i] = (uint32_t)(cr * 255.f) | ((uint32_t)(cg * 255.f) << 8) | ((uint32_t)(cb * 255.f) << 16) | (255u << 24);
+  }
+}
+
 }  // namespace dsrt
 
 // ================================================================================================ host side
 using namespace dsrt;
 
-struct dsrt_ctx {
+// everything that lives on ONE GPU
+struct DevState {
   int device = 0;
   cudaStream_t stream = nullptr;
-  std::string err;
   int sm_count = 148;
+  int trace_blocks = 148 * 6;
+  void* d_nodes = nullptr; void* d_prims = nullptr; void* d_shade = nullptr; void* d_prims64 = nullptr;
+  void* d_bsdf = nullptr; void* d_lights = nullptr;
+  size_t cap_paths = 0, cap_shadow = 0;
+  PathState ps{}; ShadowQueue sq{};
+  uint32_t* queue[2] = {nullptr, nullptr};
+  Counters* d_counters = nullptr; int n_counter_blocks = 0;
+  Totals* d_totals = nullptr;
+  float* d_accum_own = nullptr; size_t accum_pixels = 0;
+  float* d_stage = nullptr; size_t stage_floats = 0;      // device 0 only: staging for peers without P2P access
+  bool peer_ok = true;                                    // device 0 can read this device's memory directly
+  std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  struct Span { size_t e0, e1; int kind; };
+  std::vector<Span> spans;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  uint32_t launches = 0, batches = 0;
+};
+
+struct dsrt_ctx {
+  std::vector<DevState> devs;
+  std::string err;
   // host copies of the inputs
   bool have_scene = false, have_bvh = false, have_cam = false, have_accel = false;
   int n_prims = 0;
@@ -343,25 +382,9 @@ struct dsrt_ctx {
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
   int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0;
-  // accel
   WideBVH wide;
   double scene_diag = 1.0;
-  void* d_nodes = nullptr; void* d_prims = nullptr; void* d_shade = nullptr; void* d_prims64 = nullptr;
-  void* d_bsdf = nullptr; void* d_lights = nullptr;
   int n_lights = 0, n_light_samples = 0;
-  // wavefront buffers
-  size_t cap_paths = 0, cap_shadow = 0;
-  PathState ps{}; ShadowQueue sq{}; float4* s_hit = nullptr;
-  uint32_t* queue[2] = {nullptr, nullptr};
-  Counters* d_counters = nullptr; int n_counter_blocks = 0;
-  Totals* d_totals = nullptr;
-  float* d_accum_own = nullptr; size_t accum_pixels = 0;
-  // timing
-  std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
-  struct Span { size_t e0, e1; int kind; };
-  std::vector<Span> spans;
-  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-  uint32_t launches = 0, batches = 0;
 };
 
 namespace {
@@ -377,41 +400,94 @@ template <typename T> int dev_alloc(dsrt_ctx* ctx, T** p, size_t n) {
 }
 void dev_free(void* p) { if (p) cudaFree(p); }
 
-cudaEvent_t next_event(dsrt_ctx* ctx) {
-  if (ctx->ev_used == ctx->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
-  return ctx->ev_pool[ctx->ev_used++];
+cudaEvent_t next_event(DevState& D) {
+  if (D.ev_used == D.ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); D.ev_pool.push_back(e); }
+  return D.ev_pool[D.ev_used++];
 }
 
-Accel make_accel(const dsrt_ctx* ctx, bool parity) {
+Accel make_accel(const dsrt_ctx* ctx, const DevState& D, bool parity) {
   Accel A;
-  A.nodes = (const uint4*)ctx->d_nodes; A.prims = (const float4*)ctx->d_prims;
-  A.prims64 = (const double*)ctx->d_prims64;
+  A.nodes = (const uint4*)D.d_nodes; A.prims = (const float4*)D.d_prims;
+  A.prims64 = (const double*)D.d_prims64;
   A.pad = parity ? (float)(1e-5 * ctx->scene_diag) : 0.f;
   return A;
 }
 
-int trace_grid(const dsrt_ctx* ctx) { return ctx->sm_count * 8; }   // persistent: 8 CTAs of 4 warps per SM
 size_t stack_bytes() { return (size_t)kStackEntries * kTraceThreads * sizeof(uint2); }
 
-int ensure_wavefront(dsrt_ctx* ctx, size_t paths, size_t shadow) {
-  if (paths > ctx->cap_paths) {
+int init_device(dsrt_ctx* ctx, DevState& D, int device) {
+  D.device = device;
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  D.sm_count = prop.multiProcessorCount;
+  CK(cudaMalloc((void**)&D.d_totals, sizeof(Totals)));
+  CK(cudaEventCreate(&D.ev_begin)); CK(cudaEventCreate(&D.ev_end));
+  // persistent grid = resident CTAs per SM (registers / shared-memory stack) x SM count
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, false>, kTraceThreads, stack_bytes()));
+  D.trace_blocks = D.sm_count * std::max(per_sm, 1);
+  return DSRT_OK;
+}
+
+void free_device(DevState& D) {
+  cudaSetDevice(D.device);
+  if (D.stream) cudaStreamSynchronize(D.stream);
+  dev_free(D.d_nodes); dev_free(D.d_prims); dev_free(D.d_shade); dev_free(D.d_prims64); dev_free(D.d_bsdf); dev_free(D.d_lights);
+  dev_free(D.ps.ray_o); dev_free(D.ps.ray_d); dev_free(D.ps.hit); dev_free(D.ps.thr); dev_free(D.ps.pixel); dev_free(D.ps.sample);
+  dev_free(D.queue[0]); dev_free(D.queue[1]); dev_free(D.sq.a); dev_free(D.sq.b); dev_free(D.sq.c);
+  dev_free(D.d_counters); dev_free(D.d_totals); dev_free(D.d_accum_own); dev_free(D.d_stage);
+  for (cudaEvent_t e : D.ev_pool) cudaEventDestroy(e);
+  if (D.ev_begin) cudaEventDestroy(D.ev_begin);
+  if (D.ev_end) cudaEventDestroy(D.ev_end);
+  if (D.stream) cudaStreamDestroy(D.stream);
+}
+
+int ensure_wavefront(dsrt_ctx* ctx, DevState& D, size_t paths, size_t shadow) {
+  if (paths > D.cap_paths) {
     int rc;
-    if ((rc = dev_alloc(ctx, &ctx->ps.ray_o, paths))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->ps.ray_d, paths))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->ps.hit, paths))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->ps.thr, paths))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->ps.pixel, paths))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->ps.sample, paths))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->queue[0], paths))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->queue[1], paths))) return rc;
-    ctx->cap_paths = paths;
+    if ((rc = dev_alloc(ctx, &D.ps.ray_o, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.ps.ray_d, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.ps.hit, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.ps.thr, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.ps.pixel, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.ps.sample, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.queue[0], paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.queue[1], paths))) return rc;
+    D.cap_paths = paths;
   }
-  if (shadow > ctx->cap_shadow) {
+  if (shadow > D.cap_shadow) {
     int rc;
-    if ((rc = dev_alloc(ctx, &ctx->sq.a, shadow))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->sq.b, shadow))) return rc;
-    if ((rc = dev_alloc(ctx, &ctx->sq.c, shadow))) return rc;
-    ctx->cap_shadow = shadow;
+    if ((rc = dev_alloc(ctx, &D.sq.a, shadow))) return rc;
+    if ((rc = dev_alloc(ctx, &D.sq.b, shadow))) return rc;
+    if ((rc = dev_alloc(ctx, &D.sq.c, shadow))) return rc;
+    D.cap_shadow = shadow;
+  }
+  return DSRT_OK;
+}
+
+int create_impl(int n, const int* devices, dsrt_ctx** out) {
+  if (!out || n < 1 || n > 16 || !devices) return DSRT_ERR_INVALID;
+  *out = nullptr;
+  dsrt_ctx* ctx = new dsrt_ctx();
+  ctx->devs.resize(n);
+  *out = ctx;     // returned even on failure so the caller can read the message; every later call fails loudly
+  for (int i = 0; i < n; i++) {
+    int rc = init_device(ctx, ctx->devs[i], devices[i]);
+    if (rc) { ctx->err = "dsrt_create: " + ctx->err; return rc; }
+  }
+  // let device 0 read its peers' partial framebuffers directly (fused reduce + resolve)
+  for (int i = 1; i < n; i++) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, ctx->devs[0].device, ctx->devs[i].device);
+    if (can) {
+      cudaSetDevice(ctx->devs[0].device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(ctx->devs[i].device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) can = 0;
+      cudaGetLastError();
+    }
+    ctx->devs[i].peer_ok = can != 0;
   }
   return DSRT_OK;
 }
@@ -420,46 +496,15 @@ int ensure_wavefront(dsrt_ctx* ctx, size_t paths, size_t shadow) {
 
 extern "C" {
 
-const char* dsrt_version(void) { return "dsrt 0.1 (sm_100a wavefront path tracer)"; }
+const char* dsrt_version(void) { return "dsrt 0.2 (sm_100a wavefront path tracer)"; }
 
-int dsrt_create(int device, dsrt_ctx** out) {
-  if (!out) return DSRT_ERR_INVALID;
-  *out = nullptr;
-  dsrt_ctx* ctx = new dsrt_ctx();
-  ctx->device = device;
-  cudaError_t e = cudaSetDevice(device);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) {
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, device);
-    if (e == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-  }
-  if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_totals, sizeof(Totals));
-  if (e == cudaSuccess) { cudaEventCreate(&ctx->ev_begin); cudaEventCreate(&ctx->ev_end); }
-  if (e != cudaSuccess) {
-    // the context is still returned so the caller can read the message; every later call fails loudly
-    ctx->err = std::string("dsrt_create: ") + cudaGetErrorString(e);
-    *out = ctx;
-    return DSRT_ERR_CUDA;
-  }
-  *out = ctx;
-  return DSRT_OK;
-}
+int dsrt_create(int device, dsrt_ctx** out) { return create_impl(1, &device, out); }
+int dsrt_create_multi(int n_devices, const int* devices, dsrt_ctx** out) { return create_impl(n_devices, devices, out); }
+int dsrt_device_count(const dsrt_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
 
 int dsrt_destroy(dsrt_ctx* ctx) {
   if (!ctx) return DSRT_ERR_INVALID;
-  cudaSetDevice(ctx->device);
-  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  dev_free(ctx->d_nodes); dev_free(ctx->d_prims); dev_free(ctx->d_shade); dev_free(ctx->d_prims64);
-  dev_free(ctx->d_bsdf); dev_free(ctx->d_lights);
-  dev_free(ctx->ps.ray_o); dev_free(ctx->ps.ray_d); dev_free(ctx->ps.hit); dev_free(ctx->ps.thr);
-  dev_free(ctx->ps.pixel); dev_free(ctx->ps.sample); dev_free(ctx->queue[0]); dev_free(ctx->queue[1]);
-  dev_free(ctx->sq.a); dev_free(ctx->sq.b); dev_free(ctx->sq.c); dev_free(ctx->s_hit);
-  dev_free(ctx->d_counters); dev_free(ctx->d_totals); dev_free(ctx->d_accum_own);
-  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-  if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
-  if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  for (DevState& D : ctx->devs) free_device(D);
   delete ctx;
   return DSRT_OK;
 }
@@ -554,7 +599,6 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
 int dsrt_build_accel(dsrt_ctx* ctx) {
   if (!ctx) return DSRT_ERR_INVALID;
   if (!ctx->have_scene || !ctx->have_bvh) return fail(ctx, DSRT_ERR_INVALID, "dsrt_build_accel: scene and BVH must be set first");
-  CK(cudaSetDevice(ctx->device));
   dsrt_scene s{}; s.n_prims = ctx->n_prims; s.prim_type = ctx->prim_type.data(); s.prim_bsdf = ctx->prim_bsdf.data();
   s.tri_pos = ctx->tri_pos.data(); s.tri_nrm = ctx->tri_nrm.data(); s.sphere = ctx->sphere.data();
   std::vector<Box3> pbox; primitive_boxes(&s, pbox);
@@ -575,19 +619,23 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
   ctx->n_light_samples = flatten_lights((int)ctx->light_type.size(), ctx->light_type.data(), ctx->light_param.data(), ctx->ns_area_light, lights);
   ctx->n_lights = (int)lights.size();
 
-  dev_free(ctx->d_nodes); dev_free(ctx->d_prims); dev_free(ctx->d_shade); dev_free(ctx->d_prims64); dev_free(ctx->d_bsdf); dev_free(ctx->d_lights);
-  ctx->d_nodes = ctx->d_prims = ctx->d_shade = ctx->d_prims64 = ctx->d_bsdf = ctx->d_lights = nullptr;
-  auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
-    cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
-    if (e == cudaSuccess && bytes) e = cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
-    return e;
-  };
-  CK(up(&ctx->d_nodes, ctx->wide.nodes.data(), ctx->wide.nodes.size() * sizeof(WideNode)));
-  CK(up(&ctx->d_prims, recs.data(), n * sizeof(PrimRecord)));
-  CK(up(&ctx->d_shade, shd.data(), n * sizeof(ShadeRecord)));
-  CK(up(&ctx->d_prims64, r64.data(), n * sizeof(PrimRecord64)));
-  CK(up(&ctx->d_bsdf, ctx->bsdfs.data(), ctx->bsdfs.size() * sizeof(Bsdf)));
-  CK(up(&ctx->d_lights, lights.data(), lights.size() * sizeof(Light)));
+  for (DevState& D : ctx->devs) {      // the scene is replicated on every GPU
+    CK(cudaSetDevice(D.device));
+    dev_free(D.d_nodes); dev_free(D.d_prims); dev_free(D.d_shade); dev_free(D.d_prims64); dev_free(D.d_bsdf); dev_free(D.d_lights);
+    D.d_nodes = D.d_prims = D.d_shade = D.d_prims64 = D.d_bsdf = D.d_lights = nullptr;
+    auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
+      cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
+      if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, D.stream);
+      return e;
+    };
+    CK(up(&D.d_nodes, ctx->wide.nodes.data(), ctx->wide.nodes.size() * sizeof(WideNode)));
+    CK(up(&D.d_prims, recs.data(), n * sizeof(PrimRecord)));
+    CK(up(&D.d_shade, shd.data(), n * sizeof(ShadeRecord)));
+    CK(up(&D.d_prims64, r64.data(), n * sizeof(PrimRecord64)));
+    CK(up(&D.d_bsdf, ctx->bsdfs.data(), ctx->bsdfs.size() * sizeof(Bsdf)));
+    CK(up(&D.d_lights, lights.data(), lights.size() * sizeof(Light)));
+  }
+  for (DevState& D : ctx->devs) { CK(cudaSetDevice(D.device)); CK(cudaStreamSynchronize(D.stream)); }
   ctx->have_accel = true;
   return DSRT_OK;
 }
@@ -602,10 +650,11 @@ int dsrt_accel_info(const dsrt_ctx* ctx, int64_t* n_wide_nodes, int64_t* node_by
 }
 
 // ------------------------------------------------------------------------------------------------ rendering
-static int render_impl(dsrt_ctx* ctx, int spp_begin, int spp_count, int spp_stride, float* d_accum, cudaStream_t st) {
+// Enqueues the whole wavefront for samples spp_begin + k*spp_stride (k < spp_count) on one device; no host sync.
+static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count, int spp_stride, float* d_accum, cudaStream_t st) {
   if (!ctx->have_accel || !ctx->have_cam) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: call dsrt_build_accel and dsrt_set_camera first");
   if (spp_count < 0 || spp_stride < 1 || spp_begin < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: bad sample range");
-  CK(cudaSetDevice(ctx->device));
+  CK(cudaSetDevice(D.device));
   const int W = ctx->cam.width, H = ctx->cam.height;
   const int blocks_x = (W + 7) / 8, blocks_y = (H + 3) / 4;
   const int npp = blocks_x * blocks_y * 32;
@@ -615,94 +664,102 @@ static int render_impl(dsrt_ctx* ctx, int spp_begin, int spp_count, int spp_stri
   batch_spp = std::min(batch_spp, std::max(1, spp_count));
   const size_t P = (size_t)npp * batch_spp;
   const int nls = ctx->n_light_samples;
-  int rc = ensure_wavefront(ctx, P, P * (size_t)std::max(nls, 1));
+  int rc = ensure_wavefront(ctx, D, P, P * (size_t)std::max(nls, 1));
   if (rc) return rc;
   const int n_batches = (spp_count + batch_spp - 1) / batch_spp;
-  if (n_batches > ctx->n_counter_blocks) {
-    if ((rc = dev_alloc(ctx, &ctx->d_counters, (size_t)n_batches))) return rc;
-    ctx->n_counter_blocks = n_batches;
+  if (n_batches > D.n_counter_blocks) {
+    if ((rc = dev_alloc(ctx, &D.d_counters, (size_t)std::max(n_batches, 1)))) return rc;
+    D.n_counter_blocks = std::max(n_batches, 1);
   }
-  CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters) * (size_t)n_batches, st));
-  CK(cudaMemsetAsync(ctx->d_totals, 0, sizeof(Totals), st));
-  ctx->ev_used = 0; ctx->spans.clear(); ctx->launches = 0; ctx->batches = (uint32_t)n_batches;
-  CK(cudaEventRecord(ctx->ev_begin, st));
+  CK(cudaMemsetAsync(D.d_counters, 0, sizeof(Counters) * (size_t)std::max(n_batches, 1), st));
+  CK(cudaMemsetAsync(D.d_totals, 0, sizeof(Totals), st));
+  D.ev_used = 0; D.spans.clear(); D.launches = 0; D.batches = (uint32_t)n_batches;
+  CK(cudaEventRecord(D.ev_begin, st));
 
-  SceneDev sc; sc.bsdf = (const Bsdf*)ctx->d_bsdf; sc.lights = (const Light*)ctx->d_lights; sc.shade = (const float4*)ctx->d_shade;
+  SceneDev sc; sc.bsdf = (const Bsdf*)D.d_bsdf; sc.lights = (const Light*)D.d_lights; sc.shade = (const float4*)D.d_shade;
   sc.n_lights = ctx->n_lights; sc.n_light_samples = nls;
   RenderParams rp; rp.cam = ctx->cam; rp.seed = ctx->seed; rp.max_depth = ctx->max_depth; rp.spp_begin = spp_begin; rp.spp_stride = spp_stride;
   rp.n_pix_padded = npp; rp.blocks_x = blocks_x; rp.skip_null_shadow = (int)ctx->opt_skip_null; rp.batch_first_sample = 0;
-  const Accel A = make_accel(ctx, false);
+  const Accel A = make_accel(ctx, D, false);
   const bool count = ctx->opt_count != 0, timing = ctx->opt_stage_timing != 0;
-  const int tgrid = trace_grid(ctx);
+  const int tgrid = D.trace_blocks;
   const size_t sbytes = stack_bytes();
 
-  auto span_begin = [&](int kind) { if (timing) { dsrt_ctx::Span s; s.kind = kind; s.e0 = ctx->ev_used; cudaEventRecord(next_event(ctx), st); s.e1 = 0; ctx->spans.push_back(s); } };
-  auto span_end = [&]() { if (timing) { ctx->spans.back().e1 = ctx->ev_used; cudaEventRecord(next_event(ctx), st); } };
+  auto span_begin = [&](int kind) { if (timing) { DevState::Span s; s.kind = kind; s.e0 = D.ev_used; cudaEventRecord(next_event(D), st); s.e1 = 0; D.spans.push_back(s); } };
+  auto span_end = [&]() { if (timing) { D.spans.back().e1 = D.ev_used; cudaEventRecord(next_event(D), st); } };
 
   for (int bi = 0; bi < n_batches; bi++) {
     const int s0 = bi * batch_spp, ns = std::min(batch_spp, spp_count - s0);
     const int n_paths = npp * ns;
-    Counters* C = ctx->d_counters + bi;
+    Counters* C = D.d_counters + bi;
     rp.batch_first_sample = s0;
     span_begin(2);
-    k_generate<<<(n_paths + 255) / 256, 256, 0, st>>>(ctx->ps, rp, n_paths, ctx->queue[0], &C->q_count[0], aligned);
+    k_generate<<<(n_paths + 255) / 256, 256, 0, st>>>(D.ps, rp, n_paths, D.queue[0], &C->q_count[0], aligned);
     span_end();
-    ctx->launches++;
+    D.launches++;
     int cur = 0;
     for (int d = 0; d <= ctx->max_depth; d++) {
-      const uint32_t* q = (d == 0 && aligned) ? nullptr : ctx->queue[cur];
+      const uint32_t* q = (d == 0 && aligned) ? nullptr : D.queue[cur];
       span_begin(0);
-      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ctx->ps.ray_o, ctx->ps.ray_d, q, &C->q_count[d], &C->work_extend[d], ctx->ps.hit, nullptr, nullptr, ctx->d_totals);
-      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ctx->ps.ray_o, ctx->ps.ray_d, q, &C->q_count[d], &C->work_extend[d], ctx->ps.hit, nullptr, nullptr, ctx->d_totals);
+      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals);
+      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals);
       span_end();
-      // upper bound of this depth's queue: depth 0 = all paths; deeper levels can only shrink
-      const int bound = d == 0 ? n_paths : std::min(n_paths, ctx->sm_count * 16 * 128);
+      // depth 0 shades every path; deeper levels only shrink, so a capped grid-stride launch is enough
+      const int bound = d == 0 ? n_paths : std::min(n_paths, D.sm_count * 16 * 128);
       span_begin(2);
-      k_shade<<<(bound + 127) / 128, 128, 0, st>>>(ctx->ps, (const float4*)ctx->d_prims, sc, rp, q, &C->q_count[d], ctx->queue[cur ^ 1], &C->q_count[d + 1],
-                                                   ctx->sq, &C->s_count[d], d_accum, d);
+      k_shade<<<(bound + 127) / 128, 128, 0, st>>>(D.ps, (const float4*)D.d_prims, sc, rp, q, &C->q_count[d], D.queue[cur ^ 1], &C->q_count[d + 1],
+                                                   D.sq, &C->s_count[d], d_accum, d);
       span_end();
       if (nls > 0) {
         span_begin(1);
-        if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ctx->sq.a, ctx->sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, ctx->sq.c, d_accum, ctx->d_totals);
-        else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ctx->sq.a, ctx->sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, ctx->sq.c, d_accum, ctx->d_totals);
+        if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals);
+        else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals);
         span_end();
-        ctx->launches++;
+        D.launches++;
       }
-      ctx->launches += 2;
+      D.launches += 2;
       cur ^= 1;
     }
-    k_tally<<<1, 32, 0, st>>>(C, ctx->d_totals, (uint32_t)((size_t)W * H * ns));
-    ctx->launches++;
+    k_tally<<<1, 32, 0, st>>>(C, D.d_totals, (uint32_t)((size_t)W * H * ns));
+    D.launches++;
   }
-  CK(cudaEventRecord(ctx->ev_end, st));
+  CK(cudaEventRecord(D.ev_end, st));
   CK(cudaGetLastError());
   return DSRT_OK;
 }
 
+// sums the counters of all devices; times are the maximum over devices
 int dsrt_collect_stats(dsrt_ctx* ctx, dsrt_stats* stats) {
   if (!ctx) return DSRT_ERR_INVALID;
-  CK(cudaSetDevice(ctx->device));
-  CK(cudaEventSynchronize(ctx->ev_end));
-  if (!stats) return DSRT_OK;
-  std::memset(stats, 0, sizeof(*stats));
-  Totals t;
-  CK(cudaMemcpy(&t, ctx->d_totals, sizeof(t), cudaMemcpyDeviceToHost));
-  stats->camera_samples = t.camera; stats->extend_rays = t.extend; stats->shadow_rays = t.shadow;
-  stats->extend_nodes = t.nodes[0]; stats->extend_prims = t.prims[0]; stats->connect_nodes = t.nodes[1]; stats->connect_prims = t.prims[1];
-  float ms = 0; CK(cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
-  stats->gpu_seconds = ms * 1e-3;
-  for (const auto& s : ctx->spans) {
-    float m = 0; cudaEventElapsedTime(&m, ctx->ev_pool[s.e0], ctx->ev_pool[s.e1]);
-    if (s.kind == 0) stats->extend_seconds += m * 1e-3; else if (s.kind == 1) stats->connect_seconds += m * 1e-3; else stats->shade_seconds += m * 1e-3;
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  for (DevState& D : ctx->devs) {
+    CK(cudaSetDevice(D.device));
+    CK(cudaEventSynchronize(D.ev_end));
+    if (!stats) continue;
+    Totals t;
+    CK(cudaMemcpy(&t, D.d_totals, sizeof(t), cudaMemcpyDeviceToHost));
+    stats->camera_samples += t.camera; stats->extend_rays += t.extend; stats->shadow_rays += t.shadow;
+    stats->extend_nodes += t.nodes[0]; stats->extend_prims += t.prims[0]; stats->connect_nodes += t.nodes[1]; stats->connect_prims += t.prims[1];
+    float ms = 0; CK(cudaEventElapsedTime(&ms, D.ev_begin, D.ev_end));
+    stats->gpu_seconds = std::max(stats->gpu_seconds, (double)ms * 1e-3);
+    double e = 0, c = 0, sh = 0;
+    for (const auto& s : D.spans) {
+      float m = 0; cudaEventElapsedTime(&m, D.ev_pool[s.e0], D.ev_pool[s.e1]);
+      if (s.kind == 0) e += m * 1e-3; else if (s.kind == 1) c += m * 1e-3; else sh += m * 1e-3;
+    }
+    stats->extend_seconds = std::max(stats->extend_seconds, e); stats->connect_seconds = std::max(stats->connect_seconds, c);
+    stats->shade_seconds = std::max(stats->shade_seconds, sh);
+    stats->kernel_launches += D.launches; stats->batches += D.batches;
   }
-  stats->kernel_launches = ctx->launches; stats->batches = ctx->batches;
   return DSRT_OK;
 }
 
 int dsrt_render_device(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp_stride, float* d_accum, void* stream, dsrt_stats* stats) {
   if (!ctx || !d_accum) return DSRT_ERR_INVALID;
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  int rc = render_impl(ctx, spp_begin, spp_count, spp_stride, d_accum, st);
+  if (ctx->devs.size() != 1) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render_device: single-device contexts only (one process per GPU)");
+  DevState& D = ctx->devs[0];
+  cudaStream_t st = stream ? (cudaStream_t)stream : D.stream;
+  int rc = render_impl(ctx, D, spp_begin, spp_count, spp_stride, d_accum, st);
   if (rc) return rc;
   if (stats) return dsrt_collect_stats(ctx, stats);
   return DSRT_OK;
@@ -710,8 +767,9 @@ int dsrt_render_device(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int3
 
 int dsrt_resolve_device(dsrt_ctx* ctx, const float* d_accum, float* d_rgb, uint32_t* d_rgba8, void* stream) {
   if (!ctx || !d_accum || !ctx->have_cam) return DSRT_ERR_INVALID;
-  CK(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  DevState& D = ctx->devs[0];
+  CK(cudaSetDevice(D.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : D.stream;
   const int n = ctx->cam.width * ctx->cam.height;
   k_resolve<<<(n + 255) / 256, 256, 0, st>>>(d_accum, d_rgb, d_rgba8, n, 1.0f / (float)ctx->ns_aa);
   CK(cudaGetLastError());
@@ -720,23 +778,44 @@ int dsrt_resolve_device(dsrt_ctx* ctx, const float* d_accum, float* d_rgb, uint3
 
 int dsrt_sync(dsrt_ctx* ctx) {
   if (!ctx) return DSRT_ERR_INVALID;
-  CK(cudaSetDevice(ctx->device));
-  CK(cudaStreamSynchronize(ctx->stream));
+  for (DevState& D : ctx->devs) { CK(cudaSetDevice(D.device)); CK(cudaStreamSynchronize(D.stream)); }
   return DSRT_OK;
 }
 
 int dsrt_render(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp_stride, float* rgb_out, dsrt_stats* stats) {
   if (!ctx || !rgb_out) return DSRT_ERR_INVALID;
   if (!ctx->have_cam) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: call dsrt_set_camera first");
-  CK(cudaSetDevice(ctx->device));
   const size_t npix = (size_t)ctx->cam.width * ctx->cam.height;
-  if (npix > ctx->accum_pixels) { int rc = dev_alloc(ctx, &ctx->d_accum_own, npix * 3); if (rc) return rc; ctx->accum_pixels = npix; }
-  CK(cudaMemsetAsync(ctx->d_accum_own, 0, npix * 3 * sizeof(float), ctx->stream));
-  int rc = render_impl(ctx, spp_begin, spp_count, spp_stride, ctx->d_accum_own, ctx->stream);
-  if (rc) return rc;
-  k_resolve<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_accum_own, ctx->d_accum_own, nullptr, (int)npix, 1.0f / (float)ctx->ns_aa);
-  CK(cudaMemcpyAsync(rgb_out, ctx->d_accum_own, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  const int G = (int)ctx->devs.size();
+  // GPU r renders samples k with k mod G == r of the requested list (load is balanced whatever the image content)
+  for (int r = 0; r < G; r++) {
+    DevState& D = ctx->devs[r];
+    CK(cudaSetDevice(D.device));
+    if (npix > D.accum_pixels) { int rc = dev_alloc(ctx, &D.d_accum_own, npix * 3); if (rc) return rc; D.accum_pixels = npix; }
+    CK(cudaMemsetAsync(D.d_accum_own, 0, npix * 3 * sizeof(float), D.stream));
+    const int cnt = spp_count > r ? (spp_count - r + G - 1) / G : 0;
+    int rc = render_impl(ctx, D, spp_begin + r * spp_stride, cnt, spp_stride * G, D.d_accum_own, D.stream);
+    if (rc) return rc;
+  }
+  DevState& D0 = ctx->devs[0];
+  CK(cudaSetDevice(D0.device));
+  PeerPtrs pp; pp.n = G; pp.p[0] = D0.d_accum_own;
+  for (int r = 1; r < G; r++) {
+    DevState& D = ctx->devs[r];
+    CK(cudaStreamWaitEvent(D0.stream, D.ev_end, 0));
+    if (D.peer_ok) pp.p[r] = D.d_accum_own;
+    else {
+      const size_t need = npix * 3 * (size_t)(G - 1);
+      if (need > D0.stage_floats) { int rc = dev_alloc(ctx, &D0.d_stage, need); if (rc) return rc; D0.stage_floats = need; }
+      float* dst = D0.d_stage + npix * 3 * (size_t)(r - 1);
+      CK(cudaMemcpyPeerAsync(dst, D0.device, D.d_accum_own, D.device, npix * 3 * sizeof(float), D0.stream));
+      pp.p[r] = dst;
+    }
+  }
+  k_resolve_peers<<<(unsigned)((npix + 255) / 256), 256, 0, D0.stream>>>(pp, D0.d_accum_own, nullptr, (int)npix, 1.0f / (float)ctx->ns_aa);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(rgb_out, D0.d_accum_own, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, D0.stream));
+  CK(cudaStreamSynchronize(D0.stream));
   if (stats) return dsrt_collect_stats(ctx, stats);
   return DSRT_OK;
 }
@@ -758,10 +837,11 @@ static void host_generate_ray64(const Camera& c, double x, double y, double* out
 int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) {
   if (!ctx || !prim_id) return DSRT_ERR_INVALID;
   if (!ctx->have_accel || !ctx->have_cam) return fail(ctx, DSRT_ERR_INVALID, "dsrt_primary_hits: call dsrt_build_accel and dsrt_set_camera first");
-  CK(cudaSetDevice(ctx->device));
+  DevState& D = ctx->devs[0];
+  CK(cudaSetDevice(D.device));
   const int W = ctx->cam.width, H = ctx->cam.height, n = W * H;
   std::vector<int32_t> slots(n); std::vector<double> ts(n);
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = D.stream;
   if (mode == 1) {
     std::vector<double> rays((size_t)n * 6);
     for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) host_generate_ray64(ctx->cam, (x + 0.5) / W, (y + 0.5) / H, &rays[6 * ((size_t)y * W + x)]);
@@ -770,25 +850,25 @@ int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) 
     CK(cudaMalloc((void**)&d_slot, n * sizeof(int32_t)));
     CK(cudaMalloc((void**)&d_t, n * sizeof(double)));
     CK(cudaMemcpyAsync(d_rays, rays.data(), rays.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    k_primary_parity<<<(n + kTraceThreads - 1) / kTraceThreads, kTraceThreads, stack_bytes(), st>>>(make_accel(ctx, true), d_rays, n, d_slot, d_t);
+    k_primary_parity<<<(n + kTraceThreads - 1) / kTraceThreads, kTraceThreads, stack_bytes(), st>>>(make_accel(ctx, D, true), d_rays, n, d_slot, d_t);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(slots.data(), d_slot, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ts.data(), d_t, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     cudaFree(d_rays); cudaFree(d_slot); cudaFree(d_t);
   } else {
-    int rc = ensure_wavefront(ctx, (size_t)n, 1);
+    int rc = ensure_wavefront(ctx, D, (size_t)n, 1);
     if (rc) return rc;
-    if (ctx->n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &ctx->d_counters, (size_t)1))) return rc; ctx->n_counter_blocks = 1; }
-    CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), st));
+    if (D.n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &D.d_counters, (size_t)1))) return rc; D.n_counter_blocks = 1; }
+    CK(cudaMemsetAsync(D.d_counters, 0, sizeof(Counters), st));
     RenderParams rp; std::memset(&rp, 0, sizeof(rp)); rp.cam = ctx->cam;
-    k_generate_centres<<<(n + 255) / 256, 256, 0, st>>>(ctx->ps, rp, n);
-    k_set_u32<<<1, 1, 0, st>>>(&ctx->d_counters->q_count[0], (uint32_t)n);
-    k_trace<false, false><<<trace_grid(ctx), kTraceThreads, stack_bytes(), st>>>(make_accel(ctx, false), ctx->ps.ray_o, ctx->ps.ray_d, nullptr, &ctx->d_counters->q_count[0],
-                                                                             &ctx->d_counters->work_extend[0], ctx->ps.hit, nullptr, nullptr, ctx->d_totals);
+    k_generate_centres<<<(n + 255) / 256, 256, 0, st>>>(D.ps, rp, n);
+    k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
+    k_trace<false, false><<<D.trace_blocks, kTraceThreads, stack_bytes(), st>>>(make_accel(ctx, D, false), D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0],
+                                                                            &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals);
     CK(cudaGetLastError());
     std::vector<float4> hits(n);
-    CK(cudaMemcpyAsync(hits.data(), ctx->ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     for (int i = 0; i < n; i++) { int sl; std::memcpy(&sl, &hits[i].w, 4); slots[i] = sl; ts[i] = sl >= 0 ? (double)hits[i].x : (double)INFINITY; }
   }
@@ -800,28 +880,29 @@ static int trace_batch(dsrt_ctx* ctx, bool any, int64_t n, const float* o, const
   if (!ctx->have_accel) return fail(ctx, DSRT_ERR_INVALID, "dsrt_trace: call dsrt_build_accel first");
   if (n < 0 || (n > 0 && (!o || !d))) return DSRT_ERR_INVALID;
   if (n == 0) return DSRT_OK;
-  CK(cudaSetDevice(ctx->device));
-  int rc = ensure_wavefront(ctx, (size_t)n, 1);
+  DevState& D = ctx->devs[0];
+  CK(cudaSetDevice(D.device));
+  int rc = ensure_wavefront(ctx, D, (size_t)n, 1);
   if (rc) return rc;
-  if (ctx->n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &ctx->d_counters, (size_t)1))) return rc; ctx->n_counter_blocks = 1; }
-  cudaStream_t st = ctx->stream;
+  if (D.n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &D.d_counters, (size_t)1))) return rc; D.n_counter_blocks = 1; }
+  cudaStream_t st = D.stream;
   std::vector<float4> ho(n), hd(n);
   for (int64_t i = 0; i < n; i++) {
     ho[i] = make_float4(o[3 * i], o[3 * i + 1], o[3 * i + 2], tmax ? tmax[i] : INFINITY);
     int m1 = -1; float f; std::memcpy(&f, &m1, 4);
     hd[i] = make_float4(d[3 * i], d[3 * i + 1], d[3 * i + 2], f);
   }
-  CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), st));
-  CK(cudaMemsetAsync(ctx->d_totals, 0, sizeof(Totals), st));
-  CK(cudaMemcpyAsync(ctx->ps.ray_o, ho.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->ps.ray_d, hd.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
-  k_set_u32<<<1, 1, 0, st>>>(&ctx->d_counters->q_count[0], (uint32_t)n);
-  const Accel A = make_accel(ctx, false);
-  if (any) k_trace<true, true><<<trace_grid(ctx), kTraceThreads, stack_bytes(), st>>>(A, ctx->ps.ray_o, ctx->ps.ray_d, nullptr, &ctx->d_counters->q_count[0], &ctx->d_counters->work_extend[0], ctx->ps.hit, nullptr, nullptr, ctx->d_totals);
-  else k_trace<false, true><<<trace_grid(ctx), kTraceThreads, stack_bytes(), st>>>(A, ctx->ps.ray_o, ctx->ps.ray_d, nullptr, &ctx->d_counters->q_count[0], &ctx->d_counters->work_extend[0], ctx->ps.hit, nullptr, nullptr, ctx->d_totals);
+  CK(cudaMemsetAsync(D.d_counters, 0, sizeof(Counters), st));
+  CK(cudaMemsetAsync(D.d_totals, 0, sizeof(Totals), st));
+  CK(cudaMemcpyAsync(D.ps.ray_o, ho.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(D.ps.ray_d, hd.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
+  k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
+  const Accel A = make_accel(ctx, D, false);
+  if (any) k_trace<true, true><<<D.trace_blocks, kTraceThreads, stack_bytes(), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals);
+  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals);
   CK(cudaGetLastError());
   std::vector<float4> hits(n);
-  CK(cudaMemcpyAsync(hits.data(), ctx->ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   for (int64_t i = 0; i < n; i++) {
     int sl; std::memcpy(&sl, &hits[i].w, 4);
@@ -842,14 +923,15 @@ int dsrt_trace_any(dsrt_ctx* ctx, int64_t n, const float* o, const float* d, con
 
 int dsrt_tonemap(dsrt_ctx* ctx, const float* rgb, int64_t n_pixels, uint32_t* rgba8) {
   if (!ctx || !rgb || !rgba8 || n_pixels < 0) return DSRT_ERR_INVALID;
-  CK(cudaSetDevice(ctx->device));
+  DevState& D = ctx->devs[0];
+  CK(cudaSetDevice(D.device));
   float* d_in = nullptr; uint32_t* d_out = nullptr;
   CK(cudaMalloc((void**)&d_in, (size_t)n_pixels * 3 * sizeof(float) + 16));
   CK(cudaMalloc((void**)&d_out, (size_t)n_pixels * sizeof(uint32_t) + 16));
-  CK(cudaMemcpyAsync(d_in, rgb, (size_t)n_pixels * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  k_resolve<<<(unsigned)((n_pixels + 255) / 256), 256, 0, ctx->stream>>>(d_in, nullptr, d_out, (int)n_pixels, 1.0f);
-  CK(cudaMemcpyAsync(rgba8, d_out, (size_t)n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpyAsync(d_in, rgb, (size_t)n_pixels * 3 * sizeof(float), cudaMemcpyHostToDevice, D.stream));
+  k_resolve<<<(unsigned)((n_pixels + 255) / 256), 256, 0, D.stream>>>(d_in, nullptr, d_out, (int)n_pixels, 1.0f);
+  CK(cudaMemcpyAsync(rgba8, d_out, (size_t)n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream));
+  CK(cudaStreamSynchronize(D.stream));
   cudaFree(d_in); cudaFree(d_out);
   return DSRT_OK;
 }

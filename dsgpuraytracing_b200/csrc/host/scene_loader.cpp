@@ -217,22 +217,21 @@ struct Parser {
     out.clear(); out.reserve(n);
     if (!s) return n == 0;
     char* e = nullptr;
-    float last = 0;
+    bool failed = false;
     for (size_t i = 0; i < n; i++) {
-      float f = strtof(s, &e);
-      if (e == s) f = last;       // stringstream extraction failure leaves the variable unchanged (collada.cpp:633-635)
-      else s = e;
-      out.push_back(f); last = f;
+      float f = 0.f;              // a failed stream extraction stores 0 (C++11), and every later one fails too
+      if (!failed) { f = strtof(s, &e); if (e == s) { failed = true; f = 0.f; } else s = e; }
+      out.push_back(f);
     }
     return true;
   }
   static void read_sizes(const char* s, size_t n, std::vector<size_t>& out) {
     out.clear(); out.reserve(n);
-    char* e = nullptr; size_t last = 0;
+    char* e = nullptr; bool failed = (s == nullptr);
     for (size_t i = 0; i < n; i++) {
-      size_t v = last;
-      if (s) { unsigned long long u = strtoull(s, &e, 10); if (e != s) { v = (size_t)u; s = e; } }
-      out.push_back(v); last = v;
+      size_t v = 0;
+      if (!failed) { unsigned long long u = strtoull(s, &e, 10); if (e != s) { v = (size_t)u; s = e; } else failed = true; }
+      out.push_back(v);
     }
   }
 
@@ -301,9 +300,10 @@ struct Parser {
     for (XmlElement* e = xml->FirstChildElement(); e; e = e->NextSiblingElement()) {
       std::string name = e->Name();
       if (name == "matrix") {
-        std::vector<double> v; const char* s = e->GetText(); char* end = nullptr;
-        for (int i = 0; i < 16 && s; i++) { double d = strtod(s, &end); if (end == s) break; v.push_back(d); s = end; }
-        if (v.size() != 16) return fail("bad <matrix>");
+        // 16 stream extractions into a zero-initialised Matrix4x4; a short list leaves zeros (CBgems.dae's camera
+        // node has 15 numbers), collada.cpp:253-266
+        std::vector<double> v(16, 0.0); const char* s = e->GetText(); char* end = nullptr;
+        for (int i = 0; i < 16 && s; i++) { double d = strtod(s, &end); if (end == s) break; v[i] = d; s = end; }
         M4 mat; for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) mat.at(i, j) = v[i * 4 + j];
         node.transform = mat; break;
       }

@@ -81,6 +81,12 @@ typedef struct {
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */
 int dsrt_create(int device, dsrt_ctx** out);          /* replaces new CUDAPathTracer + init(), setup.cu:77-95,181-201 */
+/* One context driving several GPUs of one box from one process (the `pathtracer -g N` path): the scene is
+ * replicated, dsrt_render gives GPU r the samples k = r (mod N), and device 0 combines the partial framebuffers
+ * by reading its peers' memory over NVLink inside the resolve kernel.  (One process per GPU + one NCCL reduce,
+ * as bench.py does under torchrun, uses dsrt_create + dsrt_render_device instead.) */
+int dsrt_create_multi(int n_devices, const int* devices, dsrt_ctx** out);
+int dsrt_device_count(const dsrt_ctx* ctx);
 int dsrt_destroy(dsrt_ctx* ctx);                      /* replaces ~CUDAPathTracer, setup.cu:97-115 */
 const char* dsrt_last_error(const dsrt_ctx* ctx);     /* never NULL */
 const char* dsrt_version(void);

@@ -106,15 +106,20 @@ __global__ void k_generate_centres(PathState ps, RenderParams rp, int n_paths) {
   ps.ray_d[i] = make_float4(d.x, d.y, d.z, __int_as_float(-1));
 }
 
-// Persistent warps; a lane whose ray has finished waits until at most kRefill lanes of its warp are still
-// busy, then the warp fetches new rays for all idle lanes with one aggregated atomic (ballot + popc + shfl).
-constexpr int kRefillBusyLanes = 20;
+// Persistent warps, one ray per lane.
+//  * dynamic fetch: a lane whose ray has finished idles until at most `refill_busy` lanes of its warp are still
+//    busy, then the warp fetches new rays for ALL idle lanes with one aggregated atomic (ballot + popc + shfl);
+//  * postponed primitive tests: a node visit leaves each lane with a group of pending primitives.  Testing them
+//    at once would run the (long) primitive test with the few lanes that happen to have reached a leaf.  Instead
+//    a lane keeps its pending group (older groups go onto the stack) and the WARP tests primitives only when at
+//    least `tri_min` lanes have some pending, or when a lane has nothing else left to do -- so the primitive test
+//    executes with many lanes active.  tri_min = 0 restores test-at-once order (used by the counter tests).
 
 template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                          const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
                                                          uint32_t* work, float4* hit_out, const float4* __restrict__ contrib,
-                                                         float* accum, Totals* totals) {
+                                                         float* accum, Totals* totals, int tri_min, int refill_busy) {
   extern __shared__ uint2 smem_stack[];
   uint2* stack = smem_stack + threadIdx.x;
   const int stride = blockDim.x;
@@ -157,8 +162,15 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
 
     // ---- traverse until the warp is due for a refill
     while (true) {
+      bool done = false, did_node = false;
+      // (1) node step: open the highest-priority pending internal child, or take the next group off the stack
       if (busy) {
-        bool done = false;
+        uint2 tnew = make_uint2(0u, 0u);
+        if (ngroup.y <= 0x00ffffffu && sp > 0) {
+          sp--;
+          const uint2 e = stack[sp * stride];
+          if (e.y > 0x00ffffffu) ngroup = e; else tnew = e;          // node group / postponed primitive group
+        }
         if (ngroup.y > 0x00ffffffu) {
           const uint32_t bit = 31u - (uint32_t)__clz(ngroup.y);
           ngroup.y &= ~(1u << bit);
@@ -170,11 +182,20 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
           if (COUNT) cnt.nodes++;
           const uint32_t m = test_children<false>(ray, fr, n0, n1, n2, n3, n4, tbest, 0.f);
           ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
-          tgroup = make_uint2(n1.y, m & 0x00ffffffu);
-        } else {
-          tgroup = make_uint2(0u, 0u);
+          tnew = make_uint2(n1.y, m & 0x00ffffffu);
+          did_node = true;
         }
-        while (tgroup.y) {
+        if (tnew.y) {
+          if (tgroup.y) { stack[sp * stride] = tgroup; sp++; }        // keep the newest group in registers
+          tgroup = tnew;
+        }
+      }
+      // (2) primitive step, warp-wide decision
+      const bool pending = busy && tgroup.y != 0u;
+      const bool must = pending && !did_node;                          // this lane had no node to open: it needs its primitives now
+      const unsigned pm = __ballot_sync(kFull, pending);
+      if (pm && (__any_sync(kFull, must) || __popc(pm) >= tri_min)) {
+        while (pending && tgroup.y) {
           const uint32_t k = 31u - (uint32_t)__clz(tgroup.y);
           tgroup.y &= ~(1u << k);
           const int slot = (int)(tgroup.x + k);
@@ -193,12 +214,12 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
             if (ANY) { done = true; break; }
           }
         }
-        if (!done && ngroup.y <= 0x00ffffffu) {
-          if (sp == 0) done = true;
-          else { sp--; ngroup = stack[sp * stride]; }
-        }
+      }
+      // (3) retire finished rays
+      if (busy) {
+        if (!done && ngroup.y <= 0x00ffffffu && sp == 0 && tgroup.y == 0u) done = true;
         if (done) {
-          busy = false;
+          busy = false; tgroup.y = 0u; ngroup.y = 0u; sp = 0;
           if (ANY) {
             if (hit_out) hit_out[item] = make_float4(hit.t, 0.f, 0.f, __int_as_float(hit.slot));
             if (accum && hit.slot < 0) {       // unoccluded: add this light sample's contribution
@@ -214,7 +235,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
         }
       }
       const int nbusy = __popc(__ballot_sync(kFull, busy));
-      if (nbusy == 0 || (!exhausted && nbusy <= kRefillBusyLanes)) break;
+      if (nbusy == 0 || (!exhausted && nbusy <= refill_busy)) break;
     }
   }
   if (COUNT) {
@@ -381,7 +402,7 @@ struct dsrt_ctx {
   Camera cam{};
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
-  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20;
   WideBVH wide;
   double scene_diag = 1.0;
   int n_lights = 0, n_light_samples = 0;
@@ -413,7 +434,8 @@ Accel make_accel(const dsrt_ctx* ctx, const DevState& D, bool parity) {
   return A;
 }
 
-size_t stack_bytes() { return (size_t)kStackEntries * kTraceThreads * sizeof(uint2); }
+// shared-memory traversal stack: two entries (node group + postponed primitive group) per wide-BVH level per lane (whatever is not used stays L1 cache)
+size_t stack_bytes(const dsrt_ctx* ctx) { return (size_t)(2 * std::max(ctx->wide.max_depth, 1) + 2) * kTraceThreads * sizeof(uint2); }
 
 int init_device(dsrt_ctx* ctx, DevState& D, int device) {
   D.device = device;
@@ -424,10 +446,6 @@ int init_device(dsrt_ctx* ctx, DevState& D, int device) {
   D.sm_count = prop.multiProcessorCount;
   CK(cudaMalloc((void**)&D.d_totals, sizeof(Totals)));
   CK(cudaEventCreate(&D.ev_begin)); CK(cudaEventCreate(&D.ev_end));
-  // persistent grid = resident CTAs per SM (registers / shared-memory stack) x SM count
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<false, false>, kTraceThreads, stack_bytes()));
-  D.trace_blocks = D.sm_count * std::max(per_sm, 1);
   return DSRT_OK;
 }
 
@@ -592,6 +610,8 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
   else if (n == "batch_spp") ctx->opt_batch_spp = value;
   else if (n == "stage_timing") ctx->opt_stage_timing = value;
   else if (n == "skip_null_shadow") ctx->opt_skip_null = value;
+  else if (n == "postpone_min_lanes") ctx->opt_tri_min = value;
+  else if (n == "refill_busy_lanes") ctx->opt_refill = value;
   else return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_option: unknown option " + n);
   return DSRT_OK;
 }
@@ -635,7 +655,13 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
     CK(up(&D.d_bsdf, ctx->bsdfs.data(), ctx->bsdfs.size() * sizeof(Bsdf)));
     CK(up(&D.d_lights, lights.data(), lights.size() * sizeof(Light)));
   }
-  for (DevState& D : ctx->devs) { CK(cudaSetDevice(D.device)); CK(cudaStreamSynchronize(D.stream)); }
+  for (DevState& D : ctx->devs) {
+    CK(cudaSetDevice(D.device)); CK(cudaStreamSynchronize(D.stream));
+    // persistent grid = resident CTAs per SM (registers / shared-memory stack) x SM count
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, false>, kTraceThreads, stack_bytes(ctx)));
+    D.trace_blocks = D.sm_count * std::max(per_sm, 1);
+  }
   ctx->have_accel = true;
   return DSRT_OK;
 }
@@ -683,7 +709,8 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   const Accel A = make_accel(ctx, D, false);
   const bool count = ctx->opt_count != 0, timing = ctx->opt_stage_timing != 0;
   const int tgrid = D.trace_blocks;
-  const size_t sbytes = stack_bytes();
+  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill;
+  const size_t sbytes = stack_bytes(ctx);
 
   auto span_begin = [&](int kind) { if (timing) { DevState::Span s; s.kind = kind; s.e0 = D.ev_used; cudaEventRecord(next_event(D), st); s.e1 = 0; D.spans.push_back(s); } };
   auto span_end = [&]() { if (timing) { D.spans.back().e1 = D.ev_used; cudaEventRecord(next_event(D), st); } };
@@ -701,8 +728,8 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
     for (int d = 0; d <= ctx->max_depth; d++) {
       const uint32_t* q = (d == 0 && aligned) ? nullptr : D.queue[cur];
       span_begin(0);
-      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals);
-      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals);
+      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy);
+      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy);
       span_end();
       // depth 0 shades every path; deeper levels only shrink, so a capped grid-stride launch is enough
       const int bound = d == 0 ? n_paths : std::min(n_paths, D.sm_count * 16 * 128);
@@ -712,8 +739,8 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
       span_end();
       if (nls > 0) {
         span_begin(1);
-        if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals);
-        else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals);
+        if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals, tri_min, refill_busy);
+        else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals, tri_min, refill_busy);
         span_end();
         D.launches++;
       }
@@ -850,7 +877,7 @@ int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) 
     CK(cudaMalloc((void**)&d_slot, n * sizeof(int32_t)));
     CK(cudaMalloc((void**)&d_t, n * sizeof(double)));
     CK(cudaMemcpyAsync(d_rays, rays.data(), rays.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    k_primary_parity<<<(n + kTraceThreads - 1) / kTraceThreads, kTraceThreads, stack_bytes(), st>>>(make_accel(ctx, D, true), d_rays, n, d_slot, d_t);
+    k_primary_parity<<<(n + kTraceThreads - 1) / kTraceThreads, kTraceThreads, stack_bytes(ctx), st>>>(make_accel(ctx, D, true), d_rays, n, d_slot, d_t);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(slots.data(), d_slot, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ts.data(), d_t, n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -862,10 +889,11 @@ int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) 
     if (D.n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &D.d_counters, (size_t)1))) return rc; D.n_counter_blocks = 1; }
     CK(cudaMemsetAsync(D.d_counters, 0, sizeof(Counters), st));
     RenderParams rp; std::memset(&rp, 0, sizeof(rp)); rp.cam = ctx->cam;
+    const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill;
     k_generate_centres<<<(n + 255) / 256, 256, 0, st>>>(D.ps, rp, n);
     k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
-    k_trace<false, false><<<D.trace_blocks, kTraceThreads, stack_bytes(), st>>>(make_accel(ctx, D, false), D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0],
-                                                                            &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals);
+    k_trace<false, false><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(make_accel(ctx, D, false), D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0],
+                                                                            &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy);
     CK(cudaGetLastError());
     std::vector<float4> hits(n);
     CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
@@ -898,8 +926,9 @@ static int trace_batch(dsrt_ctx* ctx, bool any, int64_t n, const float* o, const
   CK(cudaMemcpyAsync(D.ps.ray_d, hd.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
   k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
   const Accel A = make_accel(ctx, D, false);
-  if (any) k_trace<true, true><<<D.trace_blocks, kTraceThreads, stack_bytes(), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals);
-  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals);
+  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill;
+  if (any) k_trace<true, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy);
+  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy);
   CK(cudaGetLastError());
   std::vector<float4> hits(n);
   CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));

@@ -21,7 +21,8 @@
 
 namespace dsrt {
 
-constexpr int kStackEntries = 32;    // >= levels of wide nodes (checked at dsrt_build_accel)
+constexpr int kStackEntries = 32;    // upper bound on the levels of wide nodes (checked at dsrt_build_accel); the
+                                     // kernels get exactly wide.max_depth entries of shared memory per lane
 
 
 struct TraceRay {
@@ -164,7 +165,9 @@ DSRT_HD bool hit_sphere64(const Ray64& r, const double* __restrict__ p, double t
 // ---- node test -----------------------------------------------------------------------------------------------
 struct NodeFrame {   // per-ray constants
   float idx, idy, idz;   // reciprocal direction (clamped away from 0)
-  uint32_t octinv;       // 7 - octant, replicated in the low 3 bits
+  uint32_t octinv;       // 7 - octant
+  uint32_t octinv4;      // octinv replicated into the four bytes
+  bool nx, ny, nz;       // direction component is negative: the near plane of a slab is its HIGH plane
 };
 
 DSRT_HD NodeFrame make_frame(const TraceRay& r) {
@@ -174,30 +177,46 @@ DSRT_HD NodeFrame make_frame(const TraceRay& r) {
   const float dy = fabsf(r.dy) > eps ? r.dy : copysignf(eps, r.dy);
   const float dz = fabsf(r.dz) > eps ? r.dz : copysignf(eps, r.dz);
   f.idx = 1.0f / dx; f.idy = 1.0f / dy; f.idz = 1.0f / dz;
-  const uint32_t oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+  f.nx = dx < 0.0f; f.ny = dy < 0.0f; f.nz = dz < 0.0f;
+  const uint32_t oct = (f.nx ? 1u : 0u) | (f.ny ? 2u : 0u) | (f.nz ? 4u : 0u);
   f.octinv = 7u - oct;
+  f.octinv4 = f.octinv * 0x01010101u;
   return f;
 }
 
-DSRT_HD float byte_f(uint32_t w, int i) { return (float)((w >> (8 * i)) & 0xffu); }
+// byte i of w -> the float 1 + q * 2^-15 (q placed in mantissa bits 8..15 by ONE byte-permute, no int->float
+// conversion on the XU pipe).  The node test then evaluates plane = fma(1 + q 2^-15, 2^15 s, b - 2^15 s) = q s + b.
+DSRT_HD float byte_unit(uint32_t w, int i) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(__byte_perm(w, 0x3f800000u, 0x7604u | ((uint32_t)i << 4)));
+#else
+  return hd_u2f(0x3f800000u | (((w >> (8 * i)) & 0xffu) << 8));
+#endif
+}
 
 // Tests the 8 quantised child boxes of one node; returns the 32-bit hit mask (31..24 internal children in
-// visiting priority, 23..0 primitives).  pad > 0 only in parity mode.
+// visiting priority, 23..0 primitives).  Near / far planes are picked per axis from the ray's sign (no per-child
+// min/max); far planes are scaled by 1 + 4e-7 so float rounding can only widen a box; empty slots need no test
+// because their meta byte contributes no bits.  pad > 0 only in parity mode (conservative slabs).
 template <bool PARITY>
 DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uint4 n0, const uint4 n1,
                                                   const uint4 n2, const uint4 n3, const uint4 n4, float tmax, float pad) {
   const float ox = hd_u2f(n0.x), oy = hd_u2f(n0.y), oz = hd_u2f(n0.z);
-  const float sx = hd_u2f((n0.w & 0xffu) << 23) * fr.idx;
-  const float sy = hd_u2f(((n0.w >> 8) & 0xffu) << 23) * fr.idy;
-  const float sz = hd_u2f(((n0.w >> 16) & 0xffu) << 23) * fr.idz;
-  float blx, bly, blz, bhx, bhy, bhz;
+  // 2^15 * 2^(e-127) * idir: the exponent byte is biased up by 15 instead of multiplying
+  const float sx = hd_u2f(((n0.w & 0xffu) + 15u) << 23) * fr.idx;
+  const float sy = hd_u2f((((n0.w >> 8) & 0xffu) + 15u) << 23) * fr.idy;
+  const float sz = hd_u2f((((n0.w >> 16) & 0xffu) + 15u) << 23) * fr.idz;
+  const float k = PARITY ? 1.0001f : 1.0000004f;
+  float bnx, bny, bnz, bfx, bfy, bfz;
   if (PARITY) {
-    blx = (ox - pad - r.ox) * fr.idx; bhx = (ox + pad - r.ox) * fr.idx;
-    bly = (oy - pad - r.oy) * fr.idy; bhy = (oy + pad - r.oy) * fr.idy;
-    blz = (oz - pad - r.oz) * fr.idz; bhz = (oz + pad - r.oz) * fr.idz;
+    bnx = ((fr.nx ? ox + pad : ox - pad) - r.ox) * fr.idx - sx; bfx = (((fr.nx ? ox - pad : ox + pad) - r.ox) * fr.idx - sx) * k + pad;
+    bny = ((fr.ny ? oy + pad : oy - pad) - r.oy) * fr.idy - sy; bfy = (((fr.ny ? oy - pad : oy + pad) - r.oy) * fr.idy - sy) * k + pad;
+    bnz = ((fr.nz ? oz + pad : oz - pad) - r.oz) * fr.idz - sz; bfz = (((fr.nz ? oz - pad : oz + pad) - r.oz) * fr.idz - sz) * k + pad;
   } else {
-    blx = bhx = (ox - r.ox) * fr.idx; bly = bhy = (oy - r.oy) * fr.idy; blz = bhz = (oz - r.oz) * fr.idz;
+    bnx = (ox - r.ox) * fr.idx - sx; bny = (oy - r.oy) * fr.idy - sy; bnz = (oz - r.oz) * fr.idz - sz;
+    bfx = bnx * k; bfy = bny * k; bfz = bnz * k;
   }
+  const float sfx = sx * k, sfy = sy * k, sfz = sz * k;
   uint32_t mask = 0;
 #pragma unroll
   for (int half = 0; half < 2; half++) {
@@ -205,20 +224,22 @@ DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uin
     const uint32_t qlx = half ? n2.y : n2.x, qly = half ? n2.w : n2.z;
     const uint32_t qlz = half ? n3.y : n3.x, qhx = half ? n3.w : n3.z;
     const uint32_t qhy = half ? n4.y : n4.x, qhz = half ? n4.w : n4.z;
+    const uint32_t nearx = fr.nx ? qhx : qlx, farx = fr.nx ? qlx : qhx;
+    const uint32_t neary = fr.ny ? qhy : qly, fary = fr.ny ? qly : qhy;
+    const uint32_t nearz = fr.nz ? qhz : qlz, farz = fr.nz ? qlz : qhz;
+    // per-child bit index (internal children: visiting priority (24 + slot) ^ octinv) and unary count, 4 at a time
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
+    const uint32_t bit_index4 = (meta4 ^ (fr.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const uint32_t meta = (meta4 >> (8 * i)) & 0xffu;
-      const float ax = hd_fma(byte_f(qlx, i), sx, blx), bx = hd_fma(byte_f(qhx, i), sx, bhx);
-      const float ay = hd_fma(byte_f(qly, i), sy, bly), by = hd_fma(byte_f(qhy, i), sy, bhy);
-      const float az = hd_fma(byte_f(qlz, i), sz, blz), bz = hd_fma(byte_f(qhz, i), sz, bhz);
-      const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-      float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
-      tf = PARITY ? tf * 1.0001f + pad : tf * 1.0000004f;   // conservative against float rounding
-      if (meta != 0u && tn <= tf) {
-        const bool inner = (meta & 0xe0u) == 0x20u && (meta & 0x18u) == 0x18u;
-        const uint32_t bit = inner ? ((meta & 31u) ^ fr.octinv) : (meta & 31u);
-        mask |= (meta >> 5) << bit;
-      }
+      const float ax = hd_fma(byte_unit(nearx, i), sx, bnx), bx = hd_fma(byte_unit(farx, i), sfx, bfx);
+      const float ay = hd_fma(byte_unit(neary, i), sy, bny), by = hd_fma(byte_unit(fary, i), sfy, bfy);
+      const float az = hd_fma(byte_unit(nearz, i), sz, bnz), bz = hd_fma(byte_unit(farz, i), sfz, bfz);
+      const float tn = fmaxf(fmaxf(ax, ay), fmaxf(az, 0.0f));
+      const float tf = fminf(fminf(bx, by), fminf(bz, tmax));
+      if (tn <= tf) mask |= ((child_bits4 >> (8 * i)) & 0xffu) << ((bit_index4 >> (8 * i)) & 0xffu);
     }
   }
   return mask;

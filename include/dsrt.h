@@ -101,7 +101,8 @@ int dsrt_set_camera(dsrt_ctx* ctx, const double* pos, const double* c2w, int32_t
 /* ns_aa (-s), ns_area_light (-l), max_ray_depth (-m); replaces loadParameters, setup.cu:777-811 */
 int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t max_ray_depth, uint32_t seed);
 /* named knobs: "count_traversal" (0/1), "batch_spp" (camera samples per pixel per wavefront batch),
- * "stage_timing" (0/1: per-stage CUDA events) */
+ * "stage_timing" (0/1: per-stage CUDA events), "postpone_min_lanes" (primitive tests wait until this many lanes
+ * of a warp have some pending; 0 = test at once; default 12) */
 int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value);
 
 /* Host SAH builder = BVHAccel::BVHAccel + buildBVH (src/bvh.cpp:21-202: 32 buckets, max leaf 4, with the

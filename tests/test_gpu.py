@@ -177,14 +177,21 @@ def test_arbitrary_rays_closest_any_and_fetch_counters(name, core, golden):
     wid, wt, wcnt = w.trace(o, d)
     assert (wid != ids).sum() <= 2
     core.set_option("count_traversal", 1)
+    core.set_option("postpone_min_lanes", 0)          # test primitives at once: the order the CPU walk uses
     core.set_params(1, 4, 0, 0)
     # counters of a full render == CPU walk counters of the same wavefront (same code, same rays)
     cam = g["small_camera"]; core.set_camera(cam)
     rgb, st = core.render()
     wr, wc = Walk(g, D.build_bvh2(g), 4, camera=cam).render(1, 0, seed=0)
-    core.set_option("count_traversal", 0)
     assert abs(int(st.nodes_visited) - int(wc[3])) <= 2e-3 * wc[3]
     assert abs(int(st.prims_tested) - int(wc[4])) <= 2e-3 * wc[4]
+    # postponed primitive tests (the default) change the visiting order, never the result
+    core.set_option("postpone_min_lanes", 12)
+    rgb2, st2 = core.render()
+    core.set_option("count_traversal", 0)
+    assert st2.extend_rays == st.extend_rays and st2.shadow_rays == st.shadow_rays
+    assert np.allclose(rgb2, rgb, rtol=1e-4, atol=1e-6)
+    assert st2.nodes_visited >= st.nodes_visited * 0.98 and st2.nodes_visited < st.nodes_visited * 1.5
 
 
 def test_tonemap_matches_toColor(core):

@@ -119,7 +119,7 @@ template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                          const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
                                                          uint32_t* work, float4* hit_out, const float4* __restrict__ contrib,
-                                                         float* accum, Totals* totals, int tri_min, int refill_busy) {
+                                                         float* accum, Totals* totals, int tri_min, int refill_busy, int wait_mode) {
   extern __shared__ uint2 smem_stack[];
   uint2* stack = smem_stack + threadIdx.x;
   const int stride = blockDim.x;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
           const uint4* np = A.nodes + (size_t)(ngroup.x + rel) * 5;
           const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
           if (COUNT) cnt.nodes++;
-          const uint32_t m = test_children<false>(ray, fr, n0, n1, n2, n3, n4, tbest, 0.f);
+          const uint32_t m = test_children<false>(ray, fr, n0, n1, n2, n3, n4, tbest, 0.f, A.one_bits);
           ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
           tnew = make_uint2(n1.y, m & 0x00ffffffu);
           did_node = true;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
       const bool pending = busy && tgroup.y != 0u;
       const bool must = pending && !did_node;                          // this lane had no node to open: it needs its primitives now
       const unsigned pm = __ballot_sync(kFull, pending);
-      if (pm && (__any_sync(kFull, must) || __popc(pm) >= tri_min)) {
+      if (pm && ((wait_mode ? !__any_sync(kFull, did_node) : __any_sync(kFull, must)) || __popc(pm) >= tri_min)) {
         while (pending && tgroup.y) {
           const uint32_t k = 31u - (uint32_t)__clz(tgroup.y);
           tgroup.y &= ~(1u << k);
@@ -402,7 +402,7 @@ struct dsrt_ctx {
   Camera cam{};
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
-  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20, opt_wait_mode = 0;
   WideBVH wide;
   double scene_diag = 1.0;
   int n_lights = 0, n_light_samples = 0;
@@ -431,6 +431,7 @@ Accel make_accel(const dsrt_ctx* ctx, const DevState& D, bool parity) {
   A.nodes = (const uint4*)D.d_nodes; A.prims = (const float4*)D.d_prims;
   A.prims64 = (const double*)D.d_prims64;
   A.pad = parity ? (float)(1e-5 * ctx->scene_diag) : 0.f;
+  A.one_bits = 0x3f800000u;
   return A;
 }
 
@@ -612,6 +613,7 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
   else if (n == "skip_null_shadow") ctx->opt_skip_null = value;
   else if (n == "postpone_min_lanes") ctx->opt_tri_min = value;
   else if (n == "refill_busy_lanes") ctx->opt_refill = value;
+  else if (n == "postpone_wait_mode") ctx->opt_wait_mode = value;
   else return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_option: unknown option " + n);
   return DSRT_OK;
 }
@@ -709,7 +711,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   const Accel A = make_accel(ctx, D, false);
   const bool count = ctx->opt_count != 0, timing = ctx->opt_stage_timing != 0;
   const int tgrid = D.trace_blocks;
-  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill;
+  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode;
   const size_t sbytes = stack_bytes(ctx);
 
   auto span_begin = [&](int kind) { if (timing) { DevState::Span s; s.kind = kind; s.e0 = D.ev_used; cudaEventRecord(next_event(D), st); s.e1 = 0; D.spans.push_back(s); } };
@@ -728,8 +730,8 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
     for (int d = 0; d <= ctx->max_depth; d++) {
       const uint32_t* q = (d == 0 && aligned) ? nullptr : D.queue[cur];
       span_begin(0);
-      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy);
-      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy);
+      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode);
+      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode);
       span_end();
       // depth 0 shades every path; deeper levels only shrink, so a capped grid-stride launch is enough
       const int bound = d == 0 ? n_paths : std::min(n_paths, D.sm_count * 16 * 128);
@@ -739,8 +741,8 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
       span_end();
       if (nls > 0) {
         span_begin(1);
-        if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals, tri_min, refill_busy);
-        else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals, tri_min, refill_busy);
+        if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals, tri_min, refill_busy, wait_mode);
+        else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals, tri_min, refill_busy, wait_mode);
         span_end();
         D.launches++;
       }
@@ -889,11 +891,11 @@ int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) 
     if (D.n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &D.d_counters, (size_t)1))) return rc; D.n_counter_blocks = 1; }
     CK(cudaMemsetAsync(D.d_counters, 0, sizeof(Counters), st));
     RenderParams rp; std::memset(&rp, 0, sizeof(rp)); rp.cam = ctx->cam;
-    const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill;
+    const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode;
     k_generate_centres<<<(n + 255) / 256, 256, 0, st>>>(D.ps, rp, n);
     k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
     k_trace<false, false><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(make_accel(ctx, D, false), D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0],
-                                                                            &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy);
+                                                                            &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode);
     CK(cudaGetLastError());
     std::vector<float4> hits(n);
     CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
@@ -926,9 +928,9 @@ static int trace_batch(dsrt_ctx* ctx, bool any, int64_t n, const float* o, const
   CK(cudaMemcpyAsync(D.ps.ray_d, hd.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
   k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
   const Accel A = make_accel(ctx, D, false);
-  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill;
-  if (any) k_trace<true, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy);
-  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy);
+  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode;
+  if (any) k_trace<true, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode);
+  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode);
   CK(cudaGetLastError());
   std::vector<float4> hits(n);
   CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));

@@ -39,36 +39,39 @@ struct TraceCounters { uint32_t nodes, prims; };
 // double-precision ray for the parity kernel
 struct Ray64 { double ox, oy, oz, dx, dy, dz; };
 
-DSRT_HD float sel3(int k, float x, float y, float z) { return k == 0 ? x : (k == 1 ? y : z); }
-
 // ---- production primitive tests -------------------------------------------------------------------------
-struct WatertightRay { int kx, ky, kz; float Sx, Sy, Sz; };
+// Watertight ray/triangle test (Woop, Benthin, Wald 2013).  The per-ray shear + axis permutation
+//   Ax = A[kx] - Sx*A[kz],  Ay = A[ky] - Sy*A[kz],  Az = Sz*A[kz]
+// is folded into three per-ray vectors bx, by, bz (entries 1, -Sx | -Sy, 0 / Sz in permuted positions), so a
+// vertex is mapped to ray space with three dot products and the test is free of data-dependent selects
+// (which the compiler turns into divergent branches).
+struct WatertightRay { float bxx, bxy, bxz, byx, byy, byz, bzx, bzy, bzz; };
 
 DSRT_HD WatertightRay make_watertight(const TraceRay& r) {
-  WatertightRay w;
   const float ax = fabsf(r.dx), ay = fabsf(r.dy), az = fabsf(r.dz);
-  w.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
-  w.kx = w.kz + 1; if (w.kx == 3) w.kx = 0;
-  w.ky = w.kx + 1; if (w.ky == 3) w.ky = 0;
-  const float dz = sel3(w.kz, r.dx, r.dy, r.dz);
-  if (dz < 0.0f) { int t = w.kx; w.kx = w.ky; w.ky = t; }   // preserve winding
-  const float dx = sel3(w.kx, r.dx, r.dy, r.dz), dy = sel3(w.ky, r.dx, r.dy, r.dz);
-  w.Sz = 1.0f / dz;
-  w.Sx = dx * w.Sz;
-  w.Sy = dy * w.Sz;
+  int kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+  int kx = kz + 1; if (kx == 3) kx = 0;
+  int ky = kx + 1; if (ky == 3) ky = 0;
+  const float dz = kz == 0 ? r.dx : (kz == 1 ? r.dy : r.dz);
+  if (dz < 0.0f) { int t = kx; kx = ky; ky = t; }   // preserve winding
+  const float dx = kx == 0 ? r.dx : (kx == 1 ? r.dy : r.dz), dy = ky == 0 ? r.dx : (ky == 1 ? r.dy : r.dz);
+  const float Sz = 1.0f / dz, Sx = dx * Sz, Sy = dy * Sz;
+  WatertightRay w;
+  w.bxx = (kx == 0 ? 1.0f : 0.0f) - (kz == 0 ? Sx : 0.0f); w.bxy = (kx == 1 ? 1.0f : 0.0f) - (kz == 1 ? Sx : 0.0f); w.bxz = (kx == 2 ? 1.0f : 0.0f) - (kz == 2 ? Sx : 0.0f);
+  w.byx = (ky == 0 ? 1.0f : 0.0f) - (kz == 0 ? Sy : 0.0f); w.byy = (ky == 1 ? 1.0f : 0.0f) - (kz == 1 ? Sy : 0.0f); w.byz = (ky == 2 ? 1.0f : 0.0f) - (kz == 2 ? Sy : 0.0f);
+  w.bzx = kz == 0 ? Sz : 0.0f; w.bzy = kz == 1 ? Sz : 0.0f; w.bzz = kz == 2 ? Sz : 0.0f;
   return w;
 }
 
 // returns true and updates (t,u,v) when the triangle is hit in (0, tmax)
 DSRT_HD bool hit_triangle(const TraceRay& r, const WatertightRay& w, const float4 a, const float4 b,
                                              const float4 c, float tmax, float& t_out, float& u_out, float& v_out) {
-  const float Ax0 = a.x - r.ox, Ay0 = a.y - r.oy, Az0 = a.z - r.oz;
-  const float Bx0 = b.x - r.ox, By0 = b.y - r.oy, Bz0 = b.z - r.oz;
-  const float Cx0 = c.x - r.ox, Cy0 = c.y - r.oy, Cz0 = c.z - r.oz;
-  const float Akz = sel3(w.kz, Ax0, Ay0, Az0), Bkz = sel3(w.kz, Bx0, By0, Bz0), Ckz = sel3(w.kz, Cx0, Cy0, Cz0);
-  const float Ax = hd_fma(-w.Sx, Akz, sel3(w.kx, Ax0, Ay0, Az0)), Ay = hd_fma(-w.Sy, Akz, sel3(w.ky, Ax0, Ay0, Az0));
-  const float Bx = hd_fma(-w.Sx, Bkz, sel3(w.kx, Bx0, By0, Bz0)), By = hd_fma(-w.Sy, Bkz, sel3(w.ky, Bx0, By0, Bz0));
-  const float Cx = hd_fma(-w.Sx, Ckz, sel3(w.kx, Cx0, Cy0, Cz0)), Cy = hd_fma(-w.Sy, Ckz, sel3(w.ky, Cx0, Cy0, Cz0));
+  const float A0 = a.x - r.ox, A1 = a.y - r.oy, A2 = a.z - r.oz;
+  const float B0 = b.x - r.ox, B1 = b.y - r.oy, B2 = b.z - r.oz;
+  const float C0 = c.x - r.ox, C1 = c.y - r.oy, C2 = c.z - r.oz;
+  const float Ax = hd_fma(A2, w.bxz, hd_fma(A1, w.bxy, A0 * w.bxx)), Ay = hd_fma(A2, w.byz, hd_fma(A1, w.byy, A0 * w.byx));
+  const float Bx = hd_fma(B2, w.bxz, hd_fma(B1, w.bxy, B0 * w.bxx)), By = hd_fma(B2, w.byz, hd_fma(B1, w.byy, B0 * w.byx));
+  const float Cx = hd_fma(C2, w.bxz, hd_fma(C1, w.bxy, C0 * w.bxx)), Cy = hd_fma(C2, w.byz, hd_fma(C1, w.byy, C0 * w.byx));
   // edge functions: products rounded separately, so swapping the two vertices of a shared edge negates the
   // value exactly (no cracks between adjacent triangles)
   float U = hd_sub(hd_mul(Cx, By), hd_mul(Cy, Bx));
@@ -79,10 +82,12 @@ DSRT_HD bool hit_triangle(const TraceRay& r, const WatertightRay& w, const float
     V = (float)hd_dsub(hd_dmul((double)Ax, (double)Cy), hd_dmul((double)Ay, (double)Cx));
     W = (float)hd_dsub(hd_dmul((double)Bx, (double)Ay), hd_dmul((double)By, (double)Ax));
   }
-  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  if (fminf(fminf(U, V), W) < 0.0f && fmaxf(fmaxf(U, V), W) > 0.0f) return false;
   const float det = U + V + W;
   if (det == 0.0f) return false;
-  const float Az = w.Sz * Akz, Bz = w.Sz * Bkz, Cz = w.Sz * Ckz;
+  const float Az = hd_fma(A2, w.bzz, hd_fma(A1, w.bzy, A0 * w.bzx));
+  const float Bz = hd_fma(B2, w.bzz, hd_fma(B1, w.bzy, B0 * w.bzx));
+  const float Cz = hd_fma(C2, w.bzz, hd_fma(C1, w.bzy, C0 * w.bzx));
   const float T = U * Az + V * Bz + W * Cz;
   const float rdet = 1.0f / det;
   const float t = T * rdet;
@@ -186,11 +191,13 @@ DSRT_HD NodeFrame make_frame(const TraceRay& r) {
 
 // byte i of w -> the float 1 + q * 2^-15 (q placed in mantissa bits 8..15 by ONE byte-permute, no int->float
 // conversion on the XU pipe).  The node test then evaluates plane = fma(1 + q 2^-15, 2^15 s, b - 2^15 s) = q s + b.
-DSRT_HD float byte_unit(uint32_t w, int i) {
+// `one` is 0x3f800000 handed in through the kernel parameters: kept out of the instruction's single immediate
+// slot so that the byte selector can be the immediate (otherwise every PRMT costs an extra register move).
+DSRT_HD float byte_unit(uint32_t w, int i, uint32_t one) {
 #ifdef __CUDA_ARCH__
-  return __uint_as_float(__byte_perm(w, 0x3f800000u, 0x7604u | ((uint32_t)i << 4)));
+  return __uint_as_float(__byte_perm(w, one, 0x7604u | ((uint32_t)i << 4)));
 #else
-  return hd_u2f(0x3f800000u | (((w >> (8 * i)) & 0xffu) << 8));
+  return hd_u2f(one | (((w >> (8 * i)) & 0xffu) << 8));
 #endif
 }
 
@@ -200,7 +207,7 @@ DSRT_HD float byte_unit(uint32_t w, int i) {
 // because their meta byte contributes no bits.  pad > 0 only in parity mode (conservative slabs).
 template <bool PARITY>
 DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uint4 n0, const uint4 n1,
-                                                  const uint4 n2, const uint4 n3, const uint4 n4, float tmax, float pad) {
+                                                  const uint4 n2, const uint4 n3, const uint4 n4, float tmax, float pad, uint32_t one) {
   const float ox = hd_u2f(n0.x), oy = hd_u2f(n0.y), oz = hd_u2f(n0.z);
   // 2^15 * 2^(e-127) * idir: the exponent byte is biased up by 15 instead of multiplying
   const float sx = hd_u2f(((n0.w & 0xffu) + 15u) << 23) * fr.idx;
@@ -234,9 +241,9 @@ DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uin
     const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const float ax = hd_fma(byte_unit(nearx, i), sx, bnx), bx = hd_fma(byte_unit(farx, i), sfx, bfx);
-      const float ay = hd_fma(byte_unit(neary, i), sy, bny), by = hd_fma(byte_unit(fary, i), sfy, bfy);
-      const float az = hd_fma(byte_unit(nearz, i), sz, bnz), bz = hd_fma(byte_unit(farz, i), sfz, bfz);
+      const float ax = hd_fma(byte_unit(nearx, i, one), sx, bnx), bx = hd_fma(byte_unit(farx, i, one), sfx, bfx);
+      const float ay = hd_fma(byte_unit(neary, i, one), sy, bny), by = hd_fma(byte_unit(fary, i, one), sfy, bfy);
+      const float az = hd_fma(byte_unit(nearz, i, one), sz, bnz), bz = hd_fma(byte_unit(farz, i, one), sfz, bfz);
       const float tn = fmaxf(fmaxf(ax, ay), fmaxf(az, 0.0f));
       const float tf = fminf(fminf(bx, by), fminf(bz, tmax));
       if (tn <= tf) mask |= ((child_bits4 >> (8 * i)) & 0xffu) << ((bit_index4 >> (8 * i)) & 0xffu);
@@ -253,6 +260,7 @@ struct Accel {
   const float4* __restrict__ prims;        // 3 float4 per slot
   const double* __restrict__ prims64;      // 12 doubles per slot (parity only)
   float pad;                               // parity slab padding
+  uint32_t one_bits;                       // 0x3f800000, see byte_unit()
 };
 
 template <bool ANY, bool PARITY, bool COUNT>
@@ -276,7 +284,7 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
       const uint4* np = A.nodes + (size_t)(ngroup.x + rel) * 5;
       const uint4 n0 = hd_ldg(np), n1 = hd_ldg(np + 1), n2 = hd_ldg(np + 2), n3 = hd_ldg(np + 3), n4 = hd_ldg(np + 4);
       if (COUNT) cnt->nodes++;
-      const uint32_t m = test_children<PARITY>(ray, fr, n0, n1, n2, n3, n4, tbest, A.pad);
+      const uint32_t m = test_children<PARITY>(ray, fr, n0, n1, n2, n3, n4, tbest, A.pad, A.one_bits);
       ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
       tgroup = make_uint2(n1.y, m & 0x00ffffffu);
     } else {

@@ -31,7 +31,7 @@ struct Walk {
 
 static Accel accel_of(const Walk* w, bool parity) {
   Accel A; A.nodes = (const uint4*)w->wide.nodes.data(); A.prims = (const float4*)w->recs.data();
-  A.prims64 = (const double*)w->r64.data(); A.pad = parity ? (float)(1e-5 * w->scene_diag) : 0.f;
+  A.prims64 = (const double*)w->r64.data(); A.pad = parity ? (float)(1e-5 * w->scene_diag) : 0.f; A.one_bits = 0x3f800000u;
   return A;
 }
 

@@ -119,7 +119,7 @@ template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                          const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
                                                          uint32_t* work, float4* hit_out, const float4* __restrict__ contrib,
-                                                         float* accum, Totals* totals, int tri_min, int refill_busy, int wait_mode) {
+                                                         float* accum, Totals* totals, int tri_min, int refill_busy, int wait_mode, int tri_cap) {
   extern __shared__ uint2 smem_stack[];
   uint2* stack = smem_stack + threadIdx.x;
   const int stride = blockDim.x;
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
   bool busy = false, exhausted = false;
   uint32_t item = 0;
   TraceRay ray; NodeFrame fr; WatertightRay wr;
-  float tbest = 0.f; TraceHit hit; int sp = 0;
+  float tbest = 0.f; TraceHit hit; int sp = 0, tstk = 0;   // tstk = postponed primitive groups currently on the stack
   uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
   hit.slot = -1; hit.t = 0.f; hit.u = 0.f; hit.v = 0.f;
 
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
           ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.src_slot = __float_as_int(d.w);
           fr = make_frame(ray); wr = make_watertight(ray);
           tbest = ray.tmax; hit.slot = -1; hit.t = ray.tmax; hit.u = 0.f; hit.v = 0.f;
-          sp = 0; ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
+          sp = 0; tstk = 0; ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
           busy = true;
         }
       }
@@ -163,13 +163,15 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
     // ---- traverse until the warp is due for a refill
     while (true) {
       bool done = false, did_node = false;
-      // (1) node step: open the highest-priority pending internal child, or take the next group off the stack
-      if (busy) {
+      // (1) node step: open the highest-priority pending internal child, or take the next group off the stack.
+      // The stack holds at most one node group per tree level plus `tri_cap` postponed primitive groups: a lane
+      // that holds a group and has no room to park it skips the node step and tests its primitives first.
+      if (busy && !(tgroup.y != 0u && tstk >= tri_cap)) {
         uint2 tnew = make_uint2(0u, 0u);
         if (ngroup.y <= 0x00ffffffu && sp > 0) {
           sp--;
           const uint2 e = stack[sp * stride];
-          if (e.y > 0x00ffffffu) ngroup = e; else tnew = e;          // node group / postponed primitive group
+          if (e.y > 0x00ffffffu) ngroup = e; else { tnew = e; tstk--; }   // node group / postponed primitive group
         }
         if (ngroup.y > 0x00ffffffu) {
           const uint32_t bit = 31u - (uint32_t)__clz(ngroup.y);
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
           did_node = true;
         }
         if (tnew.y) {
-          if (tgroup.y) { stack[sp * stride] = tgroup; sp++; }        // keep the newest group in registers
+          if (tgroup.y) { stack[sp * stride] = tgroup; sp++; tstk++; }   // keep the newest group in registers
           tgroup = tnew;
         }
       }
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
       if (busy) {
         if (!done && ngroup.y <= 0x00ffffffu && sp == 0 && tgroup.y == 0u) done = true;
         if (done) {
-          busy = false; tgroup.y = 0u; ngroup.y = 0u; sp = 0;
+          busy = false; tgroup.y = 0u; ngroup.y = 0u; sp = 0; tstk = 0;
           if (ANY) {
             if (hit_out) hit_out[item] = make_float4(hit.t, 0.f, 0.f, __int_as_float(hit.slot));
             if (accum && hit.slot < 0) {       // unoccluded: add this light sample's contribution
@@ -436,7 +438,8 @@ Accel make_accel(const dsrt_ctx* ctx, const DevState& D, bool parity) {
 }
 
 // shared-memory traversal stack: two entries (node group + postponed primitive group) per wide-BVH level per lane (whatever is not used stays L1 cache)
-size_t stack_bytes(const dsrt_ctx* ctx) { return (size_t)(2 * std::max(ctx->wide.max_depth, 1) + 2) * kTraceThreads * sizeof(uint2); }
+int tri_stack_cap(const dsrt_ctx* ctx) { return std::max(ctx->wide.max_depth, 1) + 3; }   // postponed primitive groups a lane may park
+size_t stack_bytes(const dsrt_ctx* ctx) { return (size_t)(std::max(ctx->wide.max_depth, 1) + tri_stack_cap(ctx) + 1) * kTraceThreads * sizeof(uint2); }
 
 int init_device(dsrt_ctx* ctx, DevState& D, int device) {
   D.device = device;
@@ -711,7 +714,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   const Accel A = make_accel(ctx, D, false);
   const bool count = ctx->opt_count != 0, timing = ctx->opt_stage_timing != 0;
   const int tgrid = D.trace_blocks;
-  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode;
+  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, tri_cap = tri_stack_cap(ctx);
   const size_t sbytes = stack_bytes(ctx);
 
   auto span_begin = [&](int kind) { if (timing) { DevState::Span s; s.kind = kind; s.e0 = D.ev_used; cudaEventRecord(next_event(D), st); s.e1 = 0; D.spans.push_back(s); } };
@@ -730,8 +733,8 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
     for (int d = 0; d <= ctx->max_depth; d++) {
       const uint32_t* q = (d == 0 && aligned) ? nullptr : D.queue[cur];
       span_begin(0);
-      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode);
-      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode);
+      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
+      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
       span_end();
       // depth 0 shades every path; deeper levels only shrink, so a capped grid-stride launch is enough
       const int bound = d == 0 ? n_paths : std::min(n_paths, D.sm_count * 16 * 128);
@@ -741,8 +744,8 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
       span_end();
       if (nls > 0) {
         span_begin(1);
-        if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals, tri_min, refill_busy, wait_mode);
-        else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals, tri_min, refill_busy, wait_mode);
+        if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
+        else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
         span_end();
         D.launches++;
       }
@@ -891,11 +894,11 @@ int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) 
     if (D.n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &D.d_counters, (size_t)1))) return rc; D.n_counter_blocks = 1; }
     CK(cudaMemsetAsync(D.d_counters, 0, sizeof(Counters), st));
     RenderParams rp; std::memset(&rp, 0, sizeof(rp)); rp.cam = ctx->cam;
-    const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode;
+    const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, tri_cap = tri_stack_cap(ctx);
     k_generate_centres<<<(n + 255) / 256, 256, 0, st>>>(D.ps, rp, n);
     k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
     k_trace<false, false><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(make_accel(ctx, D, false), D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0],
-                                                                            &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode);
+                                                                            &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
     CK(cudaGetLastError());
     std::vector<float4> hits(n);
     CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
@@ -928,9 +931,9 @@ static int trace_batch(dsrt_ctx* ctx, bool any, int64_t n, const float* o, const
   CK(cudaMemcpyAsync(D.ps.ray_d, hd.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
   k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
   const Accel A = make_accel(ctx, D, false);
-  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode;
-  if (any) k_trace<true, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode);
-  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode);
+  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, tri_cap = tri_stack_cap(ctx);
+  if (any) k_trace<true, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
+  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
   CK(cudaGetLastError());
   std::vector<float4> hits(n);
   CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));

@@ -115,6 +115,13 @@ DSRT_HD uint32_t hd_f2u(float f) {
 }
 DSRT_HD float hd_i2f(int i) { return hd_u2f((uint32_t)i); }
 DSRT_HD int hd_f2i(float f) { return (int)hd_f2u(f); }
+DSRT_HD float hd_rcp(float x) {
+#ifdef __CUDA_ARCH__
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
 DSRT_HD float hd_rsqrt(float x) {
 #ifdef __CUDA_ARCH__
   return rsqrtf(x);

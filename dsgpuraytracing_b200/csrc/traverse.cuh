@@ -55,7 +55,7 @@ DSRT_HD WatertightRay make_watertight(const TraceRay& r) {
   const float dz = kz == 0 ? r.dx : (kz == 1 ? r.dy : r.dz);
   if (dz < 0.0f) { int t = kx; kx = ky; ky = t; }   // preserve winding
   const float dx = kx == 0 ? r.dx : (kx == 1 ? r.dy : r.dz), dy = ky == 0 ? r.dx : (ky == 1 ? r.dy : r.dz);
-  const float Sz = 1.0f / dz, Sx = dx * Sz, Sy = dy * Sz;
+  const float Sz = hd_rcp(dz), Sx = dx * Sz, Sy = dy * Sz;
   WatertightRay w;
   w.bxx = (kx == 0 ? 1.0f : 0.0f) - (kz == 0 ? Sx : 0.0f); w.bxy = (kx == 1 ? 1.0f : 0.0f) - (kz == 1 ? Sx : 0.0f); w.bxz = (kx == 2 ? 1.0f : 0.0f) - (kz == 2 ? Sx : 0.0f);
   w.byx = (ky == 0 ? 1.0f : 0.0f) - (kz == 0 ? Sy : 0.0f); w.byy = (ky == 1 ? 1.0f : 0.0f) - (kz == 1 ? Sy : 0.0f); w.byz = (ky == 2 ? 1.0f : 0.0f) - (kz == 2 ? Sy : 0.0f);
@@ -89,7 +89,7 @@ DSRT_HD bool hit_triangle(const TraceRay& r, const WatertightRay& w, const float
   const float Bz = hd_fma(B2, w.bzz, hd_fma(B1, w.bzy, B0 * w.bzx));
   const float Cz = hd_fma(C2, w.bzz, hd_fma(C1, w.bzy, C0 * w.bzx));
   const float T = U * Az + V * Bz + W * Cz;
-  const float rdet = 1.0f / det;
+  const float rdet = hd_rcp(det);
   const float t = T * rdet;
   if (!(t > 0.0f && t < tmax)) return false;
   t_out = t; u_out = V * rdet; v_out = W * rdet;
@@ -181,7 +181,7 @@ DSRT_HD NodeFrame make_frame(const TraceRay& r) {
   const float dx = fabsf(r.dx) > eps ? r.dx : copysignf(eps, r.dx);
   const float dy = fabsf(r.dy) > eps ? r.dy : copysignf(eps, r.dy);
   const float dz = fabsf(r.dz) > eps ? r.dz : copysignf(eps, r.dz);
-  f.idx = 1.0f / dx; f.idy = 1.0f / dy; f.idz = 1.0f / dz;
+  f.idx = hd_rcp(dx); f.idy = hd_rcp(dy); f.idz = hd_rcp(dz);
   f.nx = dx < 0.0f; f.ny = dy < 0.0f; f.nz = dz < 0.0f;
   const uint32_t oct = (f.nx ? 1u : 0u) | (f.ny ? 2u : 0u) | (f.nz ? 4u : 0u);
   f.octinv = 7u - oct;
@@ -203,8 +203,9 @@ DSRT_HD float byte_unit(uint32_t w, int i, uint32_t one) {
 
 // Tests the 8 quantised child boxes of one node; returns the 32-bit hit mask (31..24 internal children in
 // visiting priority, 23..0 primitives).  Near / far planes are picked per axis from the ray's sign (no per-child
-// min/max); far planes are scaled by 1 + 4e-7 so float rounding can only widen a box; empty slots need no test
-// because their meta byte contributes no bits.  pad > 0 only in parity mode (conservative slabs).
+// min/max).  Float rounding of the dequantised planes (<= 2^-9 quantum) is covered by the 1/64-quantum margin the
+// host puts on every quantised plane (wide_bvh.cpp), so no widening is needed here; empty slots need no test
+// because their meta byte contributes no bits.  pad > 0 only in parity mode (extra conservative slabs).
 template <bool PARITY>
 DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uint4 n0, const uint4 n1,
                                                   const uint4 n2, const uint4 n3, const uint4 n4, float tmax, float pad, uint32_t one) {
@@ -213,17 +214,16 @@ DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uin
   const float sx = hd_u2f(((n0.w & 0xffu) + 15u) << 23) * fr.idx;
   const float sy = hd_u2f((((n0.w >> 8) & 0xffu) + 15u) << 23) * fr.idy;
   const float sz = hd_u2f((((n0.w >> 16) & 0xffu) + 15u) << 23) * fr.idz;
-  const float k = PARITY ? 1.0001f : 1.0000004f;
-  float bnx, bny, bnz, bfx, bfy, bfz;
+  float bnx, bny, bnz, bfx, bfy, bfz, sfx = sx, sfy = sy, sfz = sz;
   if (PARITY) {
+    const float k = 1.0001f;
     bnx = ((fr.nx ? ox + pad : ox - pad) - r.ox) * fr.idx - sx; bfx = (((fr.nx ? ox - pad : ox + pad) - r.ox) * fr.idx - sx) * k + pad;
     bny = ((fr.ny ? oy + pad : oy - pad) - r.oy) * fr.idy - sy; bfy = (((fr.ny ? oy - pad : oy + pad) - r.oy) * fr.idy - sy) * k + pad;
     bnz = ((fr.nz ? oz + pad : oz - pad) - r.oz) * fr.idz - sz; bfz = (((fr.nz ? oz - pad : oz + pad) - r.oz) * fr.idz - sz) * k + pad;
+    sfx = sx * k; sfy = sy * k; sfz = sz * k;
   } else {
-    bnx = (ox - r.ox) * fr.idx - sx; bny = (oy - r.oy) * fr.idy - sy; bnz = (oz - r.oz) * fr.idz - sz;
-    bfx = bnx * k; bfy = bny * k; bfz = bnz * k;
+    bnx = bfx = (ox - r.ox) * fr.idx - sx; bny = bfy = (oy - r.oy) * fr.idy - sy; bnz = bfz = (oz - r.oz) * fr.idz - sz;
   }
-  const float sfx = sx * k, sfy = sy * k, sfz = sz * k;
   uint32_t mask = 0;
 #pragma unroll
   for (int half = 0; half < 2; half++) {

@@ -80,6 +80,25 @@ void cw_trace(Walk* w, int any, int64_t n, const float* o, const float* d, const
   if (counters) { counters[0] = cn; counters[1] = cp; }
 }
 
+// brute force over all slots with the production primitive tests (no BVH): separates culling from intersection bugs
+void cw_trace_brute(Walk* w, int64_t n, const float* o, const float* d, int32_t* prim_id, float* t) {
+  const Accel A = accel_of(w, false);
+  for (int64_t i = 0; i < n; i++) {
+    TraceRay r; r.ox = o[3 * i]; r.oy = o[3 * i + 1]; r.oz = o[3 * i + 2]; r.dx = d[3 * i]; r.dy = d[3 * i + 1]; r.dz = d[3 * i + 2];
+    r.tmax = kInfF; r.src_slot = -1;
+    const WatertightRay wr = make_watertight(r);
+    float best = kInfF; int bs = -1;
+    for (size_t sl = 0; sl < w->wide.slot_prim.size(); sl++) {
+      const float4* pp = A.prims + sl * 3;
+      float tt, u, v; bool h;
+      if (pp[1].w != 0.0f) h = hit_triangle(r, wr, pp[0], pp[1], pp[2], best, tt, u, v);
+      else h = hit_sphere(r, pp[0], pp[1], false, false, best, tt);
+      if (h) { best = tt; bs = (int)sl; }
+    }
+    prim_id[i] = bs >= 0 ? w->wide.slot_prim[bs] : -1; t[i] = best;
+  }
+}
+
 static void gen_ray64(const Camera& c, double x, double y, Ray64& r) {
   const double sp[3] = {-(x - 0.5) * c.W64 / c.dist64, -(y - 0.5) * c.H64 / c.dist64, 1.0};
   double wv[3], dir[3];

@@ -66,6 +66,13 @@ class Walk:
                        C.c_void_p(ts.ctypes.data), C.c_void_p(cnt.ctypes.data))
         return ids, ts, cnt
 
+    def trace_brute(self, o, d):
+        o = _c(o, np.float32).reshape(-1, 3); d = _c(d, np.float32).reshape(-1, 3); n = len(o)
+        ids = np.zeros(n, np.int32); ts = np.zeros(n, np.float32)
+        lib().cw_trace_brute(self.h, C.c_int64(n), C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data),
+                             C.c_void_p(ids.ctypes.data), C.c_void_p(ts.ctypes.data))
+        return ids, ts
+
     def primary_hits(self, mode=1):
         ids = np.zeros((self.H, self.W), np.int32); ts = np.zeros((self.H, self.W))
         lib().cw_primary_hits(self.h, int(mode), C.c_void_p(ids.ctypes.data), C.c_void_p(ts.ctypes.data))

@@ -1,9 +1,10 @@
 // wide_bvh.cpp -- collapse the reference-identical binary SAH tree into the compressed 8-wide BVH the
 // sm_100a traversal kernels consume (layout.h), and emit primitives in leaf-contiguous order.
 //
-//  1. copy the binary tree; split any leaf with more than 3 primitives into halves (the reference allows
-//     4 per leaf, and leaves of arbitrary size after a degenerate split, bvh.cpp:143-173), because the
-//     24-bit primitive part of the hit mask gives each of the 8 children at most 3 primitives;
+//  1. copy the binary tree and refine every leaf down to single primitives with median splits (the reference
+//     allows 4 per leaf, and leaves of arbitrary size after a degenerate split, bvh.cpp:143-173); the collapse
+//     below then chooses leaf children of 1..3 primitives (the 24-bit primitive part of the hit mask gives each
+//     of the 8 children at most 3);
 //  2. SAH-optimal collapse (dynamic programme of Ylitie et al. 2017, section 3.1): C(n,i) = cheapest way to turn
 //     the binary subtree n into a forest of at most i wide-node children; a subtree with <= 3 primitives may become
 //     a leaf child, any subtree may become an internal wide node whose 8 slots are distributed over its two binary
@@ -62,7 +63,7 @@ int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_pri
   };
   {
     std::vector<int> work;
-    for (int i = 0; i < b2.n_nodes; i++) if (T[i].l < 0 && T[i].r < 0 && T[i].range > 3) work.push_back(i);
+    for (int i = 0; i < b2.n_nodes; i++) if (T[i].l < 0 && T[i].r < 0 && T[i].range > 1) work.push_back(i);
     while (!work.empty()) {
       int id = work.back(); work.pop_back();
       int s = T[id].start, r = T[id].range, h = r / 2;
@@ -71,15 +72,15 @@ int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_pri
       a.start = s; a.range = h; a.l = a.r = -1; b.start = s + h; b.range = r - h; b.l = b.r = -1;
       int ai = (int)T.size(); T.push_back(a); int bi = (int)T.size(); T.push_back(b);
       T[id].l = ai; T[id].r = bi;
-      if (a.range > 3) work.push_back(ai);
-      if (b.range > 3) work.push_back(bi);
+      if (a.range > 1) work.push_back(ai);
+      if (b.range > 1) work.push_back(bi);
     }
   }
   const int root = resolve(0);
 
   // 2. dynamic programme over the binary tree (post-order)
   const int NT = (int)T.size();
-  const double c_node = 1.0, c_prim = 0.3;   // (measured: the collapse is insensitive to c_prim between 0.15 and 4)
+  const double c_node = 1.0, c_prim = 1.0;   // measured on B200: flat optimum between 0.6 and 2.5 (primitive tests run at low lane occupancy)
   struct DP { double c[8]; uint8_t split[8]; uint8_t kind1; };      // c[i], i = 1..7 roots; split[i] = roots given to the left child
   std::vector<DP> dp((size_t)NT);                                    // kind1: 0 leaf, 1 internal wide node
   std::vector<double> c_int((size_t)NT, 0.0); std::vector<uint8_t> split8((size_t)NT, 0);

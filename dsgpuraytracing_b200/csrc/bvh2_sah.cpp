@@ -6,10 +6,16 @@
 // bucket array when a centroid lies on the node's upper bound (bvh.cpp:47-50).
 //
 // Node ids are assigned in preorder (node, left subtree, right subtree); node 0 is the root.
+// Subtrees with many primitives are built as parallel tasks (disjoint slices of the order array, node slots from an
+// atomic counter); the final preorder renumbering makes the result independent of the schedule, so the topology is
+// the reference's whatever the thread count.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <atomic>
+#include <future>
 #include <limits>
+#include <thread>
 #include <vector>
 
 #include "../../include/dsrt.h"
@@ -40,11 +46,16 @@ struct BuildNode { Box3 box; int start, range, left, right; };
 struct Builder {
   static constexpr int kBuckets = 32;
   static constexpr int kMaxLeaf = 4;
+  static constexpr int kParallelMin = 1 << 16;     // spawn a task for subtrees at least this large
   const std::vector<Box3>& pbox;
   int32_t* order;
-  std::vector<BuildNode> nodes;
+  std::vector<BuildNode> nodes;                   // preallocated: 2 * n_prims + 1 slots
+  std::atomic<int> next_node{0};
+  std::atomic<int> spare_threads{0};
 
   Builder(const std::vector<Box3>& pb, int32_t* ord) : pbox(pb), order(ord) {}
+
+  int alloc2() { return next_node.fetch_add(2); }
 
   double centroid(int slot, int axis) const {
     const Box3& b = pbox[order[slot]];
@@ -79,8 +90,7 @@ struct Builder {
   }
 
   void split(int id) {
-    // copy: nodes may reallocate below
-    BuildNode n = nodes[id];
+    const BuildNode n = nodes[id];
     double best[3]; int plane[3] = {0, 0, 0};
     for (int k = 0; k < 3; k++) {
       best[k] = std::numeric_limits<double>::infinity();
@@ -101,23 +111,30 @@ struct Builder {
       else break;
     }
     const int nl = i - n.start, nr = n.range - nl;
+    int li = -1, ri = -1;
     if (nl != 0 && nr != 0) {
-      BuildNode L, R;
+      li = alloc2(); ri = li + 1;
+      BuildNode& L = nodes[li]; BuildNode& R = nodes[ri];
       L.box.reset(); R.box.reset();
       for (int q = 0; q < n.range; q++) (q < nl ? L.box : R.box).grow(pbox[order[n.start + q]]);
       L.start = n.start; L.range = nl; L.left = L.right = -1;
       R.start = n.start + nl; R.range = nr; R.left = R.right = -1;
-      int li = (int)nodes.size(); nodes.push_back(L);
-      int ri = (int)nodes.size(); nodes.push_back(R);
       nodes[id].left = li; nodes[id].right = ri;
     }
-    const int li = nodes[id].left, ri = nodes[id].right;
     const bool lsmall = nl <= kMaxLeaf, rsmall = nr <= kMaxLeaf;
     if (lsmall && rsmall) return;
     if (lsmall) { if (nl > 0) split(ri); return; }      // nl == 0: everything on one side -> oversized leaf
     if (rsmall) { if (nr > 0) split(li); return; }
-    split(li);
-    split(ri);
+    if (std::min(nl, nr) >= kParallelMin && spare_threads.fetch_sub(1) > 0) {
+      std::future<void> f = std::async(std::launch::async, [this, li] { split(li); });
+      split(ri);
+      f.get();
+      spare_threads.fetch_add(1);
+    } else {
+      if (std::min(nl, nr) >= kParallelMin) spare_threads.fetch_add(1);   // undo the failed reservation
+      split(li);
+      split(ri);
+    }
   }
 };
 
@@ -136,9 +153,11 @@ extern "C" int dsrt_build_bvh2(const dsrt_scene* sc, double* node_bbox, int32_t*
   for (int i = 0; i < sc->n_prims; i++) { prim_order[i] = i; root.box.grow(pbox[i]); }
   root.start = 0; root.range = sc->n_prims; root.left = root.right = -1;
   Builder b(pbox, prim_order);
-  b.nodes.reserve((size_t)sc->n_prims + 16);
-  b.nodes.push_back(root);
+  b.nodes.resize(2 * (size_t)sc->n_prims + 2);
+  b.nodes[0] = root; b.next_node = 1;
+  b.spare_threads = (int)std::max(1u, std::thread::hardware_concurrency()) - 1;
   b.split(0);   // the reference splits the root unconditionally (bvh.cpp:199-200)
+  b.nodes.resize((size_t)b.next_node.load());
   // renumber in preorder
   std::vector<int> stack; stack.push_back(0);
   std::vector<int> newid(b.nodes.size(), -1);

@@ -286,14 +286,15 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algo_bytes / sec / 1e9 if sec > 0 else 0.0
-    traffic = None
+    traffic = None; traffic_detail = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+        traffic_detail = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+        traffic = traffic_detail["traffic_bytes_per_launch"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
-                "traffic": traffic, "kernel": dom, "kernel_seconds_per_step": sec,
+                "traffic": traffic, "traffic_detail": traffic_detail, "kernel": dom, "kernel_seconds_per_step": sec,
                 "kernel_share_of_step": sec / (ms_max * 1e-3 / a.steps), "bytes_per_segment": algo_bytes / max(nr, 1),
                 "nodes_per_segment": nn / max(nr, 1), "prims_per_segment": nt / max(nr, 1),
                 "note": "working set (wide BVH + primitive records = %.1f MB) is L2-resident, so the HBM roofline is an upper "

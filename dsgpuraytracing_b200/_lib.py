@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 EXPORTED_SYMBOLS = [
     "dsrt_create", "dsrt_create_multi", "dsrt_device_count", "dsrt_destroy", "dsrt_last_error", "dsrt_version", "dsrt_set_scene", "dsrt_set_bvh",
     "dsrt_set_camera", "dsrt_set_params", "dsrt_set_option", "dsrt_build_bvh2", "dsrt_build_accel",
-    "dsrt_accel_info", "dsrt_render", "dsrt_render_device", "dsrt_resolve_device", "dsrt_sync",
+    "dsrt_accel_info", "dsrt_upload_accel", "dsrt_accel_bytes", "dsrt_render", "dsrt_render_device", "dsrt_resolve_device", "dsrt_sync",
     "dsrt_collect_stats", "dsrt_primary_hits", "dsrt_trace_closest", "dsrt_trace_any", "dsrt_tonemap",
 ]
 
@@ -176,6 +176,14 @@ class Core:
 
     def build_accel(self):
         self._ck(self.L.dsrt_build_accel(self.ctx), "dsrt_build_accel")
+
+    def upload_accel(self):
+        self._ck(self.L.dsrt_upload_accel(self.ctx), "dsrt_upload_accel")
+
+    def accel_bytes(self):
+        b = C.c_int64()
+        self._ck(self.L.dsrt_accel_bytes(self.ctx, C.byref(b)), "dsrt_accel_bytes")
+        return b.value
 
     def accel_info(self):
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()

@@ -406,6 +406,7 @@ struct dsrt_ctx {
   uint32_t seed = 0;
   int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20, opt_wait_mode = 0;
   WideBVH wide;
+  std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
   double scene_diag = 1.0;
   int n_lights = 0, n_light_samples = 0;
 };
@@ -517,6 +518,8 @@ int create_impl(int n, const int* devices, dsrt_ctx** out) {
 }  // namespace
 
 extern "C" {
+
+int dsrt_upload_accel(dsrt_ctx* ctx);
 
 const char* dsrt_version(void) { return "dsrt 0.2 (sm_100a wavefront path tracer)"; }
 
@@ -638,36 +641,55 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
   double dg = 0; for (int k = 0; k < 3; k++) { double e = ctx->n_prims ? all.hi[k] - all.lo[k] : 0; double m = ctx->n_prims ? std::fmax(std::fabs(all.lo[k]), std::fabs(all.hi[k])) : 0; dg += (e + m) * (e + m); }
   ctx->scene_diag = std::sqrt(dg) + 1.0;
 
-  const size_t n = ctx->wide.slot_prim.size();
-  std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
-  flatten_records(s, ctx->wide, recs, shd, r64);
-  ctx->n_light_samples = flatten_lights((int)ctx->light_type.size(), ctx->light_type.data(), ctx->light_param.data(), ctx->ns_area_light, lights);
-  ctx->n_lights = (int)lights.size();
-
-  for (DevState& D : ctx->devs) {      // the scene is replicated on every GPU (SURVEY.md 8e)
+  flatten_records(s, ctx->wide, ctx->recs, ctx->shd, ctx->r64);
+  ctx->n_light_samples = flatten_lights((int)ctx->light_type.size(), ctx->light_type.data(), ctx->light_param.data(), ctx->ns_area_light, ctx->lights);
+  ctx->n_lights = (int)ctx->lights.size();
+  for (DevState& D : ctx->devs) {      // new sizes: (re)allocate the device copies
     CK(cudaSetDevice(D.device));
     dev_free(D.d_nodes); dev_free(D.d_prims); dev_free(D.d_shade); dev_free(D.d_prims64); dev_free(D.d_bsdf); dev_free(D.d_lights);
     D.d_nodes = D.d_prims = D.d_shade = D.d_prims64 = D.d_bsdf = D.d_lights = nullptr;
-    auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
-      cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
-      if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, D.stream);
-      return e;
-    };
-    CK(up(&D.d_nodes, ctx->wide.nodes.data(), ctx->wide.nodes.size() * sizeof(WideNode)));
-    CK(up(&D.d_prims, recs.data(), n * sizeof(PrimRecord)));
-    CK(up(&D.d_shade, shd.data(), n * sizeof(ShadeRecord)));
-    CK(up(&D.d_prims64, r64.data(), n * sizeof(PrimRecord64)));
-    CK(up(&D.d_bsdf, ctx->bsdfs.data(), ctx->bsdfs.size() * sizeof(Bsdf)));
-    CK(up(&D.d_lights, lights.data(), lights.size() * sizeof(Light)));
-  }
-  for (DevState& D : ctx->devs) {
-    CK(cudaSetDevice(D.device)); CK(cudaStreamSynchronize(D.stream));
+    const size_t n = ctx->wide.slot_prim.size();
+    CK(cudaMalloc(&D.d_nodes, std::max<size_t>(ctx->wide.nodes.size() * sizeof(WideNode), 16)));
+    CK(cudaMalloc(&D.d_prims, std::max<size_t>(n * sizeof(PrimRecord), 16)));
+    CK(cudaMalloc(&D.d_shade, std::max<size_t>(n * sizeof(ShadeRecord), 16)));
+    CK(cudaMalloc(&D.d_prims64, std::max<size_t>(n * sizeof(PrimRecord64), 16)));
+    CK(cudaMalloc(&D.d_bsdf, std::max<size_t>(ctx->bsdfs.size() * sizeof(Bsdf), 16)));
+    CK(cudaMalloc(&D.d_lights, std::max<size_t>(ctx->lights.size() * sizeof(Light), 16)));
     // persistent grid = resident CTAs per SM (registers / shared-memory stack) x SM count
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, false>, kTraceThreads, stack_bytes(ctx)));
     D.trace_blocks = D.sm_count * std::max(per_sm, 1);
   }
   ctx->have_accel = true;
+  return dsrt_upload_accel(ctx);
+}
+
+// H2D copy of the flattened scene (wide nodes, primitive / shading / fp64 records, BSDF and light tables) to every
+// GPU.  dsrt_build_accel calls it; callers may call it again to re-send the same scene (bench.py's e2e step).
+int dsrt_upload_accel(dsrt_ctx* ctx) {
+  if (!ctx) return DSRT_ERR_INVALID;
+  if (!ctx->have_accel) return fail(ctx, DSRT_ERR_INVALID, "dsrt_upload_accel: call dsrt_build_accel first");
+  const size_t n = ctx->wide.slot_prim.size();
+  for (DevState& D : ctx->devs) {      // the scene is replicated on every GPU (SURVEY.md 8e)
+    CK(cudaSetDevice(D.device));
+    CK(cudaMemcpyAsync(D.d_nodes, ctx->wide.nodes.data(), ctx->wide.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, D.stream));
+    if (n) {
+      CK(cudaMemcpyAsync(D.d_prims, ctx->recs.data(), n * sizeof(PrimRecord), cudaMemcpyHostToDevice, D.stream));
+      CK(cudaMemcpyAsync(D.d_shade, ctx->shd.data(), n * sizeof(ShadeRecord), cudaMemcpyHostToDevice, D.stream));
+      CK(cudaMemcpyAsync(D.d_prims64, ctx->r64.data(), n * sizeof(PrimRecord64), cudaMemcpyHostToDevice, D.stream));
+    }
+    if (!ctx->bsdfs.empty()) CK(cudaMemcpyAsync(D.d_bsdf, ctx->bsdfs.data(), ctx->bsdfs.size() * sizeof(Bsdf), cudaMemcpyHostToDevice, D.stream));
+    if (!ctx->lights.empty()) CK(cudaMemcpyAsync(D.d_lights, ctx->lights.data(), ctx->lights.size() * sizeof(Light), cudaMemcpyHostToDevice, D.stream));
+  }
+  for (DevState& D : ctx->devs) { CK(cudaSetDevice(D.device)); CK(cudaStreamSynchronize(D.stream)); }
+  return DSRT_OK;
+}
+
+int dsrt_accel_bytes(const dsrt_ctx* ctx, int64_t* h2d_bytes) {
+  if (!ctx || !ctx->have_accel || !h2d_bytes) return DSRT_ERR_INVALID;
+  const size_t n = ctx->wide.slot_prim.size();
+  *h2d_bytes = (int64_t)(ctx->wide.nodes.size() * sizeof(WideNode) + n * (sizeof(PrimRecord) + sizeof(ShadeRecord) + sizeof(PrimRecord64)) +
+                         ctx->bsdfs.size() * sizeof(Bsdf) + ctx->lights.size() * sizeof(Light));
   return DSRT_OK;
 }
 

@@ -113,6 +113,10 @@ int dsrt_build_bvh2(const dsrt_scene* scene, double* node_bbox, int32_t* node_st
 /* Collapse the binary BVH into the compressed 8-wide SoA BVH, reorder primitives leaf-contiguously,
  * upload.  Outputs sizes for the roofline accounting (may be NULL). */
 int dsrt_build_accel(dsrt_ctx* ctx);
+/* Re-sends the flattened scene built by dsrt_build_accel to the GPU(s): a pure host->device copy (what loadPrimitives /
+ * loadBVH / loadLights do with cudaMemcpy in the reference, setup.cu:375-402, 415-476, 745-774). */
+int dsrt_upload_accel(dsrt_ctx* ctx);
+int dsrt_accel_bytes(const dsrt_ctx* ctx, int64_t* h2d_bytes);
 int dsrt_accel_info(const dsrt_ctx* ctx, int64_t* n_wide_nodes, int64_t* node_bytes, int64_t* prim_bytes,
                     int32_t* max_depth);
 

@@ -47,7 +47,8 @@ class _Scene(C.Structure):
                 ("tri_pos", C.c_void_p), ("tri_nrm", C.c_void_p), ("sphere", C.c_void_p),
                 ("n_bsdf", C.c_int), ("bsdf_type", C.c_void_p), ("bsdf_param", C.c_void_p),
                 ("n_lights", C.c_int), ("light_type", C.c_void_p), ("light_param", C.c_void_p),
-                ("cam", C.c_void_p)]
+                ("cam", C.c_void_p), ("env_w", C.c_int), ("env_h", C.c_int), ("env_rgb", C.c_void_p),
+                ("env_pThetaPhi", C.c_void_p), ("env_pTheta", C.c_void_p), ("env_pPhiGivenTheta", C.c_void_p)]
 
 
 class _Bvh(C.Structure):
@@ -75,6 +76,9 @@ class Scene:
         self.light_type = _c(a["light_type"], np.int32)
         self.light_param = _c(a["light_param"], np.float64).reshape(-1, 28)
         self.camera = _c(a["camera"], np.float64)
+        self.env_rgb = None
+        if "env_rgb" in a and a["env_rgb"] is not None and np.size(a["env_rgb"]):
+            self.set_envmap(a["env_rgb"])
         self.bvh = None
         if "node_bbox" in a:
             self.set_bvh({k: a[k] for k in BVH_KEYS})
@@ -85,9 +89,19 @@ class Scene:
 
     def arrays(self):
         d = {k: getattr(self, k) for k in SCENE_KEYS}
+        if self.env_rgb is not None:
+            d["env_rgb"] = self.env_rgb
         if self.bvh is not None:
             d.update(self.bvh)
         return d
+
+    def set_envmap(self, rgb):
+        """EnvironmentLight tables (environment_light.cpp:6-53); the scene must list a light of type 4."""
+        self.env_rgb = _c(rgb, np.float32)
+        h, w = self.env_rgb.shape[:2]
+        self.env_tp = np.zeros((h, w), np.float32); self.env_t = np.zeros(h, np.float32); self.env_pgt = np.zeros((h, w), np.float32)
+        lib().orc_env_build(w, h, self.env_rgb.ctypes.data_as(C.c_void_p), self.env_tp.ctypes.data_as(C.c_void_p),
+                            self.env_t.ctypes.data_as(C.c_void_p), self.env_pgt.ctypes.data_as(C.c_void_p))
 
     def set_bvh(self, b):
         self.bvh = {
@@ -111,6 +125,10 @@ class Scene:
         s.n_bsdf = len(self.bsdf_type)
         s.n_lights = len(self.light_type)
         s.cam = self.camera.ctypes.data
+        if self.env_rgb is not None:
+            s.env_h, s.env_w = self.env_rgb.shape[:2]
+            s.env_rgb = self.env_rgb.ctypes.data; s.env_pThetaPhi = self.env_tp.ctypes.data
+            s.env_pTheta = self.env_t.ctypes.data; s.env_pPhiGivenTheta = self.env_pgt.ctypes.data
         return s
 
     def _cb(self):
@@ -229,7 +247,7 @@ def ref_scene_path(name):
 
 
 def run_reference(scene_path, W, H, cam=None, spp=1, nl=4, depth=1, seed=1, dump_scene=False, ids=False,
-                  render=False, threads=1, timeout=3600):
+                  render=False, threads=1, timeout=3600, envmap=None):
     """Runs oracle/_ref/ref_driver (the reference's own CPU code) and returns its .npy outputs."""
     if not have_reference():
         raise RuntimeError("oracle/_ref/ref_driver is not built (run oracle/build_ref.sh where /root/reference exists)")
@@ -238,6 +256,8 @@ def run_reference(scene_path, W, H, cam=None, spp=1, nl=4, depth=1, seed=1, dump
                str(threads), "--seed", str(seed), "--out", td]
         if cam:
             cmd += ["-f", cam]
+        if envmap:
+            cmd += ["--envmap", str(envmap[0]), str(envmap[1])]
         if dump_scene:
             cmd.append("--dump-scene")
         if ids:

@@ -24,6 +24,7 @@
  *   bsdf_type     0 diffuse 1 mirror 2 refraction 3 glass 4 emission   (bsdf.h:123-236)
  *   bsdf_param[8] a[3] (albedo|reflectance|radiance), b[3] (transmittance), ior, pad
  *   light_type    0 directional 1 hemisphere 2 point 3 area            (light.h:24-99)
+ *                 4 environment map (EnvironmentLight; the reference reuses id 1 for it, environment_light.h:47)
  *   light_param[28] radiance[3], dirToLight|position[3], direction[3], dim_x[3], dim_y[3], area,
  *                 sampleToWorld[9] column-major (at offset 16)
  *   cam[17]       pos[3], c2w[9] column-major, screenW, screenH, screenDist, hFov, vFov
@@ -89,6 +90,12 @@ typedef struct {
   const int32_t* light_type;
   const double* light_param;
   const double* cam;
+  /* optional lat-long environment map (EnvironmentLight, environment_light.cpp): light_type 4 refers to it */
+  int env_w, env_h;
+  const float* env_rgb;        /* env_h * env_w * 3 */
+  const float* env_pThetaPhi;  /* tables built by orc_env_build */
+  const float* env_pTheta;
+  const float* env_pPhiGivenTheta;
 } orc_scene;
 
 typedef struct {
@@ -528,6 +535,80 @@ static spec bsdf_sample_f(const orc_scene* s, int b, v3 wo, v3* wi, float* pdf, 
   *pdf = 1; *wi = V(0, 0, 1); return S(0, 0, 0);
 }
 
+/* ------------------------------------------------------------------ EnvironmentLight (environment_light.cpp:6-201)
+ * Tables are float and are accumulated in the reference's order (constructor, :6-53). */
+void orc_env_build(int w, int h, const float* rgb, float* pThetaPhi, float* pTheta, float* pPhiGivenTheta) {
+  float C = 0;
+  for (int y = 0; y < h; y++) {
+    float theta = (float)((y + 0.5) / h * ORC_PI);
+    float sin_theta = (float)sin(theta);
+    for (int x = 0; x < w; x++) {
+      const float* q = rgb + 3 * (x + w * y);
+      pThetaPhi[y * w + x] = sillum(S(q[0], q[1], q[2])) * sin_theta;
+      C += pThetaPhi[y * w + x];
+    }
+  }
+  for (int y = 0; y < h; y++) {
+    pTheta[y] = 0;
+    for (int x = 0; x < w; x++) { pThetaPhi[y * w + x] /= C; pTheta[y] += pThetaPhi[y * w + x]; pPhiGivenTheta[y * w + x] = 0; }
+    if (pTheta[y] != 0) for (int x = 0; x < w; x++) pPhiGivenTheta[y * w + x] = pThetaPhi[y * w + x] / pTheta[y];
+  }
+  for (int y = 0; y < h; y++) {
+    if (y > 0) pTheta[y] += pTheta[y - 1];
+    for (int x = 1; x < w; x++) pPhiGivenTheta[y * w + x] += pPhiGivenTheta[y * w + x - 1];
+  }
+}
+static int lower_bound_f(const float* a, int n, float v) {   /* std::lower_bound: first index with a[i] >= v, n if none */
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = lo + (hi - lo) / 2; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+/* EnvironmentLight::sample_dir (:129-199): bilinear lookup with wrap-around */
+static spec env_sample_dir(const orc_scene* s, v3 d) {
+  const int w = s->env_w, h = s->env_h;
+  double theta = acos(d.y);
+  double sin_theta = sqrt(1 - d.y * d.y);
+  double cl = d.z / sin_theta; cl = fmin(fmax(cl, -1.0), 1.0);
+  double phi = sin_theta == 0 ? ORC_PI : acos(cl);
+  if (d.x > 0) phi = 2 * ORC_PI - phi;
+  double u = phi / (2 * ORC_PI), v = theta / ORC_PI;
+  float tu = (float)(u * w - 0.5), tv = (float)(v * h - 0.5);
+  int su = (int)tu, sv = (int)tv;
+  float a, b; int px1, px2, py1, py2;
+  if (tu < 0) { a = tu + 1; px1 = w - 1; px2 = 0; } else if (tu >= w - 1) { a = tu - w + 1; px1 = w - 1; px2 = 0; } else { a = tu - su; px1 = su; px2 = su + 1; }
+  if (tv < 0) { b = tv + 1; py1 = h - 1; py2 = 0; } else if (tv >= h - 1) { b = tv - h + 1; py1 = h - 1; py2 = 0; } else { b = tv - sv; py1 = sv; py2 = sv + 1; }
+  const float* E = s->env_rgb;
+  #define ENVPX(x, y) S(E[3 * ((x) + w * (y))], E[3 * ((x) + w * (y)) + 1], E[3 * ((x) + w * (y)) + 2])
+  spec z11 = ENVPX(px1, py1), z21 = ENVPX(px2, py1), z12 = ENVPX(px1, py2), z22 = ENVPX(px2, py2);
+  #undef ENVPX
+  spec zy1 = sadd(sscale(z11, 1 - a), sscale(z21, a));
+  spec zy2 = sadd(sscale(z12, 1 - a), sscale(z22, a));
+  return sadd(sscale(zy1, 1 - b), sscale(zy2, b));
+}
+/* EnvironmentLight::importanceSampling (:71-113); r1, r2 are the two uniforms as FLOATS */
+static void env_importance(const orc_scene* s, float r1, float r2, v3* wi, float* pdf) {
+  const int w = s->env_w, h = s->env_h;
+  const float* pTheta = s->env_pTheta;
+  r1 *= pTheta[h - 1];
+  int t = lower_bound_f(pTheta, h, r1);
+  if (t >= h) t = h - 1;                       /* (the reference would read past the end) */
+  float prev = t > 0 ? pTheta[t - 1] : 0;
+  float y = t + (r1 - prev) / (pTheta[t] - prev);
+  float theta = (float)(fminf(y / h, 1.f) * ORC_PI);
+  const float* row = s->env_pPhiGivenTheta + (size_t)t * w;
+  r2 *= row[w - 1];
+  int q = lower_bound_f(row, w, r2);
+  if (q >= w) q = w - 1;
+  prev = q > 0 ? row[q - 1] : 0;
+  float x = q + (r2 - prev) / (row[q] - prev);
+  float phi = (float)(fminf(x / w, 1.f) * 2 * ORC_PI);
+  double sin_theta = sin(theta), cos_theta = cos(theta);
+  float p = s->env_pThetaPhi[(size_t)t * w + q];
+  p = (float)(p / (sin_theta * (2 * ORC_PI / w) * (ORC_PI / h)));
+  *pdf = p;
+  *wi = V(-sin_theta * sin(phi), cos_theta, sin_theta * cos(phi));
+}
+
 /* ------------------------------------------------------------------ lights (light.cpp:17-92) */
 static int light_is_delta(int type) { return type == 0 || type == 2; }
 static spec light_sample_L(const orc_scene* s, int l, v3 p, v3* wi, float* dist, float* pdf, const orng* g, int depth, int j) {
@@ -557,6 +638,14 @@ static spec light_sample_L(const orc_scene* s, int l, v3 p, v3* wi, float* dist,
       return cosTheta < 0 ? rad : S(0, 0, 0);
     }
   }
+  if (s->light_type[l] == 4) {      /* EnvironmentLight::sample_L (:115-127) */
+    float r1, r2;
+    if (g->mode == 0) { r1 = rand() / (float)RAND_MAX; r2 = rand() / (float)RAND_MAX; }
+    else { double u[4]; rng_block(g, depth, BLK_LIGHT0 + j / 2, u); r1 = (float)u[2 * (j & 1)]; r2 = (float)u[2 * (j & 1) + 1]; }
+    env_importance(s, r1, r2, wi, pdf);
+    *dist = INFINITY;
+    return env_sample_dir(s, *wi);
+  }
   *wi = V(0, 1, 0); *dist = INFINITY; *pdf = 1; return S(0, 0, 0);
 }
 
@@ -566,7 +655,10 @@ typedef struct { const orc_scene* s; const orc_bvh* b; int ns_area_light, max_ra
 static spec trace_ray(octx* c, oray* r, int includeLe) {
   const orc_scene* s = c->s;
   oisect isect; isect.t = INFINITY; isect.prim = -1; isect.bsdf = -1; isect.n = V(0, 0, 0);
-  if (!bvh_closest(s, c->b, r, &isect)) return S(0, 0, 0);   /* no envLight from the CLI */
+  if (!bvh_closest(s, c->b, r, &isect)) {                    /* pathtracer.cpp:411-427 */
+    if (s->env_w > 0 && includeLe) return env_sample_dir(s, r->d);
+    return S(0, 0, 0);
+  }
   spec L_out = includeLe ? bsdf_emission(s, isect.bsdf) : S(0, 0, 0);
   v3 hit_p = vadd(r->o, vmulr(r->d, isect.t));
   m3 o2w; make_coord_space(&o2w, isect.n);

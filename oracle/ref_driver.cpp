@@ -38,6 +38,7 @@
 #include "static_scene/triangle.h"
 #include "static_scene/sphere.h"
 #include "static_scene/light.h"
+#include "static_scene/environment_light.h"
 #include "static_scene/object.h"
 #include "pathtracer.h"
 #include "camera.h"
@@ -82,7 +83,21 @@ struct Args {
   int w = 1000, h = 1000, spp = 1, nl = 4, depth = 1, threads = 1;
   unsigned seed = 1;
   bool dump_scene = false, ids = false, render = false;
+  int env_w = 0, env_h = 0;   // --envmap W H: procedural lat-long environment map (no .exr ships with the reference)
 };
+
+// Procedural sky: vertical gradient + a warm "sun" lobe + a faint ground, deterministic, float RGB.
+static HDRImageBuffer* make_envmap(int w, int h) {
+  HDRImageBuffer* e = new HDRImageBuffer(w, h);
+  for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) {
+    double v = (y + 0.5) / h, u = (x + 0.5) / w;
+    double sky = v < 0.5 ? 0.35 + 0.9 * (0.5 - v) : 0.08;
+    double du = u - 0.3, dv = v - 0.22;
+    double sun = 40.0 * std::exp(-(du * du + dv * dv) / 0.0008);
+    e->data[x + w * y] = Spectrum((float)(0.6 * sky + sun), (float)(0.75 * sky + 0.9 * sun), (float)(1.0 * sky + 0.7 * sun));
+  }
+  return e;
+}
 
 static void v3(std::vector<double>& v, const Vector3D& a) { v.push_back(a.x); v.push_back(a.y); v.push_back(a.z); }
 
@@ -103,6 +118,7 @@ int main(int argc, char** argv) {
     else if (s == "--dump-scene") a.dump_scene = true;
     else if (s == "--ids") a.ids = true;
     else if (s == "--render") a.render = true;
+    else if (s == "--envmap") { a.env_w = atoi(next()); a.env_h = atoi(next()); }
     else a.scene = s;
   }
   if (a.scene.empty()) { fprintf(stderr, "usage: ref_driver [-s -l -t -m -w -h -f] [--seed N] [--out DIR] [--dump-scene] [--ids] [--render] scene.dae\n"); return 2; }
@@ -112,7 +128,8 @@ int main(int argc, char** argv) {
   Collada::SceneInfo* sceneInfo = new Collada::SceneInfo();        // main.cpp:132-137
   if (Collada::ColladaParser::load(a.scene.c_str(), sceneInfo) < 0) { fprintf(stderr, "cannot load %s\n", a.scene.c_str()); return 3; }
 
-  PathTracer* pt = new PathTracer(a.spp, a.depth, a.nl, 1, 1, 1, a.threads, NULL);   // application.cpp:28-40
+  HDRImageBuffer* envmap = (a.env_w > 0 && a.env_h > 0) ? make_envmap(a.env_w, a.env_h) : NULL;   // main.cpp:99-101 (-e)
+  PathTracer* pt = new PathTracer(a.spp, a.depth, a.nl, 1, 1, 1, a.threads, envmap);   // application.cpp:28-40
   pt->useCPU = true;
 
   // Application::init (application.cpp:87-99): dummy camera, then main.cpp:158-159 sets screenW/H
@@ -259,6 +276,8 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < nl; i++) {
       StaticScene::SceneLight* L = pt->scene->lights[i];
       ltype[i] = L->getType();
+      // EnvironmentLight::getType() also returns 1 (environment_light.h:47): flattened as type 4
+      if (dynamic_cast<StaticScene::EnvironmentLight*>(L)) { ltype[i] = 4; continue; }
       double* q = &lpar[i * 28];
       switch (ltype[i]) {
         case 0: { auto* d = static_cast<StaticScene::DirectionalLight*>(L); q[0] = d->radiance.r; q[1] = d->radiance.g; q[2] = d->radiance.b;
@@ -276,6 +295,7 @@ int main(int argc, char** argv) {
         default: break;
       }
     }
+    if (envmap) npy_write(a.out + "/env_rgb.npy", "<f4", 4, {(size_t)envmap->h, (size_t)envmap->w, 3}, envmap->data.data());
     npy_write(a.out + "/light_type.npy", "<i4", 4, {nl}, ltype.data());
     npy_write(a.out + "/light_param.npy", "<f8", 8, {nl, 28}, lpar.data());
 

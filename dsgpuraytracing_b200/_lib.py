@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 EXPORTED_SYMBOLS = [
     "dsrt_create", "dsrt_create_multi", "dsrt_device_count", "dsrt_destroy", "dsrt_last_error", "dsrt_version", "dsrt_set_scene", "dsrt_set_bvh",
-    "dsrt_set_camera", "dsrt_set_params", "dsrt_set_option", "dsrt_build_bvh2", "dsrt_build_accel",
+    "dsrt_set_camera", "dsrt_set_params", "dsrt_set_envmap", "dsrt_set_option", "dsrt_build_bvh2", "dsrt_build_accel",
     "dsrt_accel_info", "dsrt_upload_accel", "dsrt_accel_bytes", "dsrt_render", "dsrt_render_device", "dsrt_resolve_device", "dsrt_sync",
     "dsrt_collect_stats", "dsrt_primary_hits", "dsrt_trace_closest", "dsrt_trace_any", "dsrt_tonemap",
 ]
@@ -170,6 +170,14 @@ class Core:
         self.ns_aa = int(ns_aa)
         self._ck(self.L.dsrt_set_params(self.ctx, int(ns_aa), int(ns_area_light), int(max_depth), C.c_uint32(seed)),
                  "dsrt_set_params")
+
+    def set_envmap(self, rgb):
+        """rgb: [H, W, 3] float lat-long map, or None to remove the environment light."""
+        if rgb is None:
+            self._ck(self.L.dsrt_set_envmap(self.ctx, 0, 0, None), "dsrt_set_envmap")
+            return
+        rgb = _c(rgb, np.float32)
+        self._ck(self.L.dsrt_set_envmap(self.ctx, rgb.shape[1], rgb.shape[0], C.c_void_p(rgb.ctypes.data)), "dsrt_set_envmap")
 
     def set_option(self, name, value):
         self._ck(self.L.dsrt_set_option(self.ctx, name.encode(), C.c_int64(int(value))), "dsrt_set_option")

@@ -301,6 +301,13 @@ __global__ void __launch_bounds__(128) k_shade(PathState ps, const float4* __res
       sink.base = __shfl_sync(kFull, sink.base, leader);
     }
     PathOut out; out.cont = false;
+    if (live && !hitp && sc.env.w > 0) {                      // miss: envLight->sample_dir(r) if includeLe (pathtracer.cpp:421-423)
+      const float4 t4 = ps.thr[p];
+      if ((__float_as_int(t4.w) >> 8) & 1) {
+        const float4 d4 = ps.ray_d[p];
+        add_rgb(accum, ps.pixel[p], v3(t4.x, t4.y, t4.z) * env_sample_dir(sc.env, v3(d4.x, d4.y, d4.z)));
+      }
+    }
     if (hitp) {
       in.ray_o = ps.ray_o[p]; in.ray_d = ps.ray_d[p]; in.thr = ps.thr[p]; in.pix = ps.pixel[p]; in.smp = ps.sample[p];
       shade_path(in, prims, sc, rp.seed, rp.max_depth, depth, out, sink);
@@ -373,6 +380,7 @@ struct DevState {
   int trace_blocks = 148 * 6;
   void* d_nodes = nullptr; void* d_prims = nullptr; void* d_shade = nullptr; void* d_prims64 = nullptr;
   void* d_bsdf = nullptr; void* d_lights = nullptr;
+  float* d_env_rgb = nullptr; float* d_env_tp = nullptr; float* d_env_t = nullptr; float* d_env_pgt = nullptr;
   size_t cap_paths = 0, cap_shadow = 0;
   PathState ps{}; ShadowQueue sq{};
   uint32_t* queue[2] = {nullptr, nullptr};
@@ -407,6 +415,8 @@ struct dsrt_ctx {
   int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20, opt_wait_mode = 0;
   WideBVH wide;
   std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
+  int env_w = 0, env_h = 0;
+  std::vector<float> env_rgb, env_tp, env_t, env_pgt;
   double scene_diag = 1.0;
   int n_lights = 0, n_light_samples = 0;
 };
@@ -458,6 +468,7 @@ void free_device(DevState& D) {
   cudaSetDevice(D.device);
   if (D.stream) cudaStreamSynchronize(D.stream);
   dev_free(D.d_nodes); dev_free(D.d_prims); dev_free(D.d_shade); dev_free(D.d_prims64); dev_free(D.d_bsdf); dev_free(D.d_lights);
+  dev_free(D.d_env_rgb); dev_free(D.d_env_tp); dev_free(D.d_env_t); dev_free(D.d_env_pgt);
   dev_free(D.ps.ray_o); dev_free(D.ps.ray_d); dev_free(D.ps.hit); dev_free(D.ps.thr); dev_free(D.ps.pixel); dev_free(D.ps.sample);
   dev_free(D.queue[0]); dev_free(D.queue[1]); dev_free(D.sq.a); dev_free(D.sq.b); dev_free(D.sq.c);
   dev_free(D.d_counters); dev_free(D.d_totals); dev_free(D.d_accum_own); dev_free(D.d_stage);
@@ -610,6 +621,20 @@ int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t
   return DSRT_OK;
 }
 
+// PathTracer's envmap constructor argument (pathtracer.cpp:41-45): the EnvironmentLight is appended after the scene's
+// lights and also lights camera / specular rays that miss the scene.  width == 0 removes it.
+int dsrt_set_envmap(dsrt_ctx* ctx, int32_t width, int32_t height, const float* rgb) {
+  if (!ctx) return DSRT_ERR_INVALID;
+  if (width < 0 || height < 0 || ((width > 0) != (height > 0)) || (width > 0 && !rgb)) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_envmap: bad size / null data");
+  ctx->env_w = width; ctx->env_h = height;
+  if (width > 0) {
+    ctx->env_rgb.assign(rgb, rgb + (size_t)width * height * 3);
+    build_env_tables(width, height, ctx->env_rgb.data(), ctx->env_tp, ctx->env_t, ctx->env_pgt);
+  } else { ctx->env_rgb.clear(); ctx->env_tp.clear(); ctx->env_t.clear(); ctx->env_pgt.clear(); }
+  ctx->have_accel = false;
+  return DSRT_OK;
+}
+
 int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
   if (!ctx || !name) return DSRT_ERR_INVALID;
   std::string n(name);
@@ -642,7 +667,7 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
   ctx->scene_diag = std::sqrt(dg) + 1.0;
 
   flatten_records(s, ctx->wide, ctx->recs, ctx->shd, ctx->r64);
-  ctx->n_light_samples = flatten_lights((int)ctx->light_type.size(), ctx->light_type.data(), ctx->light_param.data(), ctx->ns_area_light, ctx->lights);
+  ctx->n_light_samples = flatten_lights((int)ctx->light_type.size(), ctx->light_type.data(), ctx->light_param.data(), ctx->ns_area_light, ctx->env_w > 0, ctx->lights);
   ctx->n_lights = (int)ctx->lights.size();
   for (DevState& D : ctx->devs) {      // new sizes: (re)allocate the device copies
     CK(cudaSetDevice(D.device));
@@ -655,6 +680,13 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
     CK(cudaMalloc(&D.d_prims64, std::max<size_t>(n * sizeof(PrimRecord64), 16)));
     CK(cudaMalloc(&D.d_bsdf, std::max<size_t>(ctx->bsdfs.size() * sizeof(Bsdf), 16)));
     CK(cudaMalloc(&D.d_lights, std::max<size_t>(ctx->lights.size() * sizeof(Light), 16)));
+    dev_free(D.d_env_rgb); dev_free(D.d_env_tp); dev_free(D.d_env_t); dev_free(D.d_env_pgt);
+    D.d_env_rgb = D.d_env_tp = D.d_env_t = D.d_env_pgt = nullptr;
+    if (ctx->env_w > 0) {
+      const size_t np = (size_t)ctx->env_w * ctx->env_h;
+      CK(cudaMalloc((void**)&D.d_env_rgb, np * 3 * sizeof(float))); CK(cudaMalloc((void**)&D.d_env_tp, np * sizeof(float)));
+      CK(cudaMalloc((void**)&D.d_env_t, (size_t)ctx->env_h * sizeof(float))); CK(cudaMalloc((void**)&D.d_env_pgt, np * sizeof(float)));
+    }
     // persistent grid = resident CTAs per SM (registers / shared-memory stack) x SM count
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, false>, kTraceThreads, stack_bytes(ctx)));
@@ -680,6 +712,13 @@ int dsrt_upload_accel(dsrt_ctx* ctx) {
     }
     if (!ctx->bsdfs.empty()) CK(cudaMemcpyAsync(D.d_bsdf, ctx->bsdfs.data(), ctx->bsdfs.size() * sizeof(Bsdf), cudaMemcpyHostToDevice, D.stream));
     if (!ctx->lights.empty()) CK(cudaMemcpyAsync(D.d_lights, ctx->lights.data(), ctx->lights.size() * sizeof(Light), cudaMemcpyHostToDevice, D.stream));
+    if (ctx->env_w > 0) {
+      const size_t np = (size_t)ctx->env_w * ctx->env_h;
+      CK(cudaMemcpyAsync(D.d_env_rgb, ctx->env_rgb.data(), np * 3 * sizeof(float), cudaMemcpyHostToDevice, D.stream));
+      CK(cudaMemcpyAsync(D.d_env_tp, ctx->env_tp.data(), np * sizeof(float), cudaMemcpyHostToDevice, D.stream));
+      CK(cudaMemcpyAsync(D.d_env_t, ctx->env_t.data(), (size_t)ctx->env_h * sizeof(float), cudaMemcpyHostToDevice, D.stream));
+      CK(cudaMemcpyAsync(D.d_env_pgt, ctx->env_pgt.data(), np * sizeof(float), cudaMemcpyHostToDevice, D.stream));
+    }
   }
   for (DevState& D : ctx->devs) { CK(cudaSetDevice(D.device)); CK(cudaStreamSynchronize(D.stream)); }
   return DSRT_OK;
@@ -689,7 +728,8 @@ int dsrt_accel_bytes(const dsrt_ctx* ctx, int64_t* h2d_bytes) {
   if (!ctx || !ctx->have_accel || !h2d_bytes) return DSRT_ERR_INVALID;
   const size_t n = ctx->wide.slot_prim.size();
   *h2d_bytes = (int64_t)(ctx->wide.nodes.size() * sizeof(WideNode) + n * (sizeof(PrimRecord) + sizeof(ShadeRecord) + sizeof(PrimRecord64)) +
-                         ctx->bsdfs.size() * sizeof(Bsdf) + ctx->lights.size() * sizeof(Light));
+                         ctx->bsdfs.size() * sizeof(Bsdf) + ctx->lights.size() * sizeof(Light) +
+                         (size_t)ctx->env_w * ctx->env_h * 5 * sizeof(float) + (size_t)ctx->env_h * sizeof(float));
   return DSRT_OK;
 }
 
@@ -731,6 +771,8 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
 
   SceneDev sc; sc.bsdf = (const Bsdf*)D.d_bsdf; sc.lights = (const Light*)D.d_lights; sc.shade = (const float4*)D.d_shade;
   sc.n_lights = ctx->n_lights; sc.n_light_samples = nls;
+  sc.env.rgb = D.d_env_rgb; sc.env.pThetaPhi = D.d_env_tp; sc.env.pTheta = D.d_env_t; sc.env.pPhiGivenTheta = D.d_env_pgt;
+  sc.env.w = ctx->env_w; sc.env.h = ctx->env_h;
   RenderParams rp; rp.cam = ctx->cam; rp.seed = ctx->seed; rp.max_depth = ctx->max_depth; rp.spp_begin = spp_begin; rp.spp_stride = spp_stride;
   rp.n_pix_padded = npp; rp.blocks_x = blocks_x; rp.skip_null_shadow = (int)ctx->opt_skip_null; rp.batch_first_sample = 0;
   const Accel A = make_accel(ctx, D, false);

@@ -1,6 +1,8 @@
 // main.cpp -- `pathtracer`: command-line front end with the reference's flags (reference src/main.cpp:71-188).
 //   -s <spp>  -l <area-light samples>  -m <max ray depth>  -t <threads, accepted and ignored>  -w <width>  -h <height>
 //   -f <cam_*.info>  -c (CPU render: refused, there is no CPU fallback)  -v (viewer: not part of this port)
+//   -e <environment map>: the reference declares -e but leaves it out of its getopt string (main.cpp:85, 99-101) and
+//      loads .exr through the vendored tinyexr; here -e works and reads a binary .pfm (PF, little endian) lat-long map
 // additions: -g <number of GPUs>  -o <output.png>  -S <seed>  -r <raw float dump of the linear buffer>
 // As in the reference, -h is the frame HEIGHT and the default frame is 1000x1000 (main.cpp:79-80).
 #include <unistd.h>
@@ -14,12 +16,28 @@
 
 using namespace dsrt_host;
 
+// Portable float map: "PF\n<w> <h>\n<-scale>\n" + h rows of w RGB float triplets, BOTTOM row first.
+static bool load_pfm(const std::string& path, HDRImageBuffer& img, std::string& err) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) { err = "cannot open " + path; return false; }
+  char magic[3] = {0, 0, 0}; int w = 0, h = 0; float scale = 0;
+  if (fscanf(f, "%2s %d %d %f", magic, &w, &h, &scale) != 4 || std::string(magic) != "PF" || w <= 0 || h <= 0) { fclose(f); err = "not a colour .pfm: " + path; return false; }
+  fgetc(f);
+  if (scale > 0) { fclose(f); err = "big-endian .pfm is not supported"; return false; }
+  img.resize((size_t)w, (size_t)h);
+  for (int y = h - 1; y >= 0; y--)      // file is bottom-up; the environment map wants row 0 = +y pole
+    if (fread(&img.data[(size_t)y * w * 3], sizeof(float), (size_t)w * 3, f) != (size_t)w * 3) { fclose(f); err = "truncated .pfm"; return false; }
+  fclose(f);
+  return true;
+}
+
 static void usage(const char* bin) {
   printf("Usage: %s [options] <scenefile.dae>\n", bin);
   printf("  -s <INT>  camera rays per pixel (default 1)\n  -l <INT>  samples per area light (default 4)\n");
   printf("  -t <INT>  render threads (ignored: the render runs on the GPU)\n  -m <INT>  maximum ray depth (default 1)\n");
   printf("  -w <INT>  frame width (default 1000)\n  -h <INT>  frame height (default 1000)\n  -f <FILE> camera .info file\n");
   printf("  -g <INT>  number of GPUs (default 1)\n  -o <FILE> output PNG (default \"Screen Shot GPU <time>.png\")\n");
+  printf("  -e <FILE> lat-long environment map (.pfm)\n");
   printf("  -S <INT>  Philox seed (default 0)\n  -r <FILE> also dump the linear float RGB buffer\n");
 }
 
@@ -28,9 +46,9 @@ int main(int argc, char** argv) {
   int screenW = 1000, screenH = 1000, n_gpus = 1;
   unsigned seed = 0;
   bool useCPU = false;
-  std::string camFileName, outName, rawName;
+  std::string camFileName, outName, rawName, envName;
   int opt;
-  while ((opt = getopt(argc, argv, "s:l:t:m:f:w:h:g:o:S:r:vc")) != -1) {
+  while ((opt = getopt(argc, argv, "s:l:t:m:f:w:h:g:o:S:r:e:vc")) != -1) {
     switch (opt) {
       case 's': ns_aa = (size_t)atoi(optarg); break;
       case 'l': ns_area_light = (size_t)atoi(optarg); break;
@@ -43,6 +61,7 @@ int main(int argc, char** argv) {
       case 'o': outName = optarg; break;
       case 'S': seed = (unsigned)strtoul(optarg, nullptr, 10); break;
       case 'r': rawName = optarg; break;
+      case 'e': envName = optarg; break;
       case 'c': useCPU = true; break;
       case 'v': fprintf(stderr, "the interactive viewer is not part of this port\n"); return 1;
       default: usage(argv[0]); return 1;
@@ -55,7 +74,9 @@ int main(int argc, char** argv) {
 
   FlatScene scene; HostCamera camera; std::string err;
   if (!load_collada(sceneFilePath, (size_t)screenW, (size_t)screenH, scene, camera, err)) { fprintf(stderr, "error: %s\n", err.c_str()); return 1; }
-  PathTracer pathtracer(ns_aa, max_ray_depth, ns_area_light, 1, 1, 1, num_threads, nullptr);
+  HDRImageBuffer envmap;
+  if (!envName.empty() && !load_pfm(envName, envmap, err)) { fprintf(stderr, "error: %s\n", err.c_str()); return 1; }
+  PathTracer pathtracer(ns_aa, max_ray_depth, ns_area_light, 1, 1, 1, num_threads, envName.empty() ? nullptr : &envmap);
   pathtracer.set_gpus(n_gpus); pathtracer.set_seed(seed);
   pathtracer.set_camera(&camera);
   pathtracer.set_scene(&scene);

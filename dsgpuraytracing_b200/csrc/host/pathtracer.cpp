@@ -19,7 +19,7 @@ PathTracer::PathTracer(size_t ns_aa_, size_t max_ray_depth_, size_t ns_area_ligh
   ns_refr = ns_refr_;
   (void)ns_glsy_;
   numWorkerThreads = num_threads;
-  if (envmap) error = "environment maps are not reachable from the reference CLI (main.cpp:85) and are not supported yet";
+  envMap = envmap;                                 // pathtracer.cpp:41-45: becomes an EnvironmentLight appended to the scene
 }
 
 PathTracer::~PathTracer() { if (ctx) dsrt_destroy(ctx); }
@@ -109,6 +109,7 @@ void PathTracer::start_raytracing() {
     dsrt_bvh2 b{}; b.n_nodes = (int)node_start.size(); b.node_bbox = node_bbox.data(); b.node_start = node_start.data();
     b.node_range = node_range.data(); b.node_left = node_left.data(); b.node_right = node_right.data(); b.prim_order = prim_order.data();
     if (dsrt_set_scene(ctx, &sc)) { fail("dsrt_set_scene"); state = READY; return; }
+    if (envMap && dsrt_set_envmap(ctx, (int)envMap->w, (int)envMap->h, envMap->data.data())) { fail("dsrt_set_envmap"); state = READY; return; }
     if (dsrt_set_bvh(ctx, &b)) { fail("dsrt_set_bvh"); state = READY; return; }
   }
   if (dsrt_set_params(ctx, (int)ns_aa, (int)ns_area_light, (int)max_ray_depth, seed)) { fail("dsrt_set_params"); state = READY; return; }

@@ -59,6 +59,7 @@ class PathTracer {
   const std::string& last_error() const { return error; }
   const dsrt_stats& stats() const { return last_stats; }
 
+  HDRImageBuffer* envMap = nullptr;   // lat-long environment map (row 0 = +y pole), optional
   bool useCPU = false;
   State state = INIT;
   Scene* scene = nullptr;

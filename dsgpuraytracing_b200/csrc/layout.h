@@ -76,6 +76,15 @@ struct Light {      // float restatement of light_param
   int32_t n_samples;
 };
 
+// Lat-long environment map + the importance-sampling tables of EnvironmentLight (environment_light.cpp:6-53)
+struct EnvMap {
+  const float* rgb;             // h*w*3
+  const float* pThetaPhi;       // h*w   joint pdf (normalised illum * sin theta)
+  const float* pTheta;          // h     marginal CDF
+  const float* pPhiGivenTheta;  // h*w   conditional CDFs
+  int w, h;                     // w == 0: no environment light
+};
+
 struct Camera {
   float pos[3];
   float c2w[9];     // column-major

@@ -140,6 +140,50 @@ DSRT_HD V3 light_sample_L(const Light& L, V3 p, float u0, float u1, V3* wi, floa
   }
 }
 
+// ---- EnvironmentLight (environment_light.cpp:71-199), float restatement -------------------------------------------
+DSRT_HD int env_lower_bound(const float* a, int n, float v) {      // std::lower_bound
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = lo + ((hi - lo) >> 1); if (a[mid] < v) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+// sample_dir: bilinear lookup with wrap-around (:129-199)
+DSRT_HD V3 env_sample_dir(const EnvMap& e, V3 d) {
+  const int w = e.w, h = e.h;
+  const float dy = fminf(fmaxf(d.y, -1.0f), 1.0f);
+  const float theta = acosf(dy);
+  const float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - dy * dy));
+  float phi = sin_theta == 0.0f ? kPi : acosf(fminf(fmaxf(d.z / sin_theta, -1.0f), 1.0f));
+  if (d.x > 0.0f) phi = 2.0f * kPi - phi;
+  const float tu = phi / (2.0f * kPi) * (float)w - 0.5f, tv = theta / kPi * (float)h - 0.5f;
+  const int su = (int)tu, sv = (int)tv;
+  float a, b; int px1, px2, py1, py2;
+  if (tu < 0.0f) { a = tu + 1.0f; px1 = w - 1; px2 = 0; } else if (tu >= (float)(w - 1)) { a = tu - (float)w + 1.0f; px1 = w - 1; px2 = 0; } else { a = tu - (float)su; px1 = su; px2 = su + 1; }
+  if (tv < 0.0f) { b = tv + 1.0f; py1 = h - 1; py2 = 0; } else if (tv >= (float)(h - 1)) { b = tv - (float)h + 1.0f; py1 = h - 1; py2 = 0; } else { b = tv - (float)sv; py1 = sv; py2 = sv + 1; }
+  const float* p11 = e.rgb + 3 * (px1 + w * py1); const float* p21 = e.rgb + 3 * (px2 + w * py1);
+  const float* p12 = e.rgb + 3 * (px1 + w * py2); const float* p22 = e.rgb + 3 * (px2 + w * py2);
+  const V3 zy1 = (1.0f - a) * v3(p11[0], p11[1], p11[2]) + a * v3(p21[0], p21[1], p21[2]);
+  const V3 zy2 = (1.0f - a) * v3(p12[0], p12[1], p12[2]) + a * v3(p22[0], p22[1], p22[2]);
+  return (1.0f - b) * zy1 + b * zy2;
+}
+// importanceSampling (:71-113): inverse-CDF over theta rows, then over phi within the row, piecewise linear
+DSRT_HD void env_importance(const EnvMap& e, float r1, float r2, V3* wi, float* pdf) {
+  const int w = e.w, h = e.h;
+  r1 *= e.pTheta[h - 1];
+  int t = env_lower_bound(e.pTheta, h, r1); if (t >= h) t = h - 1;
+  float prev = t > 0 ? e.pTheta[t - 1] : 0.0f;
+  const float y = (float)t + (r1 - prev) / (e.pTheta[t] - prev);
+  const float theta = fminf(y / (float)h, 1.0f) * kPi;
+  const float* row = e.pPhiGivenTheta + (size_t)t * w;
+  r2 *= row[w - 1];
+  int q = env_lower_bound(row, w, r2); if (q >= w) q = w - 1;
+  prev = q > 0 ? row[q - 1] : 0.0f;
+  const float x = (float)q + (r2 - prev) / (row[q] - prev);
+  const float phi = fminf(x / (float)w, 1.0f) * 2.0f * kPi;
+  const float st = sinf(theta), ct = cosf(theta);
+  *pdf = e.pThetaPhi[(size_t)t * w + q] / (st * (2.0f * kPi / (float)w) * (kPi / (float)h));
+  *wi = v3(-st * sinf(phi), ct, st * cosf(phi));
+}
+
 // Camera::generate_ray, camera.cpp:113-129 (x,y in [0,1])
 DSRT_HD void generate_ray(const Camera& c, float x, float y, V3* o, V3* d) {
   const V3 sp = v3(-(x - 0.5f) * c.w_over_dist, -(y - 0.5f) * c.h_over_dist, 1.0f);
@@ -156,6 +200,7 @@ struct SceneDev {
   const float4* shade;   // 3 float4 per slot: vertex normals
   int n_lights;
   int n_light_samples;   // sum over lights of samples per vertex
+  EnvMap env;            // env.w == 0 when there is no EnvironmentLight
 };
 struct PathIn { float4 ray_o, ray_d, thr, hit; uint32_t pix, smp; };
 struct PathOut {
@@ -203,12 +248,17 @@ DSRT_HD void shade_path(const PathIn& in, const float4* __restrict__ prims, cons
     for (int i = 0; i < L.n_samples; i++) {
       const int j = L.sample_base + i;
       float u0 = 0.f, u1 = 0.f;
-      if (L.type == 1 || L.type == 3) {
+      if (L.type == 1 || L.type >= 3) {
         const float4 u = rng_block(seed, in.pix, in.smp, (uint32_t)depth, kBlockLight0 + (uint32_t)(j >> 1));
         u0 = (j & 1) ? u.z : u.x; u1 = (j & 1) ? u.w : u.y;
       }
-      V3 wi; float dist, pdf;
-      const V3 light_L = light_sample_L(L, hit_p, u0, u1, &wi, &dist, &pdf);
+      V3 wi; float dist, pdf; V3 light_L;
+      if (L.type == 4) {                          // EnvironmentLight::sample_L, environment_light.cpp:115-127
+        env_importance(sc.env, u0, u1, &wi, &pdf); dist = kInfF;
+        light_L = env_sample_dir(sc.env, wi);
+      } else {
+        light_L = light_sample_L(L, hit_p, u0, u1, &wi, &dist, &pdf);
+      }
       const V3 w_in = normalize(to_local(fr, wi));
       const float cos_theta = fmaxf(0.0f, w_in.z);
       const V3 contrib = (cos_theta / pdf * scale) * (thr * (light_L * f_direct));

@@ -251,7 +251,8 @@ void flatten_records(const dsrt_scene& sc, const WideBVH& wide, std::vector<Prim
   }
 }
 
-int flatten_lights(int n_lights, const int32_t* light_type, const double* light_param, int ns_area_light, std::vector<Light>& lights) {
+int flatten_lights(int n_lights, const int32_t* light_type, const double* light_param, int ns_area_light, bool with_env,
+                   std::vector<Light>& lights) {
   lights.assign((size_t)n_lights, Light{});
   int base = 0;
   for (int i = 0; i < n_lights; i++) {
@@ -265,7 +266,36 @@ int flatten_lights(int n_lights, const int32_t* light_type, const double* light_
     L.n_samples = L.is_delta ? 1 : ns_area_light;          // pathtracer.cpp:474
     L.sample_base = base; base += L.n_samples;
   }
+  if (with_env) {   // PathTracer::set_scene appends the environment light after the scene's lights (pathtracer.cpp:88-90)
+    Light L; std::memset(&L, 0, sizeof(L));
+    L.type = 4; L.is_delta = 0; L.n_samples = ns_area_light; L.sample_base = base; base += L.n_samples;
+    lights.push_back(L);
+  }
   return base;
+}
+
+void build_env_tables(int w, int h, const float* rgb, std::vector<float>& tp, std::vector<float>& t, std::vector<float>& pgt) {
+  const double PI = 3.14159265358979323;
+  tp.assign((size_t)w * h, 0.f); t.assign((size_t)h, 0.f); pgt.assign((size_t)w * h, 0.f);
+  float C = 0;
+  for (int y = 0; y < h; y++) {
+    const float theta = (float)((y + 0.5) / h * PI);
+    const float sin_theta = (float)std::sin((double)theta);
+    for (int x = 0; x < w; x++) {
+      const float* q = rgb + 3 * ((size_t)x + (size_t)w * y);
+      const float illum = 0.2126f * q[0] + 0.7152f * q[1] + 0.0722f * q[2];
+      tp[(size_t)y * w + x] = illum * sin_theta;
+      C += tp[(size_t)y * w + x];
+    }
+  }
+  for (int y = 0; y < h; y++) {
+    for (int x = 0; x < w; x++) { tp[(size_t)y * w + x] /= C; t[y] += tp[(size_t)y * w + x]; }
+    if (t[y] != 0) for (int x = 0; x < w; x++) pgt[(size_t)y * w + x] = tp[(size_t)y * w + x] / t[y];
+  }
+  for (int y = 0; y < h; y++) {
+    if (y > 0) t[y] += t[y - 1];
+    for (int x = 1; x < w; x++) pgt[(size_t)y * w + x] += pgt[(size_t)y * w + x - 1];
+  }
 }
 
 }  // namespace dsrt

@@ -18,7 +18,11 @@ struct WideBVH {
 void flatten_records(const dsrt_scene& sc, const WideBVH& wide, std::vector<PrimRecord>& recs, std::vector<ShadeRecord>& shd,
                      std::vector<PrimRecord64>& r64);
 // float light table; returns the number of light samples per path vertex (pathtracer.cpp:474)
-int flatten_lights(int n_lights, const int32_t* light_type, const double* light_param, int ns_area_light, std::vector<Light>& out);
+int flatten_lights(int n_lights, const int32_t* light_type, const double* light_param, int ns_area_light, bool with_env,
+                   std::vector<Light>& out);
+// EnvironmentLight constructor (environment_light.cpp:6-53): float tables accumulated in the reference's order
+void build_env_tables(int w, int h, const float* rgb, std::vector<float>& pThetaPhi, std::vector<float>& pTheta,
+                      std::vector<float>& pPhiGivenTheta);
 
 int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err);
 

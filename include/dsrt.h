@@ -98,6 +98,11 @@ int dsrt_set_bvh(dsrt_ctx* ctx, const dsrt_bvh2* bvh);        /* loadBVH, setup.
  * replaces loadCamera, setup.cu:221-247 */
 int dsrt_set_camera(dsrt_ctx* ctx, const double* pos, const double* c2w, int32_t width, int32_t height,
                     double screen_dist);
+/* Lat-long environment map (row 0 = +y pole, width*height*3 floats): PathTracer's `envmap` constructor argument
+ * (src/pathtracer.cpp:41-45) -> EnvironmentLight (src/static_scene/environment_light.cpp).  The light is appended after
+ * the scene's lights; rays that leave the scene with includeLe see the map.  width == height == 0 removes it.
+ * Call before dsrt_build_accel. */
+int dsrt_set_envmap(dsrt_ctx* ctx, int32_t width, int32_t height, const float* rgb);
 /* ns_aa (-s), ns_area_light (-l), max_ray_depth (-m); replaces loadParameters, setup.cu:777-811 */
 int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t max_ray_depth, uint32_t seed);
 /* named knobs: "count_traversal" (0/1), "batch_spp" (camera samples per pixel per wavefront batch),

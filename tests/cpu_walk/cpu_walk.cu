@@ -24,6 +24,7 @@ struct Walk {
   std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
   std::vector<Bsdf> bsdfs;
   int n_light_samples = 0;
+  int env_w = 0, env_h = 0; std::vector<float> env_rgb, env_tp, env_t, env_pgt;
   double scene_diag = 1;
   Camera cam;
   std::string err;
@@ -37,12 +38,13 @@ static Accel accel_of(const Walk* w, bool parity) {
 
 extern "C" {
 
-Walk* cw_create(const dsrt_scene* s, const dsrt_bvh2* b, int ns_area_light) {
+Walk* cw_create(const dsrt_scene* s, const dsrt_bvh2* b, int ns_area_light, int env_w, int env_h, const float* env_rgb) {
   Walk* w = new Walk();
+  if (env_w > 0) { w->env_w = env_w; w->env_h = env_h; w->env_rgb.assign(env_rgb, env_rgb + (size_t)env_w * env_h * 3); build_env_tables(env_w, env_h, w->env_rgb.data(), w->env_tp, w->env_t, w->env_pgt); }
   std::vector<Box3> pbox; primitive_boxes(s, pbox);
   if (build_wide_bvh(*b, pbox, s->n_prims, w->wide, w->err)) { fprintf(stderr, "cw_create: %s\n", w->err.c_str()); delete w; return nullptr; }
   flatten_records(*s, w->wide, w->recs, w->shd, w->r64);
-  w->n_light_samples = flatten_lights(s->n_lights, s->light_type, s->light_param, ns_area_light, w->lights);
+  w->n_light_samples = flatten_lights(s->n_lights, s->light_type, s->light_param, ns_area_light, env_w > 0, w->lights);
   w->bsdfs.resize(s->n_bsdf);
   for (int i = 0; i < s->n_bsdf; i++) { Bsdf& q = w->bsdfs[i]; const float* p = s->bsdf_param + 8 * i; for (int k = 0; k < 3; k++) { q.a[k] = p[k]; q.b[k] = p[3 + k]; } q.ior = p[6]; q.type = s->bsdf_type[i]; }
   Box3 all; all.reset(); for (auto& p : pbox) all.grow(p);
@@ -154,6 +156,8 @@ void cw_render(Walk* w, int spp_begin, int spp_count, int spp_stride, int spp_to
   std::vector<uint2> stack(kStackEntries);
   SceneDev sc; sc.bsdf = w->bsdfs.data(); sc.lights = w->lights.data(); sc.shade = (const float4*)w->shd.data();
   sc.n_lights = (int)w->lights.size(); sc.n_light_samples = w->n_light_samples;
+  sc.env.rgb = w->env_rgb.data(); sc.env.pThetaPhi = w->env_tp.data(); sc.env.pTheta = w->env_t.data(); sc.env.pPhiGivenTheta = w->env_pgt.data();
+  sc.env.w = w->env_w; sc.env.h = w->env_h;
   uint64_t camera = 0, extend = 0, shadow = 0, cn = 0, cp = 0;
   for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) {
     float px[3] = {0, 0, 0};
@@ -171,7 +175,13 @@ void cw_render(Walk* w, int spp_begin, int spp_count, int spp_stride, int spp_to
         TraceHit h; TraceCounters k; k.nodes = k.prims = 0;
         trace_ray<false, false, true>(A, r, nullptr, stack.data(), 1, h, nullptr, &k);
         extend++; cn += k.nodes; cp += k.prims;
-        if (h.slot < 0) break;
+        if (h.slot < 0) {
+          if (sc.env.w > 0 && ((hd_f2i(in.thr.w) >> 8) & 1)) {
+            const V3 e = v3(in.thr.x, in.thr.y, in.thr.z) * env_sample_dir(sc.env, v3(in.ray_d.x, in.ray_d.y, in.ray_d.z));
+            px[0] += e.x; px[1] += e.y; px[2] += e.z;
+          }
+          break;
+        }
         in.hit = make_float4(h.t, h.u, h.v, hd_i2f(h.slot));
         PathOut out; ImmediateSink sink{w, A, stack.data(), px, &shadow, &cn, &cp};
         shade_path(in, A.prims, sc, seed, max_depth, depth, out, sink);

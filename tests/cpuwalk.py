@@ -22,7 +22,7 @@ def lib():
 
 
 class Walk:
-    def __init__(self, arr, bvh, ns_area_light=4, camera=None):
+    def __init__(self, arr, bvh, ns_area_light=4, camera=None, envmap=None):
         L = lib()
         keep = []
         s = _scene_struct(arr, keep)
@@ -30,7 +30,9 @@ class Walk:
               _c(bvh["node_left"], np.int32), _c(bvh["node_right"], np.int32), _c(bvh["prim_order"], np.int32)]
         b = _Bvh2(); b.n_nodes = len(kb[1])
         (b.node_bbox, b.node_start, b.node_range, b.node_left, b.node_right, b.prim_order) = [k.ctypes.data for k in kb]
-        self.h = C.c_void_p(L.cw_create(C.byref(s), C.byref(b), int(ns_area_light)))
+        env = _c(envmap, np.float32) if envmap is not None else None
+        self.h = C.c_void_p(L.cw_create(C.byref(s), C.byref(b), int(ns_area_light), env.shape[1] if env is not None else 0,
+                                        env.shape[0] if env is not None else 0, C.c_void_p(env.ctypes.data) if env is not None else None))
         if not self.h:
             raise RuntimeError("cw_create failed")
         self.n_prims = s.n_prims

@@ -269,3 +269,21 @@ def test_multi_device_context_matches_single(golden):
     b, sb = two.render(); two.close()
     assert sb.camera_samples == sa.camera_samples and sb.extend_rays == sa.extend_rays and sb.shadow_rays == sa.shadow_rays
     assert np.allclose(a, b, rtol=1e-4, atol=1e-5 * a.mean())
+
+
+@pytest.mark.parametrize("name", ["env_CBspheres", "env_bunny", "env_CBgems"])
+def test_environment_light_gpu(name, core, golden):
+    """dsrt_set_envmap: EnvironmentLight::sample_L as a light + sample_dir on rays that leave the scene."""
+    g = golden(name); depth = int(g["depth"]); W, H = SMALL_RES
+    ref, cnt = O.Scene(g).render(W, H, 8, 4, depth, rng="philox", seed=21)
+    keep = g["light_type"] != 4
+    arr = dict(g); arr["light_type"] = g["light_type"][keep]; arr["light_param"] = g["light_param"][keep]
+    core.set_params(8, 4, depth, 21)
+    core.set_envmap(g["env_rgb"])
+    core.load(arr, camera=g["camera"])
+    rgb, st = core.render()
+    core.set_envmap(None)
+    assert abs(int(st.extend_rays) - int(cnt[0])) <= 2e-4 * cnt[0] + 2
+    assert abs(int(st.shadow_rays) - int(cnt[1])) <= 2e-4 * cnt[1] + 8
+    ok, info = images_match(rgb, ref)
+    assert ok, info

@@ -203,3 +203,21 @@ def test_wide_bvh_never_culls_a_hit(name, golden):
     bi, bt = w.trace_brute(o, d)
     assert np.array_equal(ids, bi), f"{(ids != bi).sum()} rays culled"
     assert np.array_equal(ts, bt)
+
+
+def split_env(g):
+    """golden env scene -> (scene arrays without the type-4 light, env map)"""
+    keep = g["light_type"] != 4
+    arr = dict(g); arr["light_type"] = g["light_type"][keep]; arr["light_param"] = g["light_param"][keep]
+    return arr, g["env_rgb"]
+
+
+@pytest.mark.parametrize("name", ["env_CBspheres", "env_bunny", "env_CBgems"])
+def test_environment_light_float_pipeline_matches_oracle(name, golden):
+    g = golden(name); depth = int(g["depth"]); W, H = SMALL_RES
+    ref, cnt = O.Scene(g).render(W, H, 4, 4, depth, rng="philox", seed=13)
+    arr, env = split_env(g)
+    rgb, c2 = Walk(arr, D.build_bvh2(arr), 4, camera=g["camera"], envmap=env).render(4, depth, seed=13)
+    assert abs(int(c2[1]) - int(cnt[0])) <= 2 and abs(int(c2[2]) - int(cnt[1])) <= 8
+    ok, info = images_match(rgb, ref)
+    assert ok, info

@@ -200,7 +200,12 @@ def run_ours(a):
     rgba = torch.zeros(npix, dtype=torch.int32, device=dev)
     flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)      # 256 MiB > L2
     host_rgb = torch.zeros(npix * 3, dtype=torch.float32).pin_memory()
-    stream = torch.cuda.current_stream(dev)
+    # everything (torch ops, our kernels, the NCCL reduce, the timing events) is ordered on ONE explicit stream; torch's
+    # default stream has handle 0, which the C ABI reads as "use the context's own stream"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    torch.cuda.synchronize(dev)
     spp_local = a.spp // world
 
     def step(i):
@@ -233,6 +238,7 @@ def run_ours(a):
     t1 = time.time()
     ms = e0.elapsed_time(e1)
     st = core.collect_stats()                      # counters / per-stage events of the last step on this rank
+    frame_dev = rgb.cpu().numpy().reshape(a.height, a.width, 3).copy() if rank == 0 else None
     clocks = sampler.stop(t0, t1) if sampler else None
     t = torch.tensor([ms, float(st.segments), float(st.kernel_launches)], dtype=torch.float64, device=dev)
     tmax = t.clone()
@@ -276,6 +282,15 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(tw, op=dist.ReduceOp.MAX)
     e2e_value = seg_step * a.steps / float(tw[0]) / 1e6
+    frame_check = None
+    if rank == 0:      # the device-resident path and the host-buffer path render the same Philox samples
+        fh = host_rgb.numpy().reshape(a.height, a.width, 3)
+        denom = max(float(np.abs(fh).mean()), 1e-12)
+        frame_check = {"mean_rgb": [float(x) for x in frame_dev.mean(axis=(0, 1))],
+                       "device_vs_host_path_mean_abs_diff_rel": float(np.abs(frame_dev - fh).mean() / denom),
+                       "finite": bool(np.isfinite(frame_dev).all())}
+        if not frame_check["finite"] or frame_check["device_vs_host_path_mean_abs_diff_rel"] > 1e-3:
+            raise SystemExit(f"bench.py: frame check failed: {frame_check}")
 
     # ---- roofline of the dominant kernel: algorithmic bytes / CUDA-event time of its launches (last timed step)
     core.set_option("count_traversal", 1)
@@ -315,7 +330,7 @@ def run_ours(a):
                 "segments_per_step": seg_step, "s_per_frame": ms_max / a.steps * 1e-3,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "s_per_frame": float(tw[0]) / a.steps, "scene_prepare_seconds_once": scene_prepare_s},
-                "gpu_launches": launches * a.steps, "clocks": clocks, "roofline": roofline,
+                "gpu_launches": launches * a.steps, "clocks": clocks, "roofline": roofline, "frame_check": frame_check,
                 "stage_seconds_per_step": {"extend": st.extend_seconds, "connect": st.connect_seconds, "generate+shade": st.shade_seconds},
                 "accel": info}
         if world == 1 and not a.no_cpu_baseline:

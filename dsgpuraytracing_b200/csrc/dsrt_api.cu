@@ -58,6 +58,14 @@ struct Counters {             // one block per batch, zeroed with a single memse
   uint32_t work_extend[kMaxDepthSlots];   // persistent-kernel fetch counters
   uint32_t work_connect[kMaxDepthSlots];
 };
+// Deep-path pool (depth >= 1): survivors of several batches' depth-0 pass are gathered and advanced together, so the
+// short-queue iterations (a few % of the rays, but latency bound) run once per group of batches instead of once per batch.
+struct PoolCounters {
+  uint32_t q_count[kMaxDepthSlots];       // [0] = paths appended by the depth-0 passes; [i] = survivors entering iteration i
+  uint32_t s_count[kMaxDepthSlots];
+  uint32_t work_extend[kMaxDepthSlots];
+  uint32_t work_connect[kMaxDepthSlots];
+};
 struct Totals { unsigned long long camera, extend, shadow, nodes[2], prims[2]; };   // [0] extend, [1] connect
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -280,19 +288,22 @@ struct QueueSink {
   }
 };
 
+// dst == ps (in place): survivors keep their slot and are appended to next_queue (pool iterations).
+// dst != ps: survivors are COPIED into dst at an appended index (depth-0 pass of a batch -> the deep-path pool).
 __global__ void __launch_bounds__(128) k_shade(PathState ps, const float4* __restrict__ prims, SceneDev sc, RenderParams rp,
                                                const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
-                                               uint32_t* next_queue, uint32_t* next_count, ShadowQueue sq, uint32_t* s_count,
-                                               float* accum, int depth) {
+                                               PathState dst, uint32_t* next_queue, uint32_t* next_count, uint32_t dst_cap,
+                                               ShadowQueue sq, uint32_t* s_count, float* accum) {
   const uint32_t n = *n_ptr;
   const int lane = threadIdx.x & 31;
+  const bool in_place = dst.ray_o == ps.ray_o;
   for (uint32_t kb = blockIdx.x * blockDim.x; kb < n; kb += gridDim.x * blockDim.x) {
     const uint32_t k = kb + threadIdx.x;
     const bool live = k < n;
     uint32_t p = 0;
     PathIn in; in.hit = make_float4(0, 0, 0, __int_as_float(-1));
     if (live) { p = queue ? queue[k] : k; in.hit = ps.hit[p]; }
-    const bool hitp = live && __float_as_int(in.hit.w) >= 0;     // miss: no environment light from the CLI
+    const bool hitp = live && __float_as_int(in.hit.w) >= 0;
     const unsigned hm = __ballot_sync(kFull, hitp);
     QueueSink sink; sink.sq = sq; sink.base = 0; sink.nh = __popc(hm); sink.rank = __popc(hm & ((1u << lane) - 1u));
     if (hm && sc.n_light_samples > 0) {
@@ -310,6 +321,7 @@ __global__ void __launch_bounds__(128) k_shade(PathState ps, const float4* __res
     }
     if (hitp) {
       in.ray_o = ps.ray_o[p]; in.ray_d = ps.ray_d[p]; in.thr = ps.thr[p]; in.pix = ps.pixel[p]; in.smp = ps.sample[p];
+      const int depth = __float_as_int(in.thr.w) & 0xff;       // Ray::depth travels with the path
       shade_path(in, prims, sc, rp.seed, rp.max_depth, depth, out, sink);
       if (out.has_emission) add_rgb(accum, in.pix, out.emission);
     }
@@ -320,8 +332,14 @@ __global__ void __launch_bounds__(128) k_shade(PathState ps, const float4* __res
       if (lane == leader) base = atomicAdd(next_count, (uint32_t)__popc(cm));
       base = __shfl_sync(kFull, base, leader);
       if (out.cont) {
-        next_queue[base + __popc(cm & ((1u << lane) - 1u))] = p;
-        ps.ray_o[p] = out.new_o; ps.ray_d[p] = out.new_d; ps.thr[p] = out.new_thr;
+        const uint32_t idx = base + __popc(cm & ((1u << lane) - 1u));
+        if (in_place) {
+          next_queue[idx] = p;
+          ps.ray_o[p] = out.new_o; ps.ray_d[p] = out.new_d; ps.thr[p] = out.new_thr;
+        } else if (idx < dst_cap) {
+          dst.ray_o[idx] = out.new_o; dst.ray_d[idx] = out.new_d; dst.thr[idx] = out.new_thr;
+          dst.pixel[idx] = in.pix; dst.sample[idx] = in.smp;
+        }
       }
     }
   }
@@ -329,9 +347,14 @@ __global__ void __launch_bounds__(128) k_shade(PathState ps, const float4* __res
 
 __global__ void k_tally(const Counters* c, Totals* t, uint32_t camera) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    t->camera += camera; t->extend += c->q_count[0]; t->shadow += c->s_count[0];   // depth 0 of one batch
+  }
+}
+__global__ void k_tally_pool(const PoolCounters* c, Totals* t, int iterations) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
     unsigned long long e = 0, s = 0;
-    for (int d = 0; d < kMaxDepthSlots; d++) { e += c->q_count[d]; s += c->s_count[d]; }
-    t->camera += camera; t->extend += e; t->shadow += s;
+    for (int d = 0; d < iterations; d++) { e += c->q_count[d]; s += c->s_count[d]; }
+    t->extend += e; t->shadow += s;
   }
 }
 __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
@@ -384,6 +407,9 @@ struct DevState {
   size_t cap_paths = 0, cap_shadow = 0;
   PathState ps{}; ShadowQueue sq{};
   uint32_t* queue[2] = {nullptr, nullptr};
+  size_t cap_pool = 0, cap_pool_shadow = 0;
+  PathState pool{}; ShadowQueue pool_sq{}; uint32_t* pool_queue[2] = {nullptr, nullptr};
+  PoolCounters* d_pool_counters = nullptr; int n_pool_counter_blocks = 0;
   Counters* d_counters = nullptr; int n_counter_blocks = 0;
   Totals* d_totals = nullptr;
   float* d_accum_own = nullptr; size_t accum_pixels = 0;
@@ -412,7 +438,7 @@ struct dsrt_ctx {
   Camera cam{};
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
-  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20, opt_wait_mode = 0;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20, opt_wait_mode = 0, opt_pool_batches = 8;
   WideBVH wide;
   std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
   int env_w = 0, env_h = 0;
@@ -471,6 +497,8 @@ void free_device(DevState& D) {
   dev_free(D.d_env_rgb); dev_free(D.d_env_tp); dev_free(D.d_env_t); dev_free(D.d_env_pgt);
   dev_free(D.ps.ray_o); dev_free(D.ps.ray_d); dev_free(D.ps.hit); dev_free(D.ps.thr); dev_free(D.ps.pixel); dev_free(D.ps.sample);
   dev_free(D.queue[0]); dev_free(D.queue[1]); dev_free(D.sq.a); dev_free(D.sq.b); dev_free(D.sq.c);
+  dev_free(D.pool.ray_o); dev_free(D.pool.ray_d); dev_free(D.pool.hit); dev_free(D.pool.thr); dev_free(D.pool.pixel); dev_free(D.pool.sample);
+  dev_free(D.pool_queue[0]); dev_free(D.pool_queue[1]); dev_free(D.pool_sq.a); dev_free(D.pool_sq.b); dev_free(D.pool_sq.c); dev_free(D.d_pool_counters);
   dev_free(D.d_counters); dev_free(D.d_totals); dev_free(D.d_accum_own); dev_free(D.d_stage);
   for (cudaEvent_t e : D.ev_pool) cudaEventDestroy(e);
   if (D.ev_begin) cudaEventDestroy(D.ev_begin);
@@ -497,6 +525,29 @@ int ensure_wavefront(dsrt_ctx* ctx, DevState& D, size_t paths, size_t shadow) {
     if ((rc = dev_alloc(ctx, &D.sq.b, shadow))) return rc;
     if ((rc = dev_alloc(ctx, &D.sq.c, shadow))) return rc;
     D.cap_shadow = shadow;
+  }
+  return DSRT_OK;
+}
+
+int ensure_pool(dsrt_ctx* ctx, DevState& D, size_t paths, size_t shadow) {
+  if (paths > D.cap_pool) {
+    int rc;
+    if ((rc = dev_alloc(ctx, &D.pool.ray_o, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.pool.ray_d, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.pool.hit, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.pool.thr, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.pool.pixel, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.pool.sample, paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.pool_queue[0], paths))) return rc;
+    if ((rc = dev_alloc(ctx, &D.pool_queue[1], paths))) return rc;
+    D.cap_pool = paths;
+  }
+  if (shadow > D.cap_pool_shadow) {
+    int rc;
+    if ((rc = dev_alloc(ctx, &D.pool_sq.a, shadow))) return rc;
+    if ((rc = dev_alloc(ctx, &D.pool_sq.b, shadow))) return rc;
+    if ((rc = dev_alloc(ctx, &D.pool_sq.c, shadow))) return rc;
+    D.cap_pool_shadow = shadow;
   }
   return DSRT_OK;
 }
@@ -645,6 +696,7 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
   else if (n == "postpone_min_lanes") ctx->opt_tri_min = value;
   else if (n == "refill_busy_lanes") ctx->opt_refill = value;
   else if (n == "postpone_wait_mode") ctx->opt_wait_mode = value;
+  else if (n == "pool_batches") ctx->opt_pool_batches = std::max<int64_t>(1, value);
   else return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_option: unknown option " + n);
   return DSRT_OK;
 }
@@ -784,40 +836,69 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   auto span_begin = [&](int kind) { if (timing) { DevState::Span s; s.kind = kind; s.e0 = D.ev_used; cudaEventRecord(next_event(D), st); s.e1 = 0; D.spans.push_back(s); } };
   auto span_end = [&]() { if (timing) { D.spans.back().e1 = D.ev_used; cudaEventRecord(next_event(D), st); } };
 
+  // pool: survivors of up to `group` consecutive batches (worst case: every path survives, e.g. a mirror box)
+  const int group = std::max(1, std::min(n_batches, (int)ctx->opt_pool_batches));
+  const int n_groups = (n_batches + group - 1) / group;
+  const size_t pool_cap = P * (size_t)group;
+  if (ctx->max_depth > 0) {
+    if ((rc = ensure_pool(ctx, D, pool_cap, pool_cap * (size_t)std::max(nls, 1)))) return rc;
+    if (n_groups > D.n_pool_counter_blocks) {
+      if ((rc = dev_alloc(ctx, &D.d_pool_counters, (size_t)n_groups))) return rc;
+      D.n_pool_counter_blocks = n_groups;
+    }
+    CK(cudaMemsetAsync(D.d_pool_counters, 0, sizeof(PoolCounters) * (size_t)n_groups, st));
+  }
+  auto trace = [&](bool any, const float4* ro, const float4* rd, const uint32_t* q, const uint32_t* n_ptr, uint32_t* work, float4* hits, const float4* contrib) {
+    span_begin(any ? 1 : 0);
+    if (any) {
+      if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, nullptr, contrib, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
+      else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, nullptr, contrib, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
+    } else {
+      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
+      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
+    }
+    span_end();
+    D.launches++;
+  };
   for (int bi = 0; bi < n_batches; bi++) {
     const int s0 = bi * batch_spp, ns = std::min(batch_spp, spp_count - s0);
     const int n_paths = npp * ns;
     Counters* C = D.d_counters + bi;
+    PoolCounters* PC = ctx->max_depth > 0 ? D.d_pool_counters + bi / group : nullptr;
     rp.batch_first_sample = s0;
+    // ---- depth 0 of this batch: generate, extend, shade (survivors -> pool), connect
     span_begin(2);
     k_generate<<<(n_paths + 255) / 256, 256, 0, st>>>(D.ps, rp, n_paths, D.queue[0], &C->q_count[0], aligned);
     span_end();
     D.launches++;
-    int cur = 0;
-    for (int d = 0; d <= ctx->max_depth; d++) {
-      const uint32_t* q = (d == 0 && aligned) ? nullptr : D.queue[cur];
-      span_begin(0);
-      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
-      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.ps.ray_o, D.ps.ray_d, q, &C->q_count[d], &C->work_extend[d], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
-      span_end();
-      // depth 0 shades every path; deeper levels only shrink, so a capped grid-stride launch is enough
-      const int bound = d == 0 ? n_paths : std::min(n_paths, D.sm_count * 16 * 128);
-      span_begin(2);
-      k_shade<<<(bound + 127) / 128, 128, 0, st>>>(D.ps, (const float4*)D.d_prims, sc, rp, q, &C->q_count[d], D.queue[cur ^ 1], &C->q_count[d + 1],
-                                                   D.sq, &C->s_count[d], d_accum, d);
-      span_end();
-      if (nls > 0) {
-        span_begin(1);
-        if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
-        else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, D.sq.a, D.sq.b, nullptr, &C->s_count[d], &C->work_connect[d], nullptr, D.sq.c, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
-        span_end();
-        D.launches++;
-      }
-      D.launches += 2;
-      cur ^= 1;
-    }
+    const uint32_t* q0 = aligned ? nullptr : D.queue[0];
+    trace(false, D.ps.ray_o, D.ps.ray_d, q0, &C->q_count[0], &C->work_extend[0], D.ps.hit, nullptr);
+    span_begin(2);
+    k_shade<<<(n_paths + 127) / 128, 128, 0, st>>>(D.ps, (const float4*)D.d_prims, sc, rp, q0, &C->q_count[0], D.pool, nullptr,
+                                                   PC ? &PC->q_count[0] : &C->q_count[1], (uint32_t)pool_cap, D.sq, &C->s_count[0], d_accum);
+    span_end();
+    D.launches++;
+    if (nls > 0) trace(true, D.sq.a, D.sq.b, nullptr, &C->s_count[0], &C->work_connect[0], nullptr, D.sq.c);
     k_tally<<<1, 32, 0, st>>>(C, D.d_totals, (uint32_t)((size_t)W * H * ns));
     D.launches++;
+    // ---- after the last batch of a group: advance the pooled paths together, one bounce per iteration
+    if (PC && ((bi + 1) % group == 0 || bi + 1 == n_batches)) {
+      const int pgrid = std::min((int)((pool_cap + 127) / 128), D.sm_count * 16);
+      int cur = 0;
+      for (int it = 0; it < ctx->max_depth; it++) {
+        const uint32_t* q = it == 0 ? nullptr : D.pool_queue[cur];
+        trace(false, D.pool.ray_o, D.pool.ray_d, q, &PC->q_count[it], &PC->work_extend[it], D.pool.hit, nullptr);
+        span_begin(2);
+        k_shade<<<pgrid, 128, 0, st>>>(D.pool, (const float4*)D.d_prims, sc, rp, q, &PC->q_count[it], D.pool, D.pool_queue[cur ^ 1],
+                                       &PC->q_count[it + 1], 0u, D.pool_sq, &PC->s_count[it], d_accum);
+        span_end();
+        D.launches++;
+        if (nls > 0) trace(true, D.pool_sq.a, D.pool_sq.b, nullptr, &PC->s_count[it], &PC->work_connect[it], nullptr, D.pool_sq.c);
+        cur ^= 1;
+      }
+      k_tally_pool<<<1, 32, 0, st>>>(PC, D.d_totals, ctx->max_depth);
+      D.launches++;
+    }
   }
   CK(cudaEventRecord(D.ev_end, st));
   CK(cudaGetLastError());

@@ -28,6 +28,8 @@
 namespace dsrt {
 
 constexpr int kTraceThreads = 128;        // 4 warps per CTA
+constexpr int kRayBlock = 17;             // floats per lane published for the cooperative primitive test
+constexpr int kPairCap = 192;             // (ray, primitive) pairs one warp can deal out per round set
 constexpr int kMaxDepthSlots = 64;        // queue-size slots per batch (depth 0..63)
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -127,11 +129,20 @@ template <bool ANY, bool COUNT>
 __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                          const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
                                                          uint32_t* work, float4* hit_out, const float4* __restrict__ contrib,
-                                                         float* accum, Totals* totals, int tri_min, int refill_busy, int wait_mode, int tri_cap) {
+                                                         float* accum, Totals* totals, int tri_min, int refill_busy, int wait_mode, int tri_cap,
+                                                         int stack_entries, int coop_min) {
   extern __shared__ uint2 smem_stack[];
   uint2* stack = smem_stack + threadIdx.x;
   const int stride = blockDim.x;
   const int lane = threadIdx.x & 31;
+  // shared memory after the stacks (any-hit kernel only): per-lane ray blocks (kRayBlock floats, value-major so that
+  // lanes reading different owners hit different banks), and per-warp (slot, owner) pair tables + hit flags for the
+  // cooperative primitive test
+  float* rayblk = reinterpret_cast<float*>(smem_stack + (size_t)stack_entries * kTraceThreads);
+  uint32_t* pair_slot = reinterpret_cast<uint32_t*>(rayblk + kRayBlock * kTraceThreads) + (threadIdx.x >> 5) * kPairCap;
+  uint8_t* pair_owner = reinterpret_cast<uint8_t*>(reinterpret_cast<uint32_t*>(rayblk + kRayBlock * kTraceThreads) + (kTraceThreads / 32) * kPairCap) + (threadIdx.x >> 5) * kPairCap;
+  uint8_t* hit_flag = reinterpret_cast<uint8_t*>(reinterpret_cast<uint32_t*>(rayblk + kRayBlock * kTraceThreads) + (kTraceThreads / 32) * kPairCap) + (kTraceThreads / 32) * kPairCap + (threadIdx.x & ~31);
+  const int wbase = threadIdx.x & ~31;    // first thread of this warp within the CTA
   const uint32_t n = *n_ptr;
   TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
 
@@ -162,6 +173,16 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
           tbest = ray.tmax; hit.slot = -1; hit.t = ray.tmax; hit.u = 0.f; hit.v = 0.f;
           sp = 0; tstk = 0; ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
           busy = true;
+          if (ANY) {
+            float* rb = rayblk + threadIdx.x;
+            rb[0 * kTraceThreads] = ray.ox; rb[1 * kTraceThreads] = ray.oy; rb[2 * kTraceThreads] = ray.oz;
+            rb[3 * kTraceThreads] = ray.dx; rb[4 * kTraceThreads] = ray.dy; rb[5 * kTraceThreads] = ray.dz;
+            rb[6 * kTraceThreads] = wr.bxx; rb[7 * kTraceThreads] = wr.bxy; rb[8 * kTraceThreads] = wr.bxz;
+            rb[9 * kTraceThreads] = wr.byx; rb[10 * kTraceThreads] = wr.byy; rb[11 * kTraceThreads] = wr.byz;
+            rb[12 * kTraceThreads] = wr.bzx; rb[13 * kTraceThreads] = wr.bzy; rb[14 * kTraceThreads] = wr.bzz;
+            rb[15 * kTraceThreads] = ray.tmax; rb[16 * kTraceThreads] = __int_as_float(ray.src_slot);
+            hit_flag[lane] = 0;
+          }
         }
       }
       if (base + (uint32_t)__popc(idle) >= n) exhausted = true;
@@ -205,23 +226,70 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
       const bool must = pending && !did_node;                          // this lane had no node to open: it needs its primitives now
       const unsigned pm = __ballot_sync(kFull, pending);
       if (pm && ((wait_mode ? !__any_sync(kFull, did_node) : __any_sync(kFull, must)) || __popc(pm) >= tri_min)) {
-        while (pending && tgroup.y) {
-          const uint32_t k = 31u - (uint32_t)__clz(tgroup.y);
-          tgroup.y &= ~(1u << k);
-          const int slot = (int)(tgroup.x + k);
-          if (COUNT) cnt.prims++;
-          const float4* pp = A.prims + (size_t)slot * 3;
-          const float4 a = __ldg(pp), b = __ldg(pp + 1);
-          float t, u = 0.f, v = 0.f; bool h;
-          if (b.w != 0.0f) {
-            const float4 c = __ldg(pp + 2);
-            h = (slot != ray.src_slot) && hit_triangle(ray, wr, a, b, c, tbest, t, u, v);
-          } else {
-            h = hit_sphere(ray, a, b, slot == ray.src_slot, ANY, tbest, t);
+        bool coop = false;
+        if (ANY) {
+          // Cooperative test: the pending (ray, primitive) pairs of the whole warp are dealt out one per lane, so the
+          // long watertight test runs with up to 32 lanes instead of the handful that happen to hold a group.
+          const int c = pending ? __popc(tgroup.y) : 0;
+          int incl = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
+          const int P = __shfl_sync(kFull, incl, 31);
+          if (P >= coop_min && P <= kPairCap) {
+            coop = true;
+            int i = incl - c;
+            uint32_t m = pending ? tgroup.y : 0u;
+            while (m) { const uint32_t k = 31u - (uint32_t)__clz(m); m &= ~(1u << k); pair_slot[i] = tgroup.x + k; pair_owner[i] = (uint8_t)lane; i++; }
+            if (pending) tgroup.y = 0u;
+            __syncwarp();
+            for (int base = 0; base < P; base += 32) {
+              const int j = base + lane;
+              if (j < P) {
+                const int slot = (int)pair_slot[j]; const int s = pair_owner[j];
+                const float* rb = rayblk + wbase + s;
+                TraceRay r2; WatertightRay w2;
+                r2.ox = rb[0 * kTraceThreads]; r2.oy = rb[1 * kTraceThreads]; r2.oz = rb[2 * kTraceThreads];
+                r2.dx = rb[3 * kTraceThreads]; r2.dy = rb[4 * kTraceThreads]; r2.dz = rb[5 * kTraceThreads];
+                w2.bxx = rb[6 * kTraceThreads]; w2.bxy = rb[7 * kTraceThreads]; w2.bxz = rb[8 * kTraceThreads];
+                w2.byx = rb[9 * kTraceThreads]; w2.byy = rb[10 * kTraceThreads]; w2.byz = rb[11 * kTraceThreads];
+                w2.bzx = rb[12 * kTraceThreads]; w2.bzy = rb[13 * kTraceThreads]; w2.bzz = rb[14 * kTraceThreads];
+                const float tmax2 = rb[15 * kTraceThreads]; const int src2 = __float_as_int(rb[16 * kTraceThreads]);
+                if (COUNT) cnt.prims++;
+                const float4* pp = A.prims + (size_t)slot * 3;
+                const float4 a = __ldg(pp), b = __ldg(pp + 1);
+                float t, u, v; bool h;
+                if (b.w != 0.0f) {
+                  const float4 cc = __ldg(pp + 2);
+                  h = (slot != src2) && hit_triangle(r2, w2, a, b, cc, tmax2, t, u, v);
+                } else {
+                  h = hit_sphere(r2, a, b, slot == src2, true, tmax2, t);
+                }
+                if (h) hit_flag[s] = 1;
+              }
+            }
+            __syncwarp();
+            if (pending && hit_flag[lane]) { hit.slot = 0; hit.t = 0.f; done = true; }
           }
-          if (h) {
-            tbest = t; hit.slot = slot; hit.t = t; hit.u = u; hit.v = v;
-            if (ANY) { done = true; break; }
+        }
+        if (!coop) {
+          while (pending && tgroup.y) {
+            const uint32_t k = 31u - (uint32_t)__clz(tgroup.y);
+            tgroup.y &= ~(1u << k);
+            const int slot = (int)(tgroup.x + k);
+            if (COUNT) cnt.prims++;
+            const float4* pp = A.prims + (size_t)slot * 3;
+            const float4 a = __ldg(pp), b = __ldg(pp + 1);
+            float t, u = 0.f, v = 0.f; bool h;
+            if (b.w != 0.0f) {
+              const float4 c = __ldg(pp + 2);
+              h = (slot != ray.src_slot) && hit_triangle(ray, wr, a, b, c, tbest, t, u, v);
+            } else {
+              h = hit_sphere(ray, a, b, slot == ray.src_slot, ANY, tbest, t);
+            }
+            if (h) {
+              tbest = t; hit.slot = slot; hit.t = t; hit.u = u; hit.v = v;
+              if (ANY) { done = true; break; }
+            }
           }
         }
       }
@@ -438,7 +506,7 @@ struct dsrt_ctx {
   Camera cam{};
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
-  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20, opt_wait_mode = 0, opt_pool_batches = 8;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20, opt_wait_mode = 0, opt_pool_batches = 16, opt_coop_min = 6;
   WideBVH wide;
   std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
   int env_w = 0, env_h = 0;
@@ -476,7 +544,12 @@ Accel make_accel(const dsrt_ctx* ctx, const DevState& D, bool parity) {
 
 // shared-memory traversal stack: two entries (node group + postponed primitive group) per wide-BVH level per lane (whatever is not used stays L1 cache)
 int tri_stack_cap(const dsrt_ctx* ctx) { return std::max(ctx->wide.max_depth, 1) + 3; }   // postponed primitive groups a lane may park
-size_t stack_bytes(const dsrt_ctx* ctx) { return (size_t)(std::max(ctx->wide.max_depth, 1) + tri_stack_cap(ctx) + 1) * kTraceThreads * sizeof(uint2); }
+int stack_entries(const dsrt_ctx* ctx) { return std::max(ctx->wide.max_depth, 1) + tri_stack_cap(ctx) + 1; }
+// dynamic shared memory of k_trace: traversal stacks + (any-hit kernel) ray blocks, pair tables, hit flags
+size_t stack_bytes(const dsrt_ctx* ctx) {
+  return (size_t)stack_entries(ctx) * kTraceThreads * sizeof(uint2) + (size_t)kRayBlock * kTraceThreads * sizeof(float) +
+         (size_t)(kTraceThreads / 32) * kPairCap * (sizeof(uint32_t) + 1) + kTraceThreads;
+}
 
 int init_device(dsrt_ctx* ctx, DevState& D, int device) {
   D.device = device;
@@ -697,6 +770,7 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
   else if (n == "refill_busy_lanes") ctx->opt_refill = value;
   else if (n == "postpone_wait_mode") ctx->opt_wait_mode = value;
   else if (n == "pool_batches") ctx->opt_pool_batches = std::max<int64_t>(1, value);
+  else if (n == "coop_min_pairs") ctx->opt_coop_min = value;
   else return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_option: unknown option " + n);
   return DSRT_OK;
 }
@@ -830,7 +904,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   const Accel A = make_accel(ctx, D, false);
   const bool count = ctx->opt_count != 0, timing = ctx->opt_stage_timing != 0;
   const int tgrid = D.trace_blocks;
-  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, tri_cap = tri_stack_cap(ctx);
+  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, tri_cap = tri_stack_cap(ctx), coop_min = (int)ctx->opt_coop_min;
   const size_t sbytes = stack_bytes(ctx);
 
   auto span_begin = [&](int kind) { if (timing) { DevState::Span s; s.kind = kind; s.e0 = D.ev_used; cudaEventRecord(next_event(D), st); s.e1 = 0; D.spans.push_back(s); } };
@@ -851,11 +925,11 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   auto trace = [&](bool any, const float4* ro, const float4* rd, const uint32_t* q, const uint32_t* n_ptr, uint32_t* work, float4* hits, const float4* contrib) {
     span_begin(any ? 1 : 0);
     if (any) {
-      if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, nullptr, contrib, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
-      else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, nullptr, contrib, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
+      if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, nullptr, contrib, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap, stack_entries(ctx), coop_min);
+      else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, nullptr, contrib, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap, stack_entries(ctx), coop_min);
     } else {
-      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
-      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
+      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap, stack_entries(ctx), coop_min);
+      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap, stack_entries(ctx), coop_min);
     }
     span_end();
     D.launches++;
@@ -1039,11 +1113,11 @@ int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) 
     if (D.n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &D.d_counters, (size_t)1))) return rc; D.n_counter_blocks = 1; }
     CK(cudaMemsetAsync(D.d_counters, 0, sizeof(Counters), st));
     RenderParams rp; std::memset(&rp, 0, sizeof(rp)); rp.cam = ctx->cam;
-    const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, tri_cap = tri_stack_cap(ctx);
+    const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, tri_cap = tri_stack_cap(ctx), coop_min = (int)ctx->opt_coop_min;
     k_generate_centres<<<(n + 255) / 256, 256, 0, st>>>(D.ps, rp, n);
     k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
     k_trace<false, false><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(make_accel(ctx, D, false), D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0],
-                                                                            &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
+                                                                            &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap, stack_entries(ctx), coop_min);
     CK(cudaGetLastError());
     std::vector<float4> hits(n);
     CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
@@ -1076,9 +1150,9 @@ static int trace_batch(dsrt_ctx* ctx, bool any, int64_t n, const float* o, const
   CK(cudaMemcpyAsync(D.ps.ray_d, hd.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
   k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
   const Accel A = make_accel(ctx, D, false);
-  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, tri_cap = tri_stack_cap(ctx);
-  if (any) k_trace<true, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
-  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap);
+  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, tri_cap = tri_stack_cap(ctx), coop_min = (int)ctx->opt_coop_min;
+  if (any) k_trace<true, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap, stack_entries(ctx), coop_min);
+  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, tri_cap, stack_entries(ctx), coop_min);
   CK(cudaGetLastError());
   std::vector<float4> hits(n);
   CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));

@@ -184,6 +184,7 @@ def test_arbitrary_rays_closest_any_and_fetch_counters(name, core, golden):
     assert (wid != ids).sum() <= 2
     core.set_option("count_traversal", 1)
     core.set_option("postpone_min_lanes", 0)          # test primitives at once: the order the CPU walk uses
+    core.set_option("coop_min_pairs", 1 << 20)        # ... one lane per ray (no cooperative any-hit tests)
     core.set_params(1, 4, 0, 0)
     # counters of a full render == CPU walk counters of the same wavefront (same code, same rays)
     cam = g["small_camera"]; core.set_camera(cam)
@@ -192,7 +193,8 @@ def test_arbitrary_rays_closest_any_and_fetch_counters(name, core, golden):
     assert abs(int(st.nodes_visited) - int(wc[3])) <= 2e-3 * wc[3]
     assert abs(int(st.prims_tested) - int(wc[4])) <= 2e-3 * wc[4]
     # postponed primitive tests (the default) change the visiting order, never the result
-    core.set_option("postpone_min_lanes", 12)
+    core.set_option("postpone_min_lanes", 20)
+    core.set_option("coop_min_pairs", 6)
     rgb2, st2 = core.render()
     core.set_option("count_traversal", 0)
     assert st2.extend_rays == st.extend_rays and st2.shadow_rays == st.shadow_rays

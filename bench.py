@@ -230,13 +230,16 @@ def run_ours(a):
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.time()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
     e0.record(stream)
     for i in range(a.steps):
         step(i)
+        marks[i].record(stream)
     e1.record(stream)
     fence()
     t1 = time.time()
     ms = e0.elapsed_time(e1)
+    step_ms = [(e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]) for i in range(a.steps)]   # this rank, per step
     st = core.collect_stats()                      # counters / per-stage events of the last step on this rank
     frame_dev = rgb.cpu().numpy().reshape(a.height, a.width, 3).copy() if rank == 0 else None
     clocks = sampler.stop(t0, t1) if sampler else None
@@ -309,6 +312,10 @@ def run_ours(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algo_bytes / sec / 1e9 if sec > 0 else 0.0
+    # L2-resident regime: the denominator is the L2 -> SM read bandwidth, measured live with a read-only
+    # sweep of a 32 MiB buffer by every SM; the same probe over 1 GiB gives the HBM read bandwidth for comparison
+    l2_gbs = core.measure_read_bandwidth(32 << 20, 40)
+    hbm_read_gbs = core.measure_read_bandwidth(1 << 30, 3)
     traffic = None; traffic_detail = None
     try:
         traffic_detail = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
@@ -320,6 +327,9 @@ def run_ours(a):
                 "traffic": traffic, "traffic_detail": traffic_detail, "kernel": dom, "kernel_seconds_per_step": sec,
                 "kernel_share_of_step": sec / (ms_max * 1e-3 / a.steps), "bytes_per_segment": algo_bytes / max(nr, 1),
                 "nodes_per_segment": nn / max(nr, 1), "prims_per_segment": nt / max(nr, 1),
+                "l2": {"read_gbs_measured": l2_gbs, "frac": achieved / l2_gbs if l2_gbs > 0 else None,
+                       "how": "dsrt_measure_read_bandwidth: all SMs sweep one 32 MiB buffer 40x with 128-bit ld.global.cg",
+                       "hbm_read_gbs_same_probe": hbm_read_gbs},
                 "note": "working set (wide BVH + primitive records = %.1f MB) is L2-resident, so the HBM roofline is an upper "
                         "bound the kernel is not expected to approach; the kernel is latency/issue bound" % ((info["node_bytes"] + info["prim_bytes"]) / 1e6)}
 
@@ -331,6 +341,7 @@ def run_ours(a):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "s_per_frame": float(tw[0]) / a.steps, "scene_prepare_seconds_once": scene_prepare_s},
                 "gpu_launches": launches * a.steps, "clocks": clocks, "roofline": roofline, "frame_check": frame_check,
+                "step_ms_rank0": step_ms,
                 "stage_seconds_per_step": {"extend": st.extend_seconds, "connect": st.connect_seconds, "generate+shade": st.shade_seconds},
                 "accel": info}
         if world == 1 and not a.no_cpu_baseline:

@@ -10,7 +10,7 @@ EXPORTED_SYMBOLS = [
     "dsrt_create", "dsrt_create_multi", "dsrt_device_count", "dsrt_destroy", "dsrt_last_error", "dsrt_version", "dsrt_set_scene", "dsrt_set_bvh",
     "dsrt_set_camera", "dsrt_set_params", "dsrt_set_envmap", "dsrt_set_option", "dsrt_build_bvh2", "dsrt_build_accel",
     "dsrt_accel_info", "dsrt_upload_accel", "dsrt_accel_bytes", "dsrt_render", "dsrt_render_device", "dsrt_resolve_device", "dsrt_sync",
-    "dsrt_collect_stats", "dsrt_primary_hits", "dsrt_trace_closest", "dsrt_trace_any", "dsrt_tonemap",
+    "dsrt_collect_stats", "dsrt_primary_hits", "dsrt_trace_closest", "dsrt_trace_any", "dsrt_tonemap", "dsrt_measure_read_bandwidth",
 ]
 
 
@@ -258,6 +258,13 @@ class Core:
                                        C.c_void_p(tm.ctypes.data) if tm is not None else None,
                                        C.c_void_p(hit.ctypes.data)), "dsrt_trace_any")
         return hit
+
+    def measure_read_bandwidth(self, nbytes, repeats=20):
+        """GB/s of a read-only sweep over `nbytes` (32 MiB -> L2 read bandwidth, >> L2 -> HBM read bandwidth)."""
+        g = C.c_double(0)
+        self._ck(self.L.dsrt_measure_read_bandwidth(self.ctx, C.c_int64(int(nbytes)), C.c_int32(int(repeats)), C.byref(g)),
+                 "dsrt_measure_read_bandwidth")
+        return g.value
 
     def tonemap(self, rgb):
         rgb = _c(rgb, np.float32); n = rgb.size // 3

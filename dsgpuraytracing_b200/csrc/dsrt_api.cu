@@ -15,7 +15,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/dsrt.h"
@@ -458,6 +460,22 @@ __global__ void k_resolve_peers(PeerPtrs src, float* rgb, uint32_t* rgba8, int n
   }
 }
 
+// read-bandwidth probe: every CTA sweeps the whole buffer (grid-stride over 128-bit words), `repeats` times
+__global__ void __launch_bounds__(256) k_read_sweep(const uint4* __restrict__ buf, size_t n_vec, int repeats, uint32_t* sink) {
+  uint32_t acc = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (int r = 0; r < repeats; r++) {
+    // rotate the starting offset per repeat so that a CTA does not re-read the lines its own L1 just cached
+    const size_t rot = ((size_t)r * 977u * blockDim.x) % n_vec;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+      size_t j = i + rot; if (j >= n_vec) j -= n_vec;
+      const uint4 v = __ldcg(buf + j);            // cache-global: L2 only, bypasses L1
+      acc ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+  }
+  if (acc == 0x9e3779b9u) *sink = acc;             // keeps the loads alive
+}
+
 }  // namespace dsrt
 
 // ================================================================================================ host side
@@ -493,6 +511,7 @@ struct DevState {
 struct dsrt_ctx {
   std::vector<DevState> devs;
   std::string err;
+  std::mutex err_mutex;                   // dsrt_render drives its devices from one host thread each
   // host copies of the inputs
   bool have_scene = false, have_bvh = false, have_cam = false, have_accel = false;
   int n_prims = 0;
@@ -517,7 +536,10 @@ struct dsrt_ctx {
 
 namespace {
 
-int fail(dsrt_ctx* c, int code, const std::string& msg) { if (c) c->err = msg; return code; }
+int fail(dsrt_ctx* c, int code, const std::string& msg) {
+  if (c) { std::lock_guard<std::mutex> g(c->err_mutex); c->err = msg; }
+  return code;
+}
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, DSRT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
 
 template <typename T> int dev_alloc(dsrt_ctx* ctx, T** p, size_t n) {
@@ -1039,14 +1061,23 @@ int dsrt_render(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp
   const size_t npix = (size_t)ctx->cam.width * ctx->cam.height;
   const int G = (int)ctx->devs.size();
   // GPU r renders samples k with k mod G == r of the requested list (load is balanced whatever the image content)
-  for (int r = 0; r < G; r++) {
+  // one host thread per device: a frame is a few thousand launches, and enqueueing them device after device from one
+  // thread would start the last GPU tens of milliseconds late
+  auto enqueue = [&](int r) -> int {
     DevState& D = ctx->devs[r];
     CK(cudaSetDevice(D.device));
     if (npix > D.accum_pixels) { int rc = dev_alloc(ctx, &D.d_accum_own, npix * 3); if (rc) return rc; D.accum_pixels = npix; }
     CK(cudaMemsetAsync(D.d_accum_own, 0, npix * 3 * sizeof(float), D.stream));
     const int cnt = spp_count > r ? (spp_count - r + G - 1) / G : 0;
-    int rc = render_impl(ctx, D, spp_begin + r * spp_stride, cnt, spp_stride * G, D.d_accum_own, D.stream);
-    if (rc) return rc;
+    return render_impl(ctx, D, spp_begin + r * spp_stride, cnt, spp_stride * G, D.d_accum_own, D.stream);
+  };
+  if (G == 1) { int rc = enqueue(0); if (rc) return rc; }
+  else {
+    std::vector<int> rcs((size_t)G, DSRT_OK);
+    std::vector<std::thread> workers;
+    for (int r = 0; r < G; r++) workers.emplace_back([&, r] { rcs[r] = enqueue(r); });
+    for (std::thread& t : workers) t.join();
+    for (int r = 0; r < G; r++) if (rcs[r]) return rcs[r];
   }
   DevState& D0 = ctx->devs[0];
   CK(cudaSetDevice(D0.device));
@@ -1172,6 +1203,29 @@ int dsrt_trace_closest(dsrt_ctx* ctx, int64_t n, const float* o, const float* d,
 int dsrt_trace_any(dsrt_ctx* ctx, int64_t n, const float* o, const float* d, const float* tmax, int32_t* hit) {
   if (!ctx || !hit) return DSRT_ERR_INVALID;
   return trace_batch(ctx, true, n, o, d, tmax, hit, nullptr);
+}
+
+int dsrt_measure_read_bandwidth(dsrt_ctx* ctx, int64_t bytes, int32_t repeats, double* gb_per_s) {
+  if (!ctx || !gb_per_s || bytes < 16 || repeats < 1) return DSRT_ERR_INVALID;
+  DevState& D = ctx->devs[0];
+  CK(cudaSetDevice(D.device));
+  const size_t n_vec = (size_t)bytes / 16;
+  uint4* d_buf = nullptr; uint32_t* d_sink = nullptr;
+  CK(cudaMalloc((void**)&d_buf, n_vec * 16));
+  CK(cudaMalloc((void**)&d_sink, 16));
+  CK(cudaMemsetAsync(d_buf, 1, n_vec * 16, D.stream));
+  const int grid = D.sm_count * 8;                 // 8 CTAs of 256 threads per SM: the full 2048 resident threads
+  k_read_sweep<<<grid, 256, 0, D.stream>>>(d_buf, n_vec, 1, d_sink);          // warm: pulls the buffer into L2
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, D.stream));
+  k_read_sweep<<<grid, 256, 0, D.stream>>>(d_buf, n_vec, repeats, d_sink);
+  CK(cudaEventRecord(e1, D.stream));
+  CK(cudaGetLastError());
+  CK(cudaEventSynchronize(e1));
+  float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_buf); cudaFree(d_sink);
+  *gb_per_s = ms > 0 ? (double)n_vec * 16.0 * repeats / ((double)ms * 1e-3) / 1e9 : 0.0;
+  return DSRT_OK;
 }
 
 int dsrt_tonemap(dsrt_ctx* ctx, const float* rgb, int64_t n_pixels, uint32_t* rgba8) {

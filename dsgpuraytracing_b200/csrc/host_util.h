@@ -1,8 +1,11 @@
 // host_util.h -- small host-side helpers shared by the builder, the wide-BVH flattener and the API.
 #pragma once
+#include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <limits>
+#include <thread>
 #include <vector>
 
 #include "../../include/dsrt.h"
@@ -14,11 +17,12 @@ struct Box3 {
   void reset() {
     for (int k = 0; k < 3; k++) { lo[k] = std::numeric_limits<double>::infinity(); hi[k] = -lo[k]; }
   }
+  // std::min / std::max as in BBox::expand (src/bbox.h:69-91); they inline to minsd / maxsd, std::fmin is a libm call
   void grow(const Box3& o) {
-    for (int k = 0; k < 3; k++) { lo[k] = std::fmin(lo[k], o.lo[k]); hi[k] = std::fmax(hi[k], o.hi[k]); }
+    for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], o.lo[k]); hi[k] = std::max(hi[k], o.hi[k]); }
   }
   void grow(const double* p) {
-    for (int k = 0; k < 3; k++) { lo[k] = std::fmin(lo[k], p[k]); hi[k] = std::fmax(hi[k], p[k]); }
+    for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); }
   }
   // ex*ey + ex*ez + ey*ez exactly as the cost expression is written at bvh.cpp:73-74 (an empty box gives
   // +inf, and inf * 0 primitives = NaN, which never compares less than the running minimum)
@@ -28,6 +32,24 @@ struct Box3 {
   }
   double centre(int k) const { return 0.5 * (lo[k] + hi[k]); }
 };
+
+inline int host_threads() { return (int)std::max(1u, std::thread::hardware_concurrency()); }
+
+// f(begin, end) over [0, n) in chunks of `grain`, handed out dynamically to up to host_threads() workers.  The chunk
+// boundaries do not depend on the thread count, so anything a chunk computes on its own is schedule independent.
+template <class F> void parallel_for(size_t n, size_t grain, F f) {
+  if (n == 0) return;
+  grain = std::max<size_t>(grain, 1);
+  const size_t chunks = (n + grain - 1) / grain;
+  const int workers = (int)std::min<size_t>((size_t)host_threads(), chunks);
+  if (workers <= 1) { f((size_t)0, n); return; }
+  std::atomic<size_t> next{0};
+  auto body = [&] { for (size_t c; (c = next.fetch_add(1)) < chunks;) f(c * grain, std::min(n, (c + 1) * grain)); };
+  std::vector<std::thread> th;
+  for (int i = 1; i < workers; i++) th.emplace_back(body);
+  body();
+  for (std::thread& t : th) t.join();
+}
 
 // Triangle::get_bbox (triangle.cpp:11-23) / Sphere::get_bbox (sphere.h:30-32)
 void primitive_boxes(const dsrt_scene* sc, std::vector<Box3>& out);

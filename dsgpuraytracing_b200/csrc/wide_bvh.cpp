@@ -16,10 +16,13 @@
 // Wide nodes are laid out breadth-first, so the top of the tree is contiguous in memory and the internal
 // children of a node are adjacent (one child_base per node).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
-#include <queue>
+#include <deque>
+#include <future>
 
 #include "wide_bvh.h"
 
@@ -36,113 +39,123 @@ float round_down(double v) {
 
 }  // namespace
 
-int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err) {
-  out.nodes.clear(); out.slot_prim.clear(); out.max_depth = 0;
-  if (b2.n_nodes <= 0 || n_prims <= 0) {
-    // empty scene: a single node with no children
-    WideNode w; std::memset(&w, 0, sizeof(w)); w.ex = w.ey = w.ez = 1;
-    out.nodes.push_back(w); out.max_depth = 1;
-    return DSRT_OK;
-  }
-  // 1. working copy, unary nodes spliced out, big leaves split
-  std::vector<BNode> T((size_t)b2.n_nodes);
-  for (int i = 0; i < b2.n_nodes; i++) {
-    BNode& n = T[i];
-    for (int k = 0; k < 3; k++) { n.box.lo[k] = b2.node_bbox[6 * i + k]; n.box.hi[k] = b2.node_bbox[6 * i + 3 + k]; }
-    n.start = b2.node_start[i]; n.range = b2.node_range[i]; n.l = b2.node_left[i]; n.r = b2.node_right[i];
-    if (n.start < 0 || n.range < 0 || n.start + n.range > n_prims || n.l >= b2.n_nodes || n.r >= b2.n_nodes) {
-      err = "dsrt_set_bvh: node " + std::to_string(i) + " is out of range"; return DSRT_ERR_INVALID;
-    }
-  }
-  auto resolve = [&](int id) {            // follow single-child chains (bvh.cpp:238-243 does the same at run time)
+// ---- the collapse, as a context object so that the dynamic programme and the emission can run as parallel tasks ----
+namespace {
+
+struct Collapse {
+  const dsrt_bvh2& b2;
+  const std::vector<Box3>& pbox;
+  std::vector<BNode> T;
+  struct DP { double c[8]; uint8_t split[8]; uint8_t kind1; };      // c[i], i = 1..7 roots; split[i] = roots given to the left child
+  std::vector<DP> dp;                                                // kind1: 0 leaf, 1 internal wide node
+  std::vector<double> c_int; std::vector<uint8_t> split8;
+  static constexpr double c_node = 1.0, c_prim = 1.0;   // measured on B200: flat optimum between 0.6 and 2.5 (primitive tests run at low lane occupancy)
+
+  Collapse(const dsrt_bvh2& b, const std::vector<Box3>& pb) : b2(b), pbox(pb) {}
+
+  int resolve(int id) const {             // follow single-child chains (bvh.cpp:238-243 does the same at run time)
     while (id >= 0) {
       const BNode& n = T[id];
       if (n.l >= 0 && n.r < 0) id = n.l; else if (n.r >= 0 && n.l < 0) id = n.r; else break;
     }
     return id;
-  };
-  {
-    std::vector<int> work;
-    for (int i = 0; i < b2.n_nodes; i++) if (T[i].l < 0 && T[i].r < 0 && T[i].range > 1) work.push_back(i);
+  }
+
+  // 1b. median-split a leaf of r > 1 primitives down to single primitives; its 2(r-1) new nodes go to T[base...]
+  void refine_leaf(int id, int base) {
+    struct It { int id; };
+    int next = base;
+    std::vector<int> work; work.push_back(id);
     while (!work.empty()) {
-      int id = work.back(); work.pop_back();
-      int s = T[id].start, r = T[id].range, h = r / 2;
+      const int cur = work.back(); work.pop_back();
+      const int s = T[cur].start, r = T[cur].range, h = r / 2;
       BNode a, b; a.box.reset(); b.box.reset();
       for (int q = 0; q < r; q++) (q < h ? a.box : b.box).grow(pbox[b2.prim_order[s + q]]);
       a.start = s; a.range = h; a.l = a.r = -1; b.start = s + h; b.range = r - h; b.l = b.r = -1;
-      int ai = (int)T.size(); T.push_back(a); int bi = (int)T.size(); T.push_back(b);
-      T[id].l = ai; T[id].r = bi;
+      const int ai = next++, bi = next++;
+      T[ai] = a; T[bi] = b; T[cur].l = ai; T[cur].r = bi;
       if (a.range > 1) work.push_back(ai);
       if (b.range > 1) work.push_back(bi);
     }
   }
-  const int root = resolve(0);
 
-  // 2. dynamic programme over the binary tree (post-order)
-  const int NT = (int)T.size();
-  const double c_node = 1.0, c_prim = 1.0;   // measured on B200: flat optimum between 0.6 and 2.5 (primitive tests run at low lane occupancy)
-  struct DP { double c[8]; uint8_t split[8]; uint8_t kind1; };      // c[i], i = 1..7 roots; split[i] = roots given to the left child
-  std::vector<DP> dp((size_t)NT);                                    // kind1: 0 leaf, 1 internal wide node
-  std::vector<double> c_int((size_t)NT, 0.0); std::vector<uint8_t> split8((size_t)NT, 0);
-  {
-    std::vector<int> order; order.reserve(NT);
-    std::vector<int> st; st.push_back(root);
-    while (!st.empty()) { int n = st.back(); st.pop_back(); order.push_back(n); if (T[n].l >= 0) { st.push_back(resolve(T[n].l)); st.push_back(resolve(T[n].r)); } }
-    for (int q = (int)order.size() - 1; q >= 0; q--) {
-      const int n = order[q]; DP& d = dp[n];
-      double area = T[n].box.half_area(); if (!(area >= 0)) area = 0;
-      const bool is_leaf = T[n].l < 0;
-      const double c_leaf = T[n].range <= 3 ? area * T[n].range * c_prim : std::numeric_limits<double>::infinity();
-      if (is_leaf) {
-        for (int i = 1; i <= 7; i++) { d.c[i] = c_leaf; d.split[i] = 0; }
-        d.kind1 = 0; c_int[n] = std::numeric_limits<double>::infinity();
-        continue;
-      }
-      const int L = resolve(T[n].l), R = resolve(T[n].r);
-      auto distribute = [&](int j, uint8_t* arg) {                    // best split of j roots between the two children
-        double best = std::numeric_limits<double>::infinity(); int bk = 1;
-        for (int k = 1; k < j; k++) { double c = dp[L].c[std::min(k, 7)] + dp[R].c[std::min(j - k, 7)]; if (c < best) { best = c; bk = k; } }
-        *arg = (uint8_t)bk; return best;
-      };
-      c_int[n] = distribute(8, &split8[n]) + area * c_node;
-      d.c[1] = std::min(c_leaf, c_int[n]); d.kind1 = c_leaf <= c_int[n] ? 0 : 1; d.split[1] = 0;
-      for (int i = 2; i <= 7; i++) {
-        uint8_t arg = 1; const double cd = distribute(i, &arg);
-        if (cd < d.c[i - 1]) { d.c[i] = cd; d.split[i] = arg; } else { d.c[i] = d.c[i - 1]; d.split[i] = 0; }   // 0: use fewer roots
-      }
+  // 2. one node of the dynamic programme (children already done)
+  void dp_node(int n) {
+    DP& d = dp[n];
+    double area = T[n].box.half_area(); if (!(area >= 0)) area = 0;
+    const bool is_leaf = T[n].l < 0;
+    const double c_leaf = T[n].range <= 3 ? area * T[n].range * c_prim : std::numeric_limits<double>::infinity();
+    if (is_leaf) {
+      for (int i = 1; i <= 7; i++) { d.c[i] = c_leaf; d.split[i] = 0; }
+      d.kind1 = 0; c_int[n] = std::numeric_limits<double>::infinity();
+      return;
+    }
+    const int L = resolve(T[n].l), R = resolve(T[n].r);
+    auto distribute = [&](int j, uint8_t* arg) {                    // best split of j roots between the two children
+      double best = std::numeric_limits<double>::infinity(); int bk = 1;
+      for (int k = 1; k < j; k++) { double c = dp[L].c[std::min(k, 7)] + dp[R].c[std::min(j - k, 7)]; if (c < best) { best = c; bk = k; } }
+      *arg = (uint8_t)bk; return best;
+    };
+    c_int[n] = distribute(8, &split8[n]) + area * c_node;
+    d.c[1] = std::min(c_leaf, c_int[n]); d.kind1 = c_leaf <= c_int[n] ? 0 : 1; d.split[1] = 0;
+    for (int i = 2; i <= 7; i++) {
+      uint8_t arg = 1; const double cd = distribute(i, &arg);
+      if (cd < d.c[i - 1]) { d.c[i] = cd; d.split[i] = arg; } else { d.c[i] = d.c[i - 1]; d.split[i] = 0; }   // 0: use fewer roots
     }
   }
+  void dp_sequential(int root) {          // post-order with an explicit stack
+    std::vector<int> order, st; st.push_back(root);
+    while (!st.empty()) { int n = st.back(); st.pop_back(); order.push_back(n); if (T[n].l >= 0) { st.push_back(resolve(T[n].l)); st.push_back(resolve(T[n].r)); } }
+    for (size_t q = order.size(); q-- > 0;) dp_node(order[q]);
+  }
+  // subtrees with at least `big` primitives fork into tasks; a chain of nodes with one big child is walked iteratively
+  void dp_parallel(int n, int big) {
+    std::vector<int> chain;
+    while (true) {
+      if (T[n].l < 0 || T[n].range < big) { dp_sequential(n); break; }
+      const int L = resolve(T[n].l), R = resolve(T[n].r);
+      const bool bl = T[L].range >= big, br = T[R].range >= big;
+      if (bl && br) {
+        std::future<void> f = std::async(std::launch::async, [this, L, big] { dp_parallel(L, big); });
+        dp_parallel(R, big);
+        f.get();
+        dp_node(n);
+        break;
+      }
+      if (!bl && !br) { dp_sequential(n); break; }
+      dp_sequential(bl ? R : L);
+      chain.push_back(n);
+      n = bl ? L : R;
+    }
+    for (size_t q = chain.size(); q-- > 0;) dp_node(chain[q]);
+  }
+
   // children of the wide node rooted at binary node n = leaves of the DP's distribution of 8 slots
   struct Kid { int bnode; bool leaf; };
-  auto collect = [&](int n, std::vector<Kid>& kids) {
+  void collect(int n, std::vector<Kid>& kids) const {
     kids.clear();
     struct Item { int n, i; };
-    std::vector<Item> st;
+    Item st[64]; int sp = 0;
     if (T[n].l < 0) { kids.push_back({n, true}); return; }           // the root itself is a (<= 3 primitive) leaf
     const int L = resolve(T[n].l), R = resolve(T[n].r);
-    st.push_back({R, 8 - split8[n]}); st.push_back({L, split8[n]});
-    while (!st.empty()) {
-      Item it = st.back(); st.pop_back();
+    st[sp++] = {R, 8 - split8[n]}; st[sp++] = {L, split8[n]};
+    while (sp > 0) {
+      Item it = st[--sp];
       int i = std::min(it.i, 7);
       while (i > 1 && dp[it.n].split[i] == 0) i--;                    // the DP preferred fewer roots
       if (i == 1) { kids.push_back({it.n, dp[it.n].kind1 == 0}); continue; }
       const int l2 = resolve(T[it.n].l), r2 = resolve(T[it.n].r);
       const int k = dp[it.n].split[i];
-      st.push_back({r2, i - k}); st.push_back({l2, k});
+      st[sp++] = {r2, i - k}; st[sp++] = {l2, k};
     }
-  };
+  }
 
-  // 3..4. breadth-first emission
-  struct Job { int bnode; uint32_t widx; int depth; };
-  std::queue<Job> jobs;
-  out.nodes.emplace_back();
-  jobs.push({root, 0u, 1});
-  std::vector<Kid> kidv;
-  while (!jobs.empty()) {
-    Job job = jobs.front(); jobs.pop();
-    out.max_depth = std::max(out.max_depth, job.depth);
-    collect(job.bnode, kidv);
-    if (kidv.size() > 8) { err = "wide BVH: collapse produced more than 8 children"; return DSRT_ERR_LIMIT; }
+  // 3..4. one wide node: octant-ordered slots + quantisation.  Its internal children get the node indices
+  // child_base, child_base+1, ... (in slot order; their binary nodes are returned in kids_out), the primitives of its
+  // leaf children are appended to slot_prim.  Returns the number of internal children or a negative error code.
+  int emit_node(int bnode, uint32_t child_base, std::vector<int32_t>& slot_prim, WideNode& w, int* kids_out, std::vector<Kid>& kidv, std::string& err) const {
+    collect(bnode, kidv);
+    if (kidv.size() > 8) { err = "wide BVH: collapse produced more than 8 children"; return -1; }
     int kids[8]; bool kid_leaf[8]; int nk = 0;
     for (const Kid& k : kidv) { kids[nk] = k.bnode; kid_leaf[nk] = k.leaf; nk++; }
     // node box = union of children (equals the binary node's box; recomputed so virtual splits are covered)
@@ -167,12 +180,11 @@ int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_pri
     int kid_at[8]; bool leaf_at[8]; for (int s = 0; s < 8; s++) { kid_at[s] = -1; leaf_at[s] = false; }
     for (int i = 0; i < nk; i++) { kid_at[slot_of[i]] = kids[i]; leaf_at[slot_of[i]] = kid_leaf[i]; }
 
-    // 4. quantisation frame
-    WideNode w; std::memset(&w, 0, sizeof(w));
-    // Quantisation frame.  The device evaluates plane = (1 + q 2^-15) * (2^15 s) + (b - 2^15 s) in float, which is
+    // 4. quantisation frame.  The device evaluates plane = (1 + q 2^-15) * (2^15 s) + (b - 2^15 s) in float, which is
     // off by up to ~2^-9 of a quantum, and picks near/far planes separately; every child plane therefore gets a
     // guaranteed margin of 1/64 quantum (and a flat box at least one full quantum of thickness): the grid keeps one
     // spare quantum below the node's box, and its pitch never drops below 2^-18 of the coordinate magnitude.
+    std::memset(&w, 0, sizeof(w));
     float org[3]; double scale[3]; uint8_t ebits[3];
     for (int k = 0; k < 3; k++) {
       const double ext = nb.hi[k] - nb.lo[k];
@@ -189,12 +201,9 @@ int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_pri
       ebits[k] = (uint8_t)(e + 127);
     }
     w.ox = org[0]; w.oy = org[1]; w.oz = org[2]; w.ex = ebits[0]; w.ey = ebits[1]; w.ez = ebits[2];
-    w.prim_base = (uint32_t)out.slot_prim.size();
-    int n_internal = 0;
-    for (int s = 0; s < 8; s++) if (kid_at[s] >= 0 && !leaf_at[s]) n_internal++;
-    w.child_base = (uint32_t)out.nodes.size();
-    if (n_internal) out.nodes.resize(out.nodes.size() + n_internal);
-    uint32_t next_child = w.child_base; int prim_off = 0;
+    w.prim_base = (uint32_t)slot_prim.size();
+    w.child_base = child_base;
+    int n_internal = 0, prim_off = 0;
     for (int s = 0; s < 8; s++) {
       int c = kid_at[s];
       if (c < 0) continue;
@@ -208,19 +217,131 @@ int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_pri
       }
       w.qlox[s] = q[0]; w.qloy[s] = q[1]; w.qloz[s] = q[2]; w.qhix[s] = q[3]; w.qhiy[s] = q[4]; w.qhiz[s] = q[5];
       if (leaf_at[s]) {
-        if (cn.range < 1 || cn.range > 3 || prim_off + cn.range > 24) { err = "wide BVH: leaf packing overflow"; return DSRT_ERR_LIMIT; }
+        if (cn.range < 1 || cn.range > 3 || prim_off + cn.range > 24) { err = "wide BVH: leaf packing overflow"; return -1; }
         uint8_t unary = cn.range == 1 ? 1 : (cn.range == 2 ? 3 : 7);
         w.meta[s] = (uint8_t)((unary << 5) | prim_off);
-        for (int q2 = 0; q2 < cn.range; q2++) out.slot_prim.push_back(b2.prim_order[cn.start + q2]);
+        for (int q2 = 0; q2 < cn.range; q2++) slot_prim.push_back(b2.prim_order[cn.start + q2]);
         prim_off += cn.range;
       } else {
         w.meta[s] = (uint8_t)((1 << 5) | (24 + s));
         w.imask |= (uint8_t)(1 << s);
-        jobs.push({c, next_child++, job.depth + 1});
+        kids_out[n_internal++] = c;
       }
     }
-    out.nodes[job.widx] = w;
+    return n_internal;
   }
+};
+
+}  // namespace
+
+int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err) {
+  out.nodes.clear(); out.slot_prim.clear(); out.max_depth = 0;
+  if (b2.n_nodes <= 0 || n_prims <= 0) {
+    // empty scene: a single node with no children
+    WideNode w; std::memset(&w, 0, sizeof(w)); w.ex = w.ey = w.ez = 1;
+    out.nodes.push_back(w); out.max_depth = 1;
+    return DSRT_OK;
+  }
+  const bool timing = std::getenv("DSRT_BUILD_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
+  Collapse C(b2, pbox);
+  std::vector<BNode>& T = C.T;
+  // 1. working copy; leaves of more than one primitive are refined (each leaf's new nodes live in its own block of T)
+  T.resize((size_t)b2.n_nodes);
+  std::atomic<int> bad{-1};
+  parallel_for((size_t)b2.n_nodes, (size_t)1 << 16, [&](size_t i0, size_t i1) {
+    for (size_t i = i0; i < i1; i++) {
+      BNode& n = T[i];
+      for (int k = 0; k < 3; k++) { n.box.lo[k] = b2.node_bbox[6 * i + k]; n.box.hi[k] = b2.node_bbox[6 * i + 3 + k]; }
+      n.start = b2.node_start[i]; n.range = b2.node_range[i]; n.l = b2.node_left[i]; n.r = b2.node_right[i];
+      if (n.start < 0 || n.range < 0 || n.start + n.range > n_prims || n.l >= b2.n_nodes || n.r >= b2.n_nodes) bad.store((int)i);
+    }
+  });
+  if (bad.load() >= 0) { err = "dsrt_set_bvh: node " + std::to_string(bad.load()) + " is out of range"; return DSRT_ERR_INVALID; }
+  {
+    std::vector<int> leaves; std::vector<size_t> base;
+    size_t total = T.size();
+    for (int i = 0; i < b2.n_nodes; i++) if (T[i].l < 0 && T[i].r < 0 && T[i].range > 1) { leaves.push_back(i); base.push_back(total); total += 2 * (size_t)(T[i].range - 1); }
+    if (total > (size_t)std::numeric_limits<int>::max()) { err = "wide BVH: too many binary nodes"; return DSRT_ERR_LIMIT; }
+    T.resize(total);
+    parallel_for(leaves.size(), 4096, [&](size_t i0, size_t i1) { for (size_t i = i0; i < i1; i++) C.refine_leaf(leaves[i], (int)base[i]); });
+  }
+  const int root = C.resolve(0);
+
+  const double t1 = now();
+  // 2. dynamic programme over the binary tree (post-order; big subtrees as parallel tasks)
+  const size_t NT = T.size();
+  C.dp.resize(NT); C.c_int.assign(NT, 0.0); C.split8.assign(NT, 0);
+  C.dp_parallel(root, std::max(1 << 14, n_prims / (4 * host_threads())));
+
+  const double t2 = now();
+  // 3..4. emission.  The top of the tree is emitted breadth-first by one thread until kTopJobs subtrees are pending;
+  // every pending subtree is then emitted (breadth-first within itself) as an independent task into its own block and
+  // the blocks are concatenated in job order -- the layout depends on kTopJobs only, never on the thread count.
+  // Internal children of a node are adjacent (one child_base per node) in both parts.
+  constexpr size_t kTopJobs = 1024;
+  struct Job { int bnode; uint32_t widx; int depth; };
+  std::deque<Job> jobs;
+  out.nodes.emplace_back();
+  jobs.push_back({root, 0u, 1});
+  {
+    std::vector<Collapse::Kid> kidv; int kids[8];
+    while (!jobs.empty() && jobs.size() < kTopJobs) {
+      Job job = jobs.front(); jobs.pop_front();
+      out.max_depth = std::max(out.max_depth, job.depth);
+      WideNode w;
+      const int ni = C.emit_node(job.bnode, (uint32_t)out.nodes.size(), out.slot_prim, w, kids, kidv, err);
+      if (ni < 0) return DSRT_ERR_LIMIT;
+      for (int i = 0; i < ni; i++) jobs.push_back({kids[i], (uint32_t)(out.nodes.size() + i), job.depth + 1});
+      out.nodes.resize(out.nodes.size() + ni);
+      out.nodes[job.widx] = w;
+    }
+  }
+  if (!jobs.empty()) {
+    struct Block { WideNode root; std::vector<WideNode> nodes; std::vector<int32_t> prims; int depth = 0; int rc = 0; std::string err; };
+    std::vector<Job> roots(jobs.begin(), jobs.end());
+    std::vector<Block> blocks(roots.size());
+    parallel_for(roots.size(), 1, [&](size_t j0, size_t j1) {
+      std::vector<Collapse::Kid> kidv; int kids[8];
+      for (size_t j = j0; j < j1; j++) {
+        Block& B = blocks[j];
+        // local indices: the subtree's descendants are B.nodes[0..]; index -1 = the subtree root (lives in the top part)
+        struct LJob { int bnode; int lidx; int depth; };
+        std::deque<LJob> q; q.push_back({roots[j].bnode, -1, roots[j].depth});
+        while (!q.empty()) {
+          LJob job = q.front(); q.pop_front();
+          B.depth = std::max(B.depth, job.depth);
+          WideNode w;
+          const int ni = C.emit_node(job.bnode, (uint32_t)B.nodes.size(), B.prims, w, kids, kidv, B.err);
+          if (ni < 0) { B.rc = DSRT_ERR_LIMIT; break; }
+          for (int i = 0; i < ni; i++) q.push_back({kids[i], (int)(B.nodes.size() + i), job.depth + 1});
+          B.nodes.resize(B.nodes.size() + ni);
+          if (job.lidx < 0) B.root = w; else B.nodes[job.lidx] = w;
+        }
+      }
+    });
+    size_t node_off = out.nodes.size(), prim_off = out.slot_prim.size();
+    std::vector<size_t> noff(blocks.size()), poff(blocks.size());
+    for (size_t j = 0; j < blocks.size(); j++) {
+      if (blocks[j].rc) { err = blocks[j].err; return blocks[j].rc; }
+      noff[j] = node_off; poff[j] = prim_off; node_off += blocks[j].nodes.size(); prim_off += blocks[j].prims.size();
+      out.max_depth = std::max(out.max_depth, blocks[j].depth);
+    }
+    if (node_off > 0xffffffffull || prim_off > 0x7fffffffull) { err = "wide BVH: too many nodes"; return DSRT_ERR_LIMIT; }
+    out.nodes.resize(node_off); out.slot_prim.resize(prim_off);
+    parallel_for(blocks.size(), 1, [&](size_t j0, size_t j1) {
+      for (size_t j = j0; j < j1; j++) {
+        Block& B = blocks[j];
+        auto fix = [&](WideNode w) { w.child_base += (uint32_t)noff[j]; w.prim_base += (uint32_t)poff[j]; return w; };
+        out.nodes[roots[j].widx] = fix(B.root);
+        for (size_t i = 0; i < B.nodes.size(); i++) out.nodes[noff[j] + i] = fix(B.nodes[i]);
+        std::copy(B.prims.begin(), B.prims.end(), out.slot_prim.begin() + (std::ptrdiff_t)poff[j]);
+        std::vector<WideNode>().swap(B.nodes); std::vector<int32_t>().swap(B.prims);
+      }
+    });
+  }
+  if (timing) std::fprintf(stderr, "build_wide_bvh: %d prims, copy+refine %.2f s, collapse DP %.2f s, emit %.2f s\n", n_prims, t1 - t0, t2 - t1, now() - t2);
   if ((int)out.slot_prim.size() != n_prims) { err = "wide BVH: primitive count mismatch (" + std::to_string(out.slot_prim.size()) + " vs " + std::to_string(n_prims) + ")"; return DSRT_ERR_INVALID; }
   return DSRT_OK;
 }
@@ -229,7 +350,8 @@ void flatten_records(const dsrt_scene& sc, const WideBVH& wide, std::vector<Prim
                      std::vector<PrimRecord64>& r64) {
   const size_t n = wide.slot_prim.size();
   recs.assign(n ? n : 1, PrimRecord{}); shd.assign(n ? n : 1, ShadeRecord{}); r64.assign(n ? n : 1, PrimRecord64{});
-  for (size_t sl = 0; sl < n; sl++) {
+  parallel_for(n, (size_t)1 << 16, [&](size_t s0, size_t s1) {
+  for (size_t sl = s0; sl < s1; sl++) {
     const int p = wide.slot_prim[sl];
     PrimRecord& r = recs[sl]; ShadeRecord& h = shd[sl]; PrimRecord64& d = r64[sl];
     std::memset(&r, 0, sizeof(r)); std::memset(&h, 0, sizeof(h)); std::memset(&d, 0, sizeof(d));
@@ -249,6 +371,7 @@ void flatten_records(const dsrt_scene& sc, const WideBVH& wide, std::vector<Prim
       d.pad[2] = 0.0;
     }
   }
+  });
 }
 
 int flatten_lights(int n_lights, const int32_t* light_type, const double* light_param, int ns_area_light, bool with_env,

@@ -160,6 +160,12 @@ int dsrt_trace_any(dsrt_ctx* ctx, int64_t n, const float* o, const float* d, con
 /* HDRImageBuffer::toColor + ImageBuffer::update_pixel on the host result (image.h:49-58,174-189). */
 int dsrt_tonemap(dsrt_ctx* ctx, const float* rgb, int64_t n_pixels, uint32_t* rgba8);
 
+/* Roofline denominator for the L2-resident regime: every SM sweeps the same read-only buffer of `bytes`
+ * (rounded down to 16 B) `repeats` times with 128-bit loads; *gb_per_s = bytes * repeats / kernel time (CUDA events,
+ * first sweep excluded).  A 32 MiB buffer stays in the B200's L2, so the figure is the L2 -> SM read bandwidth; a buffer
+ * several times the L2 size gives the HBM read bandwidth. */
+int dsrt_measure_read_bandwidth(dsrt_ctx* ctx, int64_t bytes, int32_t repeats, double* gb_per_s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,10 +11,14 @@ from dsgpuraytracing_b200 import scenes as S
 V, F = S.torus_knot(); V = V.astype(np.float32).astype(np.float64)
 sc = S.cb_mesh_scene(V, F); cam = S.cam_dragon(1920, 1080)
 core = D.Core(0)
-spp = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+args = [x for x in sys.argv[1:] if "=" not in x]
+spp = int(args[0]) if args else 2
 core.set_params(spp, 4, 8, 0)
 core.load(sc, camera=cam)
 core.set_option("stage_timing", 1)
+for kv in sys.argv[1:]:          # e.g. refill_busy_lanes=0 postpone_min_lanes=0 coop_min_pairs=1000000 (no compaction)
+    if "=" in kv:
+        k, v = kv.split("="); core.set_option(k, int(v))
 for i in range(2):
     rgb, st = core.render()
 print("segments %d  gpu_s %.4f  Mrays/s %.1f  extend %.4f connect %.4f shade %.4f" % (

@@ -21,17 +21,23 @@ def golden(name, W, H):
     return g, cam
 
 
+N_GPUS = 1
+
+
 def run(tag, sc, cam, spp, nl, depth, reps=2):
     t0 = time.time(); bvh = D.build_bvh2(sc); t_sah = time.time() - t0
-    core = D.Core(0)
+    # N_GPUS > 1: one context over N devices (dsrt_create_multi): sample-split render, partial framebuffers combined by
+    # device 0 reading its peers over NVLink inside the resolve kernel
+    core = D.Core(0) if N_GPUS == 1 else D.Core(devices=list(range(N_GPUS)))
     core.set_params(spp, nl, depth, 0)
     t0 = time.time(); core.load(sc, camera=cam, bvh=bvh); t_accel = time.time() - t0
     core.set_option("stage_timing", 1)
-    best = None
+    best = None; wall = None
     for _ in range(reps):
-        rgb, st = core.render()
+        w0 = time.perf_counter(); rgb, st = core.render(); w1 = time.perf_counter()
         if best is None or st.gpu_seconds < best.gpu_seconds:
             best = st
+        wall = (w1 - w0) if wall is None else min(wall, w1 - w0)
     core.set_option("count_traversal", 1)
     core.set_params(max(1, min(spp, 4)), nl, depth, 0)
     _, sc2 = core.render()
@@ -39,10 +45,10 @@ def run(tag, sc, cam, spp, nl, depth, reps=2):
     seg = best.segments
     nn = sc2.nodes_visited / sc2.segments; nt = sc2.prims_tested / sc2.segments
     bps = nn * 80 + nt * 48 + 48
-    out = {"case": tag, "prims": int(len(sc["prim_type"])), "wide_nodes": info["wide_nodes"], "wide_depth": info["max_depth"],
+    out = {"case": tag, "n_gpus": N_GPUS, "prims": int(len(sc["prim_type"])), "wide_nodes": info["wide_nodes"], "wide_depth": info["max_depth"],
            "accel_MB": (info["node_bytes"] + info["prim_bytes"]) / 1e6, "sah_build_s": round(t_sah, 3), "flatten_upload_s": round(t_accel, 3),
            "width": int(cam[12]), "height": int(cam[13]), "spp": spp, "light_samples": nl, "max_depth": depth,
-           "segments": int(seg), "segments_per_sample": seg / best.camera_samples, "s_per_frame": best.gpu_seconds,
+           "segments": int(seg), "segments_per_sample": seg / best.camera_samples, "s_per_frame": best.gpu_seconds, "wall_s_incl_reduce_and_readback": wall,
            "Mrays_s": seg / best.gpu_seconds / 1e6, "extend_s": best.extend_seconds, "connect_s": best.connect_seconds,
            "shade_s": best.shade_seconds, "nodes_per_seg": nn, "prims_per_seg": nt, "bytes_per_seg": bps,
            "algorithmic_GB_s": seg * bps / best.gpu_seconds / 1e9, "mean_rgb": [float(x) for x in rgb.mean(axis=(0, 1))]}
@@ -53,22 +59,34 @@ def run(tag, sc, cam, spp, nl, depth, reps=2):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--soup-max", type=int, default=8, help="largest soup in Mi triangles")
+    ap.add_argument("--soup-min", type=int, default=1, help="smallest soup in Mi triangles")
     ap.add_argument("--quick", action="store_true", help="16 spp instead of the configured 256/512")
+    ap.add_argument("--gpus", type=int, default=1, help="GPUs of this box driven by one context (dsrt_create_multi)")
+    ap.add_argument("--only", default="", help="comma list of case prefixes to run, e.g. C4,C5")
     a = ap.parse_args()
     q = a.quick
-    g, cam = golden("CBspheres_lambertian", 480, 360)
-    run("C1 CBspheres_lambertian 480x360 16spp l4 m5", g, cam, 16, 4, 5)
-    sc, cam = S.cbdragon_standin(1920, 1080)
-    run("C2 CBdragon stand-in (100012-tri mesh) 1080p 256spp l4 m8", sc, cam, 16 if q else 256, 4, 8)
-    sc, cam = S.cblucy_standin(1920, 1080)
-    run("C3 CBlucy stand-in (133796-tri GLASS mesh) 1080p 256spp l4 m8", sc, cam, 16 if q else 256, 4, 8)
-    for nm in ("CBgems", "CBcoil", "CBbunny"):
-        g, cam = golden(nm, 1920, 1080)
-        run(f"C3' {nm} 1080p 256spp l4 m8", g, cam, 16 if q else 256, 4, 8)
-    g, cam = golden("bunny", 1920, 1080)
-    run("C4 bunny (hemisphere light) 1080p 512spp l4 m8, 1 GPU", g, cam, 16 if q else 512, 4, 8)
-    n = 1
-    while n <= a.soup_max:
+    N_GPUS = a.gpus
+    only = [x for x in a.only.split(",") if x]
+    want = lambda c: not only or any(c == x for x in only)
+    gtag = f"{N_GPUS} GPU" + ("s" if N_GPUS > 1 else "")
+    if want("C1"):
+        g, cam = golden("CBspheres_lambertian", 480, 360)
+        run(f"C1 CBspheres_lambertian 480x360 16spp l4 m5, {gtag}", g, cam, 16, 4, 5)
+    if want("C2"):
+        sc, cam = S.cbdragon_standin(1920, 1080)
+        run(f"C2 CBdragon stand-in (100012-tri mesh) 1080p 256spp l4 m8, {gtag}", sc, cam, 16 if q else 256, 4, 8)
+    if want("C3"):
+        sc, cam = S.cblucy_standin(1920, 1080)
+        run(f"C3 CBlucy stand-in (133796-tri GLASS mesh) 1080p 256spp l4 m8, {gtag}", sc, cam, 16 if q else 256, 4, 8)
+        for nm in ("CBgems", "CBcoil", "CBbunny"):
+            g, cam = golden(nm, 1920, 1080)
+            run(f"C3' {nm} 1080p 256spp l4 m8, {gtag}", g, cam, 16 if q else 256, 4, 8)
+    if want("C4"):
+        g, cam = golden("bunny", 1920, 1080)
+        run(f"C4 bunny (hemisphere light) 1080p 512spp l4 m8, {gtag}", g, cam, 16 if q else 512, 4, 8)
+    n = a.soup_min
+    while want("C5") and n <= a.soup_max:
         sc, cam = S.triangle_soup(n << 20)
-        run(f"C5 triangle soup {n}Mi tris 3840x2160 64spp l1 m8, 1 GPU", sc, cam, 8 if q else 64, 1, 8, reps=1)
+        run(f"C5 triangle soup {n}Mi tris 3840x2160 64spp l1 m8, {gtag}", sc, cam, 8 if q else 64, 1, 8, reps=1)
+        del sc
         n *= 2

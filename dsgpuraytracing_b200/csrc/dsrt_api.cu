@@ -814,7 +814,8 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
   double dg = 0; for (int k = 0; k < 3; k++) { double e = ctx->n_prims ? all.hi[k] - all.lo[k] : 0; double m = ctx->n_prims ? std::fmax(std::fabs(all.lo[k]), std::fabs(all.hi[k])) : 0; dg += (e + m) * (e + m); }
   ctx->scene_diag = std::sqrt(dg) + 1.0;
 
-  flatten_records(s, ctx->wide, ctx->recs, ctx->shd, ctx->r64);
+  flatten_records(s, ctx->wide, ctx->recs, ctx->shd);
+  ctx->r64.clear(); ctx->r64.shrink_to_fit();     // fp64 records: built and uploaded by the first dsrt_primary_hits(mode 1)
   ctx->n_light_samples = flatten_lights((int)ctx->light_type.size(), ctx->light_type.data(), ctx->light_param.data(), ctx->ns_area_light, ctx->env_w > 0, ctx->lights);
   ctx->n_lights = (int)ctx->lights.size();
   for (DevState& D : ctx->devs) {      // new sizes: (re)allocate the device copies
@@ -825,7 +826,6 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
     CK(cudaMalloc(&D.d_nodes, std::max<size_t>(ctx->wide.nodes.size() * sizeof(WideNode), 16)));
     CK(cudaMalloc(&D.d_prims, std::max<size_t>(n * sizeof(PrimRecord), 16)));
     CK(cudaMalloc(&D.d_shade, std::max<size_t>(n * sizeof(ShadeRecord), 16)));
-    CK(cudaMalloc(&D.d_prims64, std::max<size_t>(n * sizeof(PrimRecord64), 16)));
     CK(cudaMalloc(&D.d_bsdf, std::max<size_t>(ctx->bsdfs.size() * sizeof(Bsdf), 16)));
     CK(cudaMalloc(&D.d_lights, std::max<size_t>(ctx->lights.size() * sizeof(Light), 16)));
     dev_free(D.d_env_rgb); dev_free(D.d_env_tp); dev_free(D.d_env_t); dev_free(D.d_env_pgt);
@@ -850,13 +850,12 @@ int dsrt_upload_accel(dsrt_ctx* ctx) {
   if (!ctx) return DSRT_ERR_INVALID;
   if (!ctx->have_accel) return fail(ctx, DSRT_ERR_INVALID, "dsrt_upload_accel: call dsrt_build_accel first");
   const size_t n = ctx->wide.slot_prim.size();
-  for (DevState& D : ctx->devs) {      // the scene is replicated on every GPU
+  auto upload = [&](DevState& D) -> int {      // the scene is replicated on every GPU
     CK(cudaSetDevice(D.device));
     CK(cudaMemcpyAsync(D.d_nodes, ctx->wide.nodes.data(), ctx->wide.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, D.stream));
     if (n) {
       CK(cudaMemcpyAsync(D.d_prims, ctx->recs.data(), n * sizeof(PrimRecord), cudaMemcpyHostToDevice, D.stream));
       CK(cudaMemcpyAsync(D.d_shade, ctx->shd.data(), n * sizeof(ShadeRecord), cudaMemcpyHostToDevice, D.stream));
-      CK(cudaMemcpyAsync(D.d_prims64, ctx->r64.data(), n * sizeof(PrimRecord64), cudaMemcpyHostToDevice, D.stream));
     }
     if (!ctx->bsdfs.empty()) CK(cudaMemcpyAsync(D.d_bsdf, ctx->bsdfs.data(), ctx->bsdfs.size() * sizeof(Bsdf), cudaMemcpyHostToDevice, D.stream));
     if (!ctx->lights.empty()) CK(cudaMemcpyAsync(D.d_lights, ctx->lights.data(), ctx->lights.size() * sizeof(Light), cudaMemcpyHostToDevice, D.stream));
@@ -867,15 +866,22 @@ int dsrt_upload_accel(dsrt_ctx* ctx) {
       CK(cudaMemcpyAsync(D.d_env_t, ctx->env_t.data(), (size_t)ctx->env_h * sizeof(float), cudaMemcpyHostToDevice, D.stream));
       CK(cudaMemcpyAsync(D.d_env_pgt, ctx->env_pgt.data(), np * sizeof(float), cudaMemcpyHostToDevice, D.stream));
     }
-  }
-  for (DevState& D : ctx->devs) { CK(cudaSetDevice(D.device)); CK(cudaStreamSynchronize(D.stream)); }
+    CK(cudaStreamSynchronize(D.stream));
+    return DSRT_OK;
+  };
+  if (ctx->devs.size() == 1) return upload(ctx->devs[0]);
+  std::vector<int> rcs(ctx->devs.size(), DSRT_OK);     // pageable-memory copies block the calling thread: one thread per GPU
+  std::vector<std::thread> workers;
+  for (size_t r = 0; r < ctx->devs.size(); r++) workers.emplace_back([&, r] { rcs[r] = upload(ctx->devs[r]); });
+  for (std::thread& t : workers) t.join();
+  for (int rc : rcs) if (rc) return rc;
   return DSRT_OK;
 }
 
 int dsrt_accel_bytes(const dsrt_ctx* ctx, int64_t* h2d_bytes) {
   if (!ctx || !ctx->have_accel || !h2d_bytes) return DSRT_ERR_INVALID;
   const size_t n = ctx->wide.slot_prim.size();
-  *h2d_bytes = (int64_t)(ctx->wide.nodes.size() * sizeof(WideNode) + n * (sizeof(PrimRecord) + sizeof(ShadeRecord) + sizeof(PrimRecord64)) +
+  *h2d_bytes = (int64_t)(ctx->wide.nodes.size() * sizeof(WideNode) + n * (sizeof(PrimRecord) + sizeof(ShadeRecord)) +
                          ctx->bsdfs.size() * sizeof(Bsdf) + ctx->lights.size() * sizeof(Light) +
                          (size_t)ctx->env_w * ctx->env_h * 5 * sizeof(float) + (size_t)ctx->env_h * sizeof(float));
   return DSRT_OK;
@@ -1125,6 +1131,14 @@ int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) 
   std::vector<int32_t> slots(n); std::vector<double> ts(n);
   cudaStream_t st = D.stream;
   if (mode == 1) {
+    if (!D.d_prims64) {     // the parity kernel's fp64 primitive records are not part of the render path: built here, once
+      dsrt_scene s{}; s.n_prims = ctx->n_prims; s.prim_type = ctx->prim_type.data(); s.prim_bsdf = ctx->prim_bsdf.data();
+      s.tri_pos = ctx->tri_pos.data(); s.tri_nrm = ctx->tri_nrm.data(); s.sphere = ctx->sphere.data();
+      flatten_records64(s, ctx->wide, ctx->r64);
+      CK(cudaMalloc(&D.d_prims64, ctx->r64.size() * sizeof(PrimRecord64)));
+      CK(cudaMemcpy(D.d_prims64, ctx->r64.data(), ctx->r64.size() * sizeof(PrimRecord64), cudaMemcpyHostToDevice));
+      ctx->r64.clear(); ctx->r64.shrink_to_fit();
+    }
     std::vector<double> rays((size_t)n * 6);
     for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) host_generate_ray64(ctx->cam, (x + 0.5) / W, (y + 0.5) / H, &rays[6 * ((size_t)y * W + x)]);
     double* d_rays = nullptr; int32_t* d_slot = nullptr; double* d_t = nullptr;

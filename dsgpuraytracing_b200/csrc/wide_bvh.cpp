@@ -346,31 +346,49 @@ int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_pri
   return DSRT_OK;
 }
 
-void flatten_records(const dsrt_scene& sc, const WideBVH& wide, std::vector<PrimRecord>& recs, std::vector<ShadeRecord>& shd,
-                     std::vector<PrimRecord64>& r64) {
+void flatten_records(const dsrt_scene& sc, const WideBVH& wide, std::vector<PrimRecord>& recs, std::vector<ShadeRecord>& shd) {
   const size_t n = wide.slot_prim.size();
-  recs.assign(n ? n : 1, PrimRecord{}); shd.assign(n ? n : 1, ShadeRecord{}); r64.assign(n ? n : 1, PrimRecord64{});
+  recs.resize(n ? n : 1); shd.resize(n ? n : 1);
+  if (!n) { std::memset(&recs[0], 0, sizeof(PrimRecord)); std::memset(&shd[0], 0, sizeof(ShadeRecord)); }
   parallel_for(n, (size_t)1 << 16, [&](size_t s0, size_t s1) {
-  for (size_t sl = s0; sl < s1; sl++) {
-    const int p = wide.slot_prim[sl];
-    PrimRecord& r = recs[sl]; ShadeRecord& h = shd[sl]; PrimRecord64& d = r64[sl];
-    std::memset(&r, 0, sizeof(r)); std::memset(&h, 0, sizeof(h)); std::memset(&d, 0, sizeof(d));
-    r.prim_id = p; r.bsdf = sc.prim_bsdf[p];
-    if (sc.prim_type[p] == 1) {
-      const double* q = &sc.tri_pos[9 * (size_t)p]; const double* nn = &sc.tri_nrm[9 * (size_t)p];
-      r.ax = (float)q[0]; r.ay = (float)q[1]; r.az = (float)q[2]; r.bx = (float)q[3]; r.by = (float)q[4]; r.bz = (float)q[5];
-      r.cx = (float)q[6]; r.cy = (float)q[7]; r.cz = (float)q[8]; r.is_tri = 1.0f;
-      h.n1x = (float)nn[0]; h.n1y = (float)nn[1]; h.n1z = (float)nn[2]; h.n2x = (float)nn[3]; h.n2y = (float)nn[4]; h.n2z = (float)nn[5];
-      h.n3x = (float)nn[6]; h.n3y = (float)nn[7]; h.n3z = (float)nn[8];
-      for (int k = 0; k < 9; k++) d.p[k] = q[k];
-      d.pad[2] = 1.0;                                // triangle flag
-    } else {
-      const double* q = &sc.sphere[4 * (size_t)p];
-      r.ax = (float)q[0]; r.ay = (float)q[1]; r.az = (float)q[2]; r.bx = (float)q[3]; r.by = (float)(q[3] * q[3]); r.is_tri = 0.0f;
-      d.p[0] = q[0]; d.p[1] = q[1]; d.p[2] = q[2]; d.p[3] = q[3]; d.p[4] = q[3] * q[3];   // r2 = r*r, sphere.h:23-24
-      d.pad[2] = 0.0;
+    for (size_t sl = s0; sl < s1; sl++) {
+      const int p = wide.slot_prim[sl];
+      PrimRecord& r = recs[sl]; ShadeRecord& h = shd[sl];
+      std::memset(&r, 0, sizeof(r)); std::memset(&h, 0, sizeof(h));
+      r.prim_id = p; r.bsdf = sc.prim_bsdf[p];
+      if (sc.prim_type[p] == 1) {
+        const double* q = &sc.tri_pos[9 * (size_t)p]; const double* nn = &sc.tri_nrm[9 * (size_t)p];
+        r.ax = (float)q[0]; r.ay = (float)q[1]; r.az = (float)q[2]; r.bx = (float)q[3]; r.by = (float)q[4]; r.bz = (float)q[5];
+        r.cx = (float)q[6]; r.cy = (float)q[7]; r.cz = (float)q[8]; r.is_tri = 1.0f;
+        h.n1x = (float)nn[0]; h.n1y = (float)nn[1]; h.n1z = (float)nn[2]; h.n2x = (float)nn[3]; h.n2y = (float)nn[4]; h.n2z = (float)nn[5];
+        h.n3x = (float)nn[6]; h.n3y = (float)nn[7]; h.n3z = (float)nn[8];
+      } else {
+        const double* q = &sc.sphere[4 * (size_t)p];
+        r.ax = (float)q[0]; r.ay = (float)q[1]; r.az = (float)q[2]; r.bx = (float)q[3]; r.by = (float)(q[3] * q[3]); r.is_tri = 0.0f;
+      }
     }
-  }
+  });
+}
+
+void flatten_records64(const dsrt_scene& sc, const WideBVH& wide, std::vector<PrimRecord64>& r64) {
+  const size_t n = wide.slot_prim.size();
+  r64.resize(n ? n : 1);
+  if (!n) std::memset(&r64[0], 0, sizeof(PrimRecord64));
+  parallel_for(n, (size_t)1 << 16, [&](size_t s0, size_t s1) {
+    for (size_t sl = s0; sl < s1; sl++) {
+      const int p = wide.slot_prim[sl];
+      PrimRecord64& d = r64[sl];
+      std::memset(&d, 0, sizeof(d));
+      if (sc.prim_type[p] == 1) {
+        const double* q = &sc.tri_pos[9 * (size_t)p];
+        for (int k = 0; k < 9; k++) d.p[k] = q[k];
+        d.pad[2] = 1.0;                                // triangle flag
+      } else {
+        const double* q = &sc.sphere[4 * (size_t)p];
+        d.p[0] = q[0]; d.p[1] = q[1]; d.p[2] = q[2]; d.p[3] = q[3]; d.p[4] = q[3] * q[3];   // r2 = r*r, sphere.h:23-24
+        d.pad[2] = 0.0;
+      }
+    }
   });
 }
 

@@ -14,9 +14,10 @@ struct WideBVH {
   int max_depth = 0;                // levels of wide nodes (bounds the traversal stack)
 };
 
-// primitive / shading / fp64 records in leaf-contiguous slot order (layout.h)
-void flatten_records(const dsrt_scene& sc, const WideBVH& wide, std::vector<PrimRecord>& recs, std::vector<ShadeRecord>& shd,
-                     std::vector<PrimRecord64>& r64);
+// primitive / shading records in leaf-contiguous slot order (layout.h)
+void flatten_records(const dsrt_scene& sc, const WideBVH& wide, std::vector<PrimRecord>& recs, std::vector<ShadeRecord>& shd);
+// fp64 records of the parity kernel (same slot order); built on demand by dsrt_primary_hits(mode 1)
+void flatten_records64(const dsrt_scene& sc, const WideBVH& wide, std::vector<PrimRecord64>& r64);
 // float light table; returns the number of light samples per path vertex (pathtracer.cpp:474)
 int flatten_lights(int n_lights, const int32_t* light_type, const double* light_param, int ns_area_light, bool with_env,
                    std::vector<Light>& out);

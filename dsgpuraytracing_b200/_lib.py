@@ -19,7 +19,8 @@ class DsrtError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libdsrt.so")
+    # DSRT_LIB: A/B runs of differently compiled builds of the same library (tools/sweeps/sweep_variants.py); never a fallback
+    return os.environ.get("DSRT_LIB") or os.path.join(_HERE, "libdsrt.so")
 
 
 _lib = None

@@ -30,6 +30,9 @@
 namespace dsrt {
 
 constexpr int kTraceThreads = 128;        // 4 warps per CTA
+#ifndef DSRT_TRACE_MIN_CTAS
+#define DSRT_TRACE_MIN_CTAS 7             // resident CTAs per SM the traversal kernels are compiled for (register cap 72; measured best of 6, 7, 8)
+#endif
 constexpr int kRayBlock = 17;             // floats per lane published for the cooperative primitive test
 constexpr int kPairCap = 192;             // (ray, primitive) pairs one warp can deal out per round set
 constexpr int kMaxDepthSlots = 64;        // queue-size slots per batch (depth 0..63)
@@ -127,36 +130,66 @@ __global__ void k_generate_centres(PathState ps, RenderParams rp, int n_paths) {
 //    least `tri_min` lanes have some pending, or when a lane has nothing else left to do -- so the primitive test
 //    executes with many lanes active.  tri_min = 0 restores test-at-once order (used by the counter tests).
 
+// shared-memory accesses of k_trace by 32-bit shared-window address (no generic-address arithmetic in the hot loop)
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(a), "r"(v.x), "r"(v.y)); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float ldsf(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)); }
+__device__ __forceinline__ void stsf(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v)); }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v)); }
+
+constexpr uint32_t kStackPitch = kTraceThreads * 8;     // bytes between consecutive stack entries of one lane
+constexpr uint32_t kBlkPitch = kTraceThreads * 4;       // bytes between consecutive values of one lane's ray block
+constexpr int kOwnerShift = 27;                         // pair word = slot | owner lane << 27 (slots < 2^27)
+
 template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
+__global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Accel A, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
                                                          const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
                                                          uint32_t* work, float4* hit_out, const float4* __restrict__ contrib,
                                                          float* accum, Totals* totals, int tri_min, int refill_busy, int wait_mode, int tri_cap,
                                                          int stack_entries, int coop_min) {
   extern __shared__ uint2 smem_stack[];
-  uint2* stack = smem_stack + threadIdx.x;
-  const int stride = blockDim.x;
   const int lane = threadIdx.x & 31;
-  // shared memory after the stacks (any-hit kernel only): per-lane ray blocks (kRayBlock floats, value-major so that
-  // lanes reading different owners hit different banks), and per-warp (slot, owner) pair tables + hit flags for the
-  // cooperative primitive test
-  float* rayblk = reinterpret_cast<float*>(smem_stack + (size_t)stack_entries * kTraceThreads);
-  uint32_t* pair_slot = reinterpret_cast<uint32_t*>(rayblk + kRayBlock * kTraceThreads) + (threadIdx.x >> 5) * kPairCap;
-  uint8_t* pair_owner = reinterpret_cast<uint8_t*>(reinterpret_cast<uint32_t*>(rayblk + kRayBlock * kTraceThreads) + (kTraceThreads / 32) * kPairCap) + (threadIdx.x >> 5) * kPairCap;
-  uint8_t* hit_flag = reinterpret_cast<uint8_t*>(reinterpret_cast<uint32_t*>(rayblk + kRayBlock * kTraceThreads) + (kTraceThreads / 32) * kPairCap) + (kTraceThreads / 32) * kPairCap + (threadIdx.x & ~31);
-  const int wbase = threadIdx.x & ~31;    // first thread of this warp within the CTA
+  // shared memory: [stacks: entry-major, 8 B per lane -> conflict free][any-hit kernel only: per-lane ray blocks (kRayBlock
+  // floats, value-major so that lanes reading different owners hit different banks) | per-warp pair words | hit flags]
+  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_stack);
+  const uint32_t s_stack = s_base + threadIdx.x * 8u;                                      // entry e at s_stack + e * kStackPitch
+  const uint32_t s_blk0 = s_base + (uint32_t)stack_entries * kStackPitch;                   // ray blocks of the CTA
+  const uint32_t s_blk_warp = s_blk0 + (threadIdx.x & ~31u) * 4u;                           // ... of this warp's lane 0
+  const uint32_t s_pair = s_blk0 + kRayBlock * kBlkPitch + (threadIdx.x >> 5) * (kPairCap * 4u);
+  const uint32_t s_flag_warp = s_blk0 + kRayBlock * kBlkPitch + (kTraceThreads / 32) * (kPairCap * 4u) + (threadIdx.x & ~31u);
   const uint32_t n = *n_ptr;
   TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
 
   // per-lane traversal state (kept across refills)
   bool busy = false, exhausted = false;
   uint32_t item = 0;
-  TraceRay ray; NodeFrame fr; WatertightRay wr;
-  float tbest = 0.f; TraceHit hit; int sp = 0, tstk = 0;   // tstk = postponed primitive groups currently on the stack
+  TraceRay ray; NodeFrame fr;
+  float tbest = 0.f; TraceHit hit; int tstk = 0;   // tstk = postponed primitive groups currently on the stack
+  uint32_t spa = s_stack;                          // address of the first free stack entry (== s_stack: empty)
   uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
   hit.slot = -1; hit.t = 0.f; hit.u = 0.f; hit.v = 0.f;
 
+  bool fin = false;                                // ray finished, result not written yet
   while (true) {
+    // ---- write the results of the rays that finished since the last refill (together: more lanes per store / atomic)
+    if (fin) {
+      fin = false;
+      if (ANY) {
+        if (hit_out) hit_out[item] = make_float4(hit.t, 0.f, 0.f, __int_as_float(hit.slot));
+        if (accum && hit.slot < 0) {       // unoccluded: add this light sample's contribution
+          const float4 c = contrib[item];
+          float* px = accum + 3 * (size_t)__float_as_uint(c.w);
+          if (c.x != 0.f) atomicAdd(px, c.x);
+          if (c.y != 0.f) atomicAdd(px + 1, c.y);
+          if (c.z != 0.f) atomicAdd(px + 2, c.z);
+        }
+      } else {
+        hit_out[item] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.slot));
+      }
+    }
     // ---- refill idle lanes
     const unsigned idle = __ballot_sync(kFull, !busy);
     if (idle && !exhausted) {
@@ -171,19 +204,22 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
           const float4 o = ray_o[item], d = ray_d[item];
           ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.tmax = o.w;
           ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.src_slot = __float_as_int(d.w);
-          fr = make_frame(ray); wr = make_watertight(ray);
+          fr = make_frame(ray);
+          const WatertightRay wr = make_watertight(ray);
           tbest = ray.tmax; hit.slot = -1; hit.t = ray.tmax; hit.u = 0.f; hit.v = 0.f;
-          sp = 0; tstk = 0; ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
+          spa = s_stack; tstk = 0; ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
           busy = true;
+          const uint32_t rb = s_blk_warp + lane * 4u;
           if (ANY) {
-            float* rb = rayblk + threadIdx.x;
-            rb[0 * kTraceThreads] = ray.ox; rb[1 * kTraceThreads] = ray.oy; rb[2 * kTraceThreads] = ray.oz;
-            rb[3 * kTraceThreads] = ray.dx; rb[4 * kTraceThreads] = ray.dy; rb[5 * kTraceThreads] = ray.dz;
-            rb[6 * kTraceThreads] = wr.bxx; rb[7 * kTraceThreads] = wr.bxy; rb[8 * kTraceThreads] = wr.bxz;
-            rb[9 * kTraceThreads] = wr.byx; rb[10 * kTraceThreads] = wr.byy; rb[11 * kTraceThreads] = wr.byz;
-            rb[12 * kTraceThreads] = wr.bzx; rb[13 * kTraceThreads] = wr.bzy; rb[14 * kTraceThreads] = wr.bzz;
-            rb[15 * kTraceThreads] = ray.tmax; rb[16 * kTraceThreads] = __int_as_float(ray.src_slot);
-            hit_flag[lane] = 0;
+            stsf(rb + 0 * kBlkPitch, ray.ox); stsf(rb + 1 * kBlkPitch, ray.oy); stsf(rb + 2 * kBlkPitch, ray.oz);
+            stsf(rb + 3 * kBlkPitch, ray.dx); stsf(rb + 4 * kBlkPitch, ray.dy); stsf(rb + 5 * kBlkPitch, ray.dz);
+            stsf(rb + 15 * kBlkPitch, ray.tmax); sts32(rb + 16 * kBlkPitch, (uint32_t)ray.src_slot);
+            sts8(s_flag_warp + lane, 0u);
+          }
+          {
+            stsf(rb + 6 * kBlkPitch, wr.bxx); stsf(rb + 7 * kBlkPitch, wr.bxy); stsf(rb + 8 * kBlkPitch, wr.bxz);
+            stsf(rb + 9 * kBlkPitch, wr.byx); stsf(rb + 10 * kBlkPitch, wr.byy); stsf(rb + 11 * kBlkPitch, wr.byz);
+            stsf(rb + 12 * kBlkPitch, wr.bzx); stsf(rb + 13 * kBlkPitch, wr.bzy); stsf(rb + 14 * kBlkPitch, wr.bzz);
           }
         }
       }
@@ -199,15 +235,15 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
       // that holds a group and has no room to park it skips the node step and tests its primitives first.
       if (busy && !(tgroup.y != 0u && tstk >= tri_cap)) {
         uint2 tnew = make_uint2(0u, 0u);
-        if (ngroup.y <= 0x00ffffffu && sp > 0) {
-          sp--;
-          const uint2 e = stack[sp * stride];
+        if (ngroup.y <= 0x00ffffffu && spa != s_stack) {
+          spa -= kStackPitch;
+          const uint2 e = lds64(spa);
           if (e.y > 0x00ffffffu) ngroup = e; else { tnew = e; tstk--; }   // node group / postponed primitive group
         }
         if (ngroup.y > 0x00ffffffu) {
           const uint32_t bit = 31u - (uint32_t)__clz(ngroup.y);
           ngroup.y &= ~(1u << bit);
-          if (ngroup.y > 0x00ffffffu) { stack[sp * stride] = ngroup; sp++; }
+          if (ngroup.y > 0x00ffffffu) { sts64(spa, ngroup); spa += kStackPitch; }
           const uint32_t slot = (bit - 24u) ^ fr.octinv;
           const uint32_t rel = __popc(ngroup.y & 0xffu & ((1u << slot) - 1u));
           const uint4* np = A.nodes + (size_t)(ngroup.x + rel) * 5;
@@ -219,7 +255,7 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
           did_node = true;
         }
         if (tnew.y) {
-          if (tgroup.y) { stack[sp * stride] = tgroup; sp++; tstk++; }   // keep the newest group in registers
+          if (tgroup.y) { sts64(spa, tgroup); spa += kStackPitch; tstk++; }   // keep the newest group in registers
           tgroup = tnew;
         }
       }
@@ -239,23 +275,25 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
           const int P = __shfl_sync(kFull, incl, 31);
           if (P >= coop_min && P <= kPairCap) {
             coop = true;
-            int i = incl - c;
+            uint32_t pa = s_pair + (uint32_t)(incl - c) * 4u;
             uint32_t m = pending ? tgroup.y : 0u;
-            while (m) { const uint32_t k = 31u - (uint32_t)__clz(m); m &= ~(1u << k); pair_slot[i] = tgroup.x + k; pair_owner[i] = (uint8_t)lane; i++; }
+            const uint32_t tag = tgroup.x | ((uint32_t)lane << kOwnerShift);
+            while (m) { const uint32_t k = 31u - (uint32_t)__clz(m); m &= ~(1u << k); sts32(pa, tag + k); pa += 4u; }
             if (pending) tgroup.y = 0u;
             __syncwarp();
             for (int base = 0; base < P; base += 32) {
               const int j = base + lane;
               if (j < P) {
-                const int slot = (int)pair_slot[j]; const int s = pair_owner[j];
-                const float* rb = rayblk + wbase + s;
+                const uint32_t pw = lds32(s_pair + (uint32_t)j * 4u);
+                const int slot = (int)(pw & ((1u << kOwnerShift) - 1u)); const uint32_t s = pw >> kOwnerShift;
+                const uint32_t rb = s_blk_warp + s * 4u;
                 TraceRay r2; WatertightRay w2;
-                r2.ox = rb[0 * kTraceThreads]; r2.oy = rb[1 * kTraceThreads]; r2.oz = rb[2 * kTraceThreads];
-                r2.dx = rb[3 * kTraceThreads]; r2.dy = rb[4 * kTraceThreads]; r2.dz = rb[5 * kTraceThreads];
-                w2.bxx = rb[6 * kTraceThreads]; w2.bxy = rb[7 * kTraceThreads]; w2.bxz = rb[8 * kTraceThreads];
-                w2.byx = rb[9 * kTraceThreads]; w2.byy = rb[10 * kTraceThreads]; w2.byz = rb[11 * kTraceThreads];
-                w2.bzx = rb[12 * kTraceThreads]; w2.bzy = rb[13 * kTraceThreads]; w2.bzz = rb[14 * kTraceThreads];
-                const float tmax2 = rb[15 * kTraceThreads]; const int src2 = __float_as_int(rb[16 * kTraceThreads]);
+                r2.ox = ldsf(rb + 0 * kBlkPitch); r2.oy = ldsf(rb + 1 * kBlkPitch); r2.oz = ldsf(rb + 2 * kBlkPitch);
+                r2.dx = ldsf(rb + 3 * kBlkPitch); r2.dy = ldsf(rb + 4 * kBlkPitch); r2.dz = ldsf(rb + 5 * kBlkPitch);
+                w2.bxx = ldsf(rb + 6 * kBlkPitch); w2.bxy = ldsf(rb + 7 * kBlkPitch); w2.bxz = ldsf(rb + 8 * kBlkPitch);
+                w2.byx = ldsf(rb + 9 * kBlkPitch); w2.byy = ldsf(rb + 10 * kBlkPitch); w2.byz = ldsf(rb + 11 * kBlkPitch);
+                w2.bzx = ldsf(rb + 12 * kBlkPitch); w2.bzy = ldsf(rb + 13 * kBlkPitch); w2.bzz = ldsf(rb + 14 * kBlkPitch);
+                const float tmax2 = ldsf(rb + 15 * kBlkPitch); const int src2 = (int)lds32(rb + 16 * kBlkPitch);
                 if (COUNT) cnt.prims++;
                 const float4* pp = A.prims + (size_t)slot * 3;
                 const float4 a = __ldg(pp), b = __ldg(pp + 1);
@@ -266,11 +304,11 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
                 } else {
                   h = hit_sphere(r2, a, b, slot == src2, true, tmax2, t);
                 }
-                if (h) hit_flag[s] = 1;
+                if (h) sts8(s_flag_warp + s, 1u);
               }
             }
             __syncwarp();
-            if (pending && hit_flag[lane]) { hit.slot = 0; hit.t = 0.f; done = true; }
+            if (pending && lds8(s_flag_warp + lane)) { hit.slot = 0; hit.t = 0.f; done = true; }
           }
         }
         if (!coop) {
@@ -284,7 +322,13 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
             float t, u = 0.f, v = 0.f; bool h;
             if (b.w != 0.0f) {
               const float4 c = __ldg(pp + 2);
-              h = (slot != ray.src_slot) && hit_triangle(ray, wr, a, b, c, tbest, t, u, v);
+              // the watertight basis lives in the lane's shared-memory ray block only (9 registers less in the loop)
+              const uint32_t rb = s_blk_warp + lane * 4u;
+              WatertightRay w2;
+              w2.bxx = ldsf(rb + 6 * kBlkPitch); w2.bxy = ldsf(rb + 7 * kBlkPitch); w2.bxz = ldsf(rb + 8 * kBlkPitch);
+              w2.byx = ldsf(rb + 9 * kBlkPitch); w2.byy = ldsf(rb + 10 * kBlkPitch); w2.byz = ldsf(rb + 11 * kBlkPitch);
+              w2.bzx = ldsf(rb + 12 * kBlkPitch); w2.bzy = ldsf(rb + 13 * kBlkPitch); w2.bzz = ldsf(rb + 14 * kBlkPitch);
+              h = (slot != ray.src_slot) && hit_triangle(ray, w2, a, b, c, tbest, t, u, v);
             } else {
               h = hit_sphere(ray, a, b, slot == ray.src_slot, ANY, tbest, t);
             }
@@ -295,24 +339,10 @@ __global__ void __launch_bounds__(kTraceThreads) k_trace(Accel A, const float4* 
           }
         }
       }
-      // (3) retire finished rays
+      // (3) retire finished rays (their results are written at the next refill)
       if (busy) {
-        if (!done && ngroup.y <= 0x00ffffffu && sp == 0 && tgroup.y == 0u) done = true;
-        if (done) {
-          busy = false; tgroup.y = 0u; ngroup.y = 0u; sp = 0; tstk = 0;
-          if (ANY) {
-            if (hit_out) hit_out[item] = make_float4(hit.t, 0.f, 0.f, __int_as_float(hit.slot));
-            if (accum && hit.slot < 0) {       // unoccluded: add this light sample's contribution
-              const float4 c = contrib[item];
-              float* px = accum + 3 * (size_t)__float_as_uint(c.w);
-              if (c.x != 0.f) atomicAdd(px, c.x);
-              if (c.y != 0.f) atomicAdd(px + 1, c.y);
-              if (c.z != 0.f) atomicAdd(px + 2, c.z);
-            }
-          } else {
-            hit_out[item] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.slot));
-          }
-        }
+        if (!done && ngroup.y <= 0x00ffffffu && spa == s_stack && tgroup.y == 0u) done = true;
+        if (done) { busy = false; fin = true; tgroup.y = 0u; ngroup.y = 0u; spa = s_stack; tstk = 0; }
       }
       const int nbusy = __popc(__ballot_sync(kFull, busy));
       if (nbusy == 0 || (!exhausted && nbusy <= refill_busy)) break;
@@ -525,7 +555,7 @@ struct dsrt_ctx {
   Camera cam{};
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
-  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20, opt_wait_mode = 0, opt_pool_batches = 16, opt_coop_min = 6;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20, opt_wait_mode = 0, opt_pool_batches = 16, opt_coop_min = 6, opt_tri_cap = -1, opt_max_ctas = 0;
   WideBVH wide;
   std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
   int env_w = 0, env_h = 0;
@@ -565,12 +595,21 @@ Accel make_accel(const dsrt_ctx* ctx, const DevState& D, bool parity) {
 }
 
 // shared-memory traversal stack: two entries (node group + postponed primitive group) per wide-BVH level per lane (whatever is not used stays L1 cache)
-int tri_stack_cap(const dsrt_ctx* ctx) { return std::max(ctx->wide.max_depth, 1) + 3; }   // postponed primitive groups a lane may park
+int tri_stack_cap(const dsrt_ctx* ctx) { return ctx->opt_tri_cap >= 0 ? (int)ctx->opt_tri_cap : 6; }   // postponed primitive groups a lane may park
 int stack_entries(const dsrt_ctx* ctx) { return std::max(ctx->wide.max_depth, 1) + tri_stack_cap(ctx) + 1; }
 // dynamic shared memory of k_trace: traversal stacks + (any-hit kernel) ray blocks, pair tables, hit flags
 size_t stack_bytes(const dsrt_ctx* ctx) {
   return (size_t)stack_entries(ctx) * kTraceThreads * sizeof(uint2) + (size_t)kRayBlock * kTraceThreads * sizeof(float) +
-         (size_t)(kTraceThreads / 32) * kPairCap * (sizeof(uint32_t) + 1) + kTraceThreads;
+         (size_t)(kTraceThreads / 32) * kPairCap * sizeof(uint32_t) + kTraceThreads;
+}
+
+// persistent grid = resident CTAs per SM (registers / shared-memory stack) x SM count
+int size_trace_grid(dsrt_ctx* ctx, DevState& D) {
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, false>, kTraceThreads, stack_bytes(ctx)));
+  if (ctx->opt_max_ctas > 0) per_sm = std::min(per_sm, (int)ctx->opt_max_ctas);
+  D.trace_blocks = D.sm_count * std::max(per_sm, 1);
+  return DSRT_OK;
 }
 
 int init_device(dsrt_ctx* ctx, DevState& D, int device) {
@@ -793,6 +832,8 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
   else if (n == "postpone_wait_mode") ctx->opt_wait_mode = value;
   else if (n == "pool_batches") ctx->opt_pool_batches = std::max<int64_t>(1, value);
   else if (n == "coop_min_pairs") ctx->opt_coop_min = value;
+  else if (n == "postpone_stack_groups") ctx->opt_tri_cap = value;     // -1: default (6)
+  else if (n == "max_ctas_per_sm") ctx->opt_max_ctas = value;          // 0: whatever fits
   else return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_option: unknown option " + n);
   return DSRT_OK;
 }
@@ -810,6 +851,7 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
   int rc = build_wide_bvh(b, pbox, ctx->n_prims, ctx->wide, err);
   if (rc) return fail(ctx, rc, err);
   if (ctx->wide.max_depth > kStackEntries) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel: wide BVH deeper than the traversal stack");
+  if (ctx->wide.slot_prim.size() >= ((size_t)1 << kOwnerShift)) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel: more than 2^27 primitives");
   Box3 all; all.reset(); for (const Box3& p : pbox) all.grow(p);
   double dg = 0; for (int k = 0; k < 3; k++) { double e = ctx->n_prims ? all.hi[k] - all.lo[k] : 0; double m = ctx->n_prims ? std::fmax(std::fabs(all.lo[k]), std::fabs(all.hi[k])) : 0; dg += (e + m) * (e + m); }
   ctx->scene_diag = std::sqrt(dg) + 1.0;
@@ -835,10 +877,6 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
       CK(cudaMalloc((void**)&D.d_env_rgb, np * 3 * sizeof(float))); CK(cudaMalloc((void**)&D.d_env_tp, np * sizeof(float)));
       CK(cudaMalloc((void**)&D.d_env_t, (size_t)ctx->env_h * sizeof(float))); CK(cudaMalloc((void**)&D.d_env_pgt, np * sizeof(float)));
     }
-    // persistent grid = resident CTAs per SM (registers / shared-memory stack) x SM count
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, false>, kTraceThreads, stack_bytes(ctx)));
-    D.trace_blocks = D.sm_count * std::max(per_sm, 1);
   }
   ctx->have_accel = true;
   return dsrt_upload_accel(ctx);
@@ -902,6 +940,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   if (!ctx->have_accel || !ctx->have_cam) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: call dsrt_build_accel and dsrt_set_camera first");
   if (spp_count < 0 || spp_stride < 1 || spp_begin < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: bad sample range");
   CK(cudaSetDevice(D.device));
+  { int rc0 = size_trace_grid(ctx, D); if (rc0) return rc0; }
   const int W = ctx->cam.width, H = ctx->cam.height;
   const int blocks_x = (W + 7) / 8, blocks_y = (H + 3) / 4;
   const int npp = blocks_x * blocks_y * 32;
@@ -1127,6 +1166,7 @@ int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) 
   if (!ctx->have_accel || !ctx->have_cam) return fail(ctx, DSRT_ERR_INVALID, "dsrt_primary_hits: call dsrt_build_accel and dsrt_set_camera first");
   DevState& D = ctx->devs[0];
   CK(cudaSetDevice(D.device));
+  { int rc0 = size_trace_grid(ctx, D); if (rc0) return rc0; }
   const int W = ctx->cam.width, H = ctx->cam.height, n = W * H;
   std::vector<int32_t> slots(n); std::vector<double> ts(n);
   cudaStream_t st = D.stream;
@@ -1179,6 +1219,7 @@ static int trace_batch(dsrt_ctx* ctx, bool any, int64_t n, const float* o, const
   if (n == 0) return DSRT_OK;
   DevState& D = ctx->devs[0];
   CK(cudaSetDevice(D.device));
+  { int rc0 = size_trace_grid(ctx, D); if (rc0) return rc0; }
   int rc = ensure_wavefront(ctx, D, (size_t)n, 1);
   if (rc) return rc;
   if (D.n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &D.d_counters, (size_t)1))) return rc; D.n_counter_blocks = 1; }

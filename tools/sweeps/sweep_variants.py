@@ -1,0 +1,38 @@
+"""A/B of differently compiled builds of libdsrt.so (DSRT_LIB) x run-time knobs on the bench workload.
+  python tools/sweeps/sweep_variants.py [spp]            # parent: one subprocess per library
+Each line: library, option set, Mrays/s and per-stage seconds of a 64-spp render (second of two)."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+LIBS = ["libdsrt.so"]
+OPTS = [{}, {"refill_busy_lanes": 12}, {"refill_busy_lanes": 16}, {"refill_busy_lanes": 18}, {"refill_busy_lanes": 22},
+        {"refill_busy_lanes": 16, "postpone_min_lanes": 12}, {"refill_busy_lanes": 16, "postpone_min_lanes": 16},
+        {"postpone_min_lanes": 12}, {"postpone_min_lanes": 16}, {"postpone_min_lanes": 24}, {"postpone_min_lanes": 28},
+        {"coop_min_pairs": 2}, {"coop_min_pairs": 10}, {"postpone_wait_mode": 1}, {"pool_batches": 32}, {"batch_spp": 4, "pool_batches": 8}]
+
+if len(sys.argv) > 1 and sys.argv[1] == "child":
+    import numpy as np
+    import dsgpuraytracing_b200 as D
+    from dsgpuraytracing_b200 import scenes as S
+    spp = int(sys.argv[2])
+    V, F = S.torus_knot(); V = V.astype(np.float32).astype(np.float64)
+    sc = S.cb_mesh_scene(V, F); cam = S.cam_dragon(1920, 1080)
+    core = D.Core(0); core.set_params(spp, 4, 8, 0); core.load(sc, camera=cam); core.set_option("stage_timing", 1)
+    defaults = {"postpone_stack_groups": -1, "max_ctas_per_sm": 0, "postpone_min_lanes": 20, "refill_busy_lanes": 20, "coop_min_pairs": 6, "postpone_wait_mode": 0, "pool_batches": 16, "batch_spp": 0}
+    for o in OPTS:
+        try:
+            for k, v in {**defaults, **o}.items():
+                core.set_option(k, v)
+        except D.DsrtError as e:
+            print(os.path.basename(os.environ.get("DSRT_LIB", "libdsrt.so")), o, "unsupported:", str(e)[:60]); continue
+        core.render(); rgb, st = core.render()
+        print("%-18s %-60s Mrays/s %7.1f  gpu_s %.4f extend %.4f connect %.4f shade %.4f" % (
+            os.path.basename(os.environ.get("DSRT_LIB", "libdsrt.so")), o, st.segments / st.gpu_seconds / 1e6, st.gpu_seconds,
+            st.extend_seconds, st.connect_seconds, st.shade_seconds), flush=True)
+else:
+    spp = sys.argv[1] if len(sys.argv) > 1 else "64"
+    for lib in LIBS:
+        p = os.path.join(ROOT, "dsgpuraytracing_b200", lib)
+        if not os.path.exists(p):
+            continue
+        subprocess.run([sys.executable, os.path.abspath(__file__), "child", spp], env={**os.environ, "DSRT_LIB": p})

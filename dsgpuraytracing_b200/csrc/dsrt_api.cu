@@ -555,7 +555,7 @@ struct dsrt_ctx {
   Camera cam{};
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
-  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20, opt_wait_mode = 0, opt_pool_batches = 16, opt_coop_min = 6, opt_tri_cap = -1, opt_max_ctas = 0;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 20, opt_refill = 20, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_tri_cap = -1, opt_max_ctas = 0;
   WideBVH wide;
   std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
   int env_w = 0, env_h = 0;
@@ -946,7 +946,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   const int npp = blocks_x * blocks_y * 32;
   const int aligned = (W % 8 == 0 && H % 4 == 0) ? 1 : 0;
   int batch_spp = (int)ctx->opt_batch_spp;
-  if (batch_spp <= 0) batch_spp = std::max(1, (int)((4u << 20) / (unsigned)npp));   // ~4M paths per batch
+  if (batch_spp <= 0) batch_spp = std::max(1, (int)((8u << 20) / (unsigned)npp));   // ~8M paths per batch
   batch_spp = std::min(batch_spp, std::max(1, spp_count));
   const size_t P = (size_t)npp * batch_spp;
   const int nls = ctx->n_light_samples;

@@ -108,7 +108,7 @@ int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t
 /* named knobs: "count_traversal" (0/1), "batch_spp" (camera samples per pixel per wavefront batch),
  * "stage_timing" (0/1: per-stage CUDA events), "postpone_min_lanes" (primitive tests wait until this many lanes
  * of a warp have some pending; 0 = test at once; default 20), "pool_batches" (how many consecutive batches share one
- * deep-path pool: paths that survive depth 0 are gathered and advanced together; default 16, 1 = per batch),
+ * deep-path pool: paths that survive depth 0 are gathered and advanced together; default 8, 1 = per batch),
  * "coop_min_pairs" (any-hit kernel: when a warp has at least this many pending (ray, primitive) pairs they are
  * dealt out one per lane; default 6, a huge value disables the cooperative test) */
 int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value);

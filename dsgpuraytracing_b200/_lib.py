@@ -276,7 +276,7 @@ class Core:
 
 
 # ---- host side (libdsrt_host.so): COLLADA import + the PathTracer mirror -------------------------------------------
-HOST_EXPORTED_SYMBOLS = ["dsrth_load_dae", "dsrth_free", "dsrth_get_scene", "dsrth_get_camera", "dsrth_render_file"]
+HOST_EXPORTED_SYMBOLS = ["dsrth_load_dae", "dsrth_free", "dsrth_get_scene", "dsrth_get_camera", "dsrth_render_file", "dsrth_load_envmap"]
 _hostlib = None
 
 
@@ -319,6 +319,20 @@ def load_dae(path, width, height, cam_info=None):
         return out, cam
     finally:
         H.dsrth_free(h)
+
+
+def load_envmap(path):
+    """-e option: scan-line OpenEXR or .pfm lat-long map -> float32 [h, w, 3], top row first (dsrt_set_envmap layout)."""
+    H = load_host_library()
+    w, h = C.c_int32(0), C.c_int32(0); err = C.create_string_buffer(512)
+    rc = H.dsrth_load_envmap(path.encode(), C.byref(w), C.byref(h), None, C.c_int64(0), err, 512)
+    if rc:
+        raise DsrtError(f"dsrth_load_envmap({path}) failed: {err.value.decode()}")
+    out = np.zeros((h.value, w.value, 3), np.float32)
+    rc = H.dsrth_load_envmap(path.encode(), C.byref(w), C.byref(h), C.c_void_p(out.ctypes.data), C.c_int64(out.size), err, 512)
+    if rc:
+        raise DsrtError(f"dsrth_load_envmap({path}) failed: {err.value.decode()}")
+    return out
 
 
 def render_file(path, width, height, spp, ns_area_light, max_depth, cam_info=None, n_gpus=1, seed=0, png=None):

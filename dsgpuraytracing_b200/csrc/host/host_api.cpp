@@ -3,6 +3,7 @@
 #include <string>
 
 #include "../../../include/dsrt_host.h"
+#include "image_io.h"
 #include "pathtracer.h"
 #include "scene_loader.h"
 
@@ -67,6 +68,18 @@ int dsrth_render_file(const char* dae_path, const char* cam_info, int32_t width,
   if (bvh_seconds) *bvh_seconds = pt.bvh_build_seconds;
   if (render_seconds) *render_seconds = pt.render_seconds;
   if (png_path && *png_path && !pt.save_image(png_path)) { set_err(err, err_len, pt.last_error()); return DSRT_ERR_INVALID; }
+  return DSRT_OK;
+}
+
+int dsrth_load_envmap(const char* path, int32_t* width, int32_t* height, float* rgb, int64_t cap, char* err, int32_t err_len) {
+  if (!path || !width || !height) { set_err(err, err_len, "bad arguments"); return DSRT_ERR_INVALID; }
+  HDRImageBuffer img; std::string e;
+  if (!load_envmap(path, img, e)) { set_err(err, err_len, e); return DSRT_ERR_INVALID; }
+  *width = (int32_t)img.w; *height = (int32_t)img.h;
+  if (rgb) {
+    if (cap < (int64_t)img.data.size()) { set_err(err, err_len, "buffer too small"); return DSRT_ERR_INVALID; }
+    std::memcpy(rgb, img.data.data(), img.data.size() * sizeof(float));
+  }
   return DSRT_OK;
 }
 

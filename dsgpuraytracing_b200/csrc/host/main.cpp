@@ -2,7 +2,8 @@
 //   -s <spp>  -l <area-light samples>  -m <max ray depth>  -t <threads, accepted and ignored>  -w <width>  -h <height>
 //   -f <cam_*.info>  -c (CPU render: refused, there is no CPU fallback)  -v (viewer: not part of this port)
 //   -e <environment map>: the reference declares -e but leaves it out of its getopt string (main.cpp:85, 99-101) and
-//      loads .exr through the vendored tinyexr; here -e works and reads a binary .pfm (PF, little endian) lat-long map
+//      loads .exr through the vendored tinyexr; here -e works and reads scan-line OpenEXR (NONE / RLE / ZIPS / ZIP, host/image_io.cpp)
+//      or a binary .pfm (PF, little endian) lat-long map
 // additions: -g <number of GPUs>  -o <output.png>  -S <seed>  -r <raw float dump of the linear buffer>
 // As in the reference, -h is the frame HEIGHT and the default frame is 1000x1000 (main.cpp:79-80).
 #include <unistd.h>
@@ -11,25 +12,11 @@
 #include <cstdlib>
 #include <string>
 
+#include "image_io.h"
 #include "pathtracer.h"
 #include "scene_loader.h"
 
 using namespace dsrt_host;
-
-// Portable float map: "PF\n<w> <h>\n<-scale>\n" + h rows of w RGB float triplets, BOTTOM row first.
-static bool load_pfm(const std::string& path, HDRImageBuffer& img, std::string& err) {
-  FILE* f = fopen(path.c_str(), "rb");
-  if (!f) { err = "cannot open " + path; return false; }
-  char magic[3] = {0, 0, 0}; int w = 0, h = 0; float scale = 0;
-  if (fscanf(f, "%2s %d %d %f", magic, &w, &h, &scale) != 4 || std::string(magic) != "PF" || w <= 0 || h <= 0) { fclose(f); err = "not a colour .pfm: " + path; return false; }
-  fgetc(f);
-  if (scale > 0) { fclose(f); err = "big-endian .pfm is not supported"; return false; }
-  img.resize((size_t)w, (size_t)h);
-  for (int y = h - 1; y >= 0; y--)      // file is bottom-up; the environment map wants row 0 = +y pole
-    if (fread(&img.data[(size_t)y * w * 3], sizeof(float), (size_t)w * 3, f) != (size_t)w * 3) { fclose(f); err = "truncated .pfm"; return false; }
-  fclose(f);
-  return true;
-}
 
 static void usage(const char* bin) {
   printf("Usage: %s [options] <scenefile.dae>\n", bin);
@@ -37,7 +24,7 @@ static void usage(const char* bin) {
   printf("  -t <INT>  render threads (ignored: the render runs on the GPU)\n  -m <INT>  maximum ray depth (default 1)\n");
   printf("  -w <INT>  frame width (default 1000)\n  -h <INT>  frame height (default 1000)\n  -f <FILE> camera .info file\n");
   printf("  -g <INT>  number of GPUs (default 1)\n  -o <FILE> output PNG (default \"Screen Shot GPU <time>.png\")\n");
-  printf("  -e <FILE> lat-long environment map (.pfm)\n");
+  printf("  -e <FILE> lat-long environment map (.exr or .pfm)\n");
   printf("  -S <INT>  Philox seed (default 0)\n  -r <FILE> also dump the linear float RGB buffer\n");
 }
 
@@ -75,7 +62,7 @@ int main(int argc, char** argv) {
   FlatScene scene; HostCamera camera; std::string err;
   if (!load_collada(sceneFilePath, (size_t)screenW, (size_t)screenH, scene, camera, err)) { fprintf(stderr, "error: %s\n", err.c_str()); return 1; }
   HDRImageBuffer envmap;
-  if (!envName.empty() && !load_pfm(envName, envmap, err)) { fprintf(stderr, "error: %s\n", err.c_str()); return 1; }
+  if (!envName.empty() && !load_envmap(envName, envmap, err)) { fprintf(stderr, "error: %s\n", err.c_str()); return 1; }
   PathTracer pathtracer(ns_aa, max_ray_depth, ns_area_light, 1, 1, 1, num_threads, envName.empty() ? nullptr : &envmap);
   pathtracer.set_gpus(n_gpus); pathtracer.set_seed(seed);
   pathtracer.set_camera(&camera);

@@ -59,6 +59,8 @@ pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 
 $CXX "$OUT"/obj/*.o -o "$OUT/ref_driver" -lpthread -Wl,--unresolved-symbols=ignore-all
+# the reference's vendored tinyexr behind a tiny command-line tool: pins the product's own OpenEXR reader
+$CXX -std=gnu++11 -O2 -w -fpermissive -I$REF/CMU462/include/CMU462 "$HERE/exr_ref.cpp" -o "$OUT/exr_ref"
 
 # stage the scene/camera DATA files next to the binary so GPU-box tests can use them
 # (data, not source; still kept out of git history by .gitignore)

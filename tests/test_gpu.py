@@ -289,3 +289,26 @@ def test_environment_light_gpu(name, core, golden):
     assert abs(int(st.shadow_rays) - int(cnt[1])) <= 2e-4 * cnt[1] + 8
     ok, info = images_match(rgb, ref)
     assert ok, info
+
+
+@needs_scenes
+def test_cli_environment_map_from_exr(tmp_path, core):
+    """`pathtracer -e map.exr` (the reference's dead -e option, main.cpp:99-101): the file goes through the host OpenEXR
+    reader into dsrt_set_envmap; same frame as handing the decoded array to the C ABI directly."""
+    import subprocess
+    exr = os.path.join(GOLDEN, "exr", "zip_half.exr")
+    exe = os.path.join(os.path.dirname(D.lib_path()), "pathtracer")
+    raw = tmp_path / "e.raw"; png = tmp_path / "e.png"
+    dae = O.ref_scene_path("CBspheres_lambertian.dae")
+    r = subprocess.run([exe, "-s", "4", "-l", "2", "-m", "3", "-w", "96", "-h", "72", "-S", "9", "-e", exr, "-o", str(png), "-r", str(raw), dae],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = np.fromfile(raw, np.float32).reshape(72, 96, 3)
+    arr, cam = D.load_dae(dae, 96, 72)
+    core.set_params(4, 2, 3, 9)
+    core.set_envmap(D.load_envmap(exr))
+    core.load(arr, camera=cam)
+    want, _ = core.render()
+    core.set_envmap(None)
+    assert np.isfinite(got).all() and got.mean() > 0
+    assert np.allclose(got, want, rtol=1e-4, atol=1e-5 * want.mean())

@@ -221,3 +221,50 @@ def test_environment_light_float_pipeline_matches_oracle(name, golden):
     assert abs(int(c2[1]) - int(cnt[0])) <= 2 and abs(int(c2[2]) - int(cnt[1])) <= 8
     ok, info = images_match(rgb, ref)
     assert ok, info
+
+
+# ---- host C++ side: environment-map readers (-e option, reference src/main.cpp:30-67) --------------------------------
+EXR_DIR = os.path.join(ROOT, "tests", "golden", "exr")
+
+
+@pytest.mark.parametrize("name", ["zip_half", "zip_float", "none_float", "zips_half", "zip_half_decreasing", "rle_half"])
+def test_exr_reader_matches_reference_tinyexr(name):
+    """<name>.npy = what the reference's load_exr (vendored tinyexr) reads from <name>.exr (tests/golden/exr/make_exr_golden.py;
+    zip_half / zip_float were also WRITTEN by tinyexr).  rle_half (not supported by that tinyexr) is pinned by the writer's input."""
+    got = D.load_envmap(os.path.join(EXR_DIR, name + ".exr"))
+    want = np.load(os.path.join(EXR_DIR, name + ".npy"))
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))      # bit exact, halves included
+
+
+def test_exr_reader_extra_channels_offsets_and_errors(tmp_path):
+    from tests.exr_writer import write_exr
+    rng = np.random.default_rng(7)
+    a = rng.random((19, 23, 4)).astype(np.float32)
+    # RGBA with a HALF alpha and a UINT id channel, data window not at the origin: channels are found by NAME
+    p = str(tmp_path / "rgba.exr")
+    write_exr(p, {"R": a[..., 0], "G": a[..., 1], "B": a[..., 2], "A": a[..., 3].astype(np.float16),
+                  "id": (a[..., 3] * 100).astype(np.uint32)}, "zip", data_window_origin=(-5, 11))
+    assert np.array_equal(D.load_envmap(p), a[..., :3])
+    # 1x1 image, ragged last ZIP block (19 rows = 16 + 3)
+    q = str(tmp_path / "one.exr")
+    write_exr(q, {"R": a[:1, :1, 0], "G": a[:1, :1, 1], "B": a[:1, :1, 2]}, "zips")
+    assert np.array_equal(D.load_envmap(q), a[:1, :1, :3])
+    # .pfm through the same entry point (bottom row first in the file)
+    f = str(tmp_path / "m.pfm")
+    with open(f, "wb") as fh:
+        fh.write(b"PF\n23 19\n-1.0\n" + a[::-1, :, :3].tobytes())
+    assert np.array_equal(D.load_envmap(f), a[..., :3])
+    # errors are returned, never exit(): missing file, not an image, truncated, unsupported compression (PIZ = 4), no RGB
+    raw = open(p, "rb").read()
+    bad = {"trunc.exr": raw[: len(raw) // 2], "junk.exr": b"hello world, not an image", "piz.exr": raw.replace(b"compression\0compression\0\x01\0\0\0\x03", b"compression\0compression\0\x01\0\0\0\x04")}
+    for nm, data in bad.items():
+        fp = str(tmp_path / nm); open(fp, "wb").write(data)
+        with pytest.raises(D.DsrtError):
+            D.load_envmap(fp)
+    with pytest.raises(D.DsrtError):
+        D.load_envmap(str(tmp_path / "missing.exr"))
+    g = str(tmp_path / "grey.exr")
+    write_exr(g, {"Y": a[..., 0]}, "none")
+    with pytest.raises(D.DsrtError):
+        D.load_envmap(g)

@@ -30,6 +30,9 @@
 namespace dsrt {
 
 constexpr int kTraceThreads = 128;        // 4 warps per CTA
+#ifndef DSRT_SHADE_MIN_CTAS
+#define DSRT_SHADE_MIN_CTAS 6             // k_shade: 80 registers (unbounded it takes 159 and runs at 12 warps / SM); measured 3: 17.3, 4: 14.3, 5: 13.6, 6: 13.0 ms per 64 spp
+#endif
 #ifndef DSRT_TRACE_MIN_CTAS
 #define DSRT_TRACE_MIN_CTAS 7             // resident CTAs per SM the traversal kernels are compiled for (register cap 72; measured best of 6, 7, 8)
 #endif
@@ -390,7 +393,7 @@ struct QueueSink {
 
 // dst == ps (in place): survivors keep their slot and are appended to next_queue (pool iterations).
 // dst != ps: survivors are COPIED into dst at an appended index (depth-0 pass of a batch -> the deep-path pool).
-__global__ void __launch_bounds__(128) k_shade(PathState ps, const float4* __restrict__ prims, SceneDev sc, RenderParams rp,
+__global__ void __launch_bounds__(128, DSRT_SHADE_MIN_CTAS) k_shade(PathState ps, const float4* __restrict__ prims, SceneDev sc, RenderParams rp,
                                                const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
                                                PathState dst, uint32_t* next_queue, uint32_t* next_count, uint32_t dst_cap,
                                                ShadowQueue sq, uint32_t* s_count, float* accum) {

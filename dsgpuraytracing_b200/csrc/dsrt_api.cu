@@ -266,7 +266,12 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
       const bool pending = busy && tgroup.y != 0u;
       const bool must = pending && !did_node;                          // this lane had no node to open: it needs its primitives now
       const unsigned pm = __ballot_sync(kFull, pending);
-      if (pm && ((wait_mode ? !__any_sync(kFull, did_node) : __any_sync(kFull, must)) || __popc(pm) >= tri_min)) {
+      // wait_mode 0: test as soon as ANY lane must; 1: only when no lane opened a node; K >= 2: when K lanes must (or no lane
+      // opened a node, so the warp always makes progress)
+      const bool trigger = wait_mode == 0 ? __any_sync(kFull, must)
+                         : (wait_mode == 1 ? !__any_sync(kFull, did_node)
+                                           : (__popc(__ballot_sync(kFull, must)) >= wait_mode || !__any_sync(kFull, did_node)));
+      if (pm && (trigger || __popc(pm) >= tri_min)) {
         bool coop = false;
         if (ANY) {
           // Cooperative test: the pending (ray, primitive) pairs of the whole warp are dealt out one per lane, so the

@@ -5,7 +5,8 @@ import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 LIBS = ["libdsrt.so"]
-OPTS = [{}, {}]
+OPTS = [{}, {"postpone_wait_mode": 2}, {"postpone_wait_mode": 3}, {"postpone_wait_mode": 4}, {"postpone_wait_mode": 6}, {"postpone_wait_mode": 8},
+        {"postpone_wait_mode": 4, "postpone_min_lanes": 24}, {"postpone_wait_mode": 4, "postpone_min_lanes": 28}, {"postpone_wait_mode": 6, "postpone_min_lanes": 28}]
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import numpy as np

@@ -196,7 +196,7 @@ extern "C" int dsrt_build_bvh2(const dsrt_scene* sc, double* node_bbox, int32_t*
   std::vector<Box3>().swap(pbox);
   b.nodes.resize(2 * (size_t)sc->n_prims + 2);
   b.nodes[0] = root; b.next_node = 1;
-  b.spare_threads = (int)std::max(1u, std::thread::hardware_concurrency()) - 1;
+  b.spare_threads = host_threads() - 1;
   const double t1 = now();
   b.split(0);   // the reference splits the root unconditionally (bvh.cpp:199-200)
   const double t2 = now();

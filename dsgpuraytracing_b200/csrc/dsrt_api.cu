@@ -968,7 +968,6 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   CK(cudaMemsetAsync(D.d_counters, 0, sizeof(Counters) * (size_t)std::max(n_batches, 1), st));
   CK(cudaMemsetAsync(D.d_totals, 0, sizeof(Totals), st));
   D.ev_used = 0; D.spans.clear(); D.launches = 0; D.batches = (uint32_t)n_batches;
-  CK(cudaEventRecord(D.ev_begin, st));
 
   SceneDev sc; sc.bsdf = (const Bsdf*)D.d_bsdf; sc.lights = (const Light*)D.d_lights; sc.shade = (const float4*)D.d_shade;
   sc.n_lights = ctx->n_lights; sc.n_light_samples = nls;
@@ -997,6 +996,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
     }
     CK(cudaMemsetAsync(D.d_pool_counters, 0, sizeof(PoolCounters) * (size_t)n_groups, st));
   }
+  CK(cudaEventRecord(D.ev_begin, st));     // after every (re)allocation: gpu_seconds covers the kernels of the frame only
   auto trace = [&](bool any, const float4* ro, const float4* rd, const uint32_t* q, const uint32_t* n_ptr, uint32_t* work, float4* hits, const float4* contrib) {
     span_begin(any ? 1 : 0);
     if (any) {

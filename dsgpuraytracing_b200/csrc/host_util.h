@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <limits>
 #include <thread>
 #include <vector>
@@ -33,7 +34,11 @@ struct Box3 {
   double centre(int k) const { return 0.5 * (lo[k] + hi[k]); }
 };
 
-inline int host_threads() { return (int)std::max(1u, std::thread::hardware_concurrency()); }
+// worker threads of the host-side builders; DSRT_HOST_THREADS overrides the core count (the results never depend on it)
+inline int host_threads() {
+  if (const char* e = std::getenv("DSRT_HOST_THREADS")) { const int n = std::atoi(e); if (n >= 1) return n; }
+  return (int)std::max(1u, std::thread::hardware_concurrency());
+}
 
 // f(begin, end) over [0, n) in chunks of `grain`, handed out dynamically to up to host_threads() workers.  The chunk
 // boundaries do not depend on the thread count, so anything a chunk computes on its own is schedule independent.

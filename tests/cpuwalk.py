@@ -48,6 +48,12 @@ class Walk:
         lib().cw_info(self.h, C.byref(n), C.byref(d))
         return n.value, d.value
 
+    def nodes(self):
+        n, _ = self.info()
+        out = np.zeros((n, 80), np.uint8)
+        lib().cw_nodes(self.h, C.c_void_p(out.ctypes.data))
+        return out
+
     def slot_prim(self):
         out = np.zeros(self.n_prims, np.int32)
         lib().cw_slot_prim(self.h, C.c_void_p(out.ctypes.data))

@@ -268,3 +268,29 @@ def test_exr_reader_extra_channels_offsets_and_errors(tmp_path):
     write_exr(g, {"Y": a[..., 0]}, "none")
     with pytest.raises(D.DsrtError):
         D.load_envmap(g)
+
+
+def test_parallel_host_builders_do_not_depend_on_the_thread_count():
+    """SAH build (task parallel), DP collapse (subtree tasks) and wide-node emission (1024 independent subtrees after a
+    breadth-first top) must give byte-identical results whatever the number of worker threads."""
+    from dsgpuraytracing_b200 import scenes as S
+    sc, _ = S.triangle_soup(300000, seed=11)
+    res = []
+    old = os.environ.get("DSRT_HOST_THREADS")
+    try:
+        for threads in ("1", "5"):
+            os.environ["DSRT_HOST_THREADS"] = threads
+            bvh = D.build_bvh2(sc)
+            w = Walk(sc, bvh, 1)
+            res.append((bvh, w.nodes(), w.slot_prim(), w.info()))
+    finally:
+        if old is None:
+            os.environ.pop("DSRT_HOST_THREADS", None)
+        else:
+            os.environ["DSRT_HOST_THREADS"] = old
+    (b1, n1, s1, i1), (b5, n5, s5, i5) = res
+    for k in b1:
+        assert np.array_equal(b1[k], b5[k]), k
+    assert i1 == i5 and np.array_equal(n1, n5) and np.array_equal(s1, s5)
+    assert i1[0] > 1024 * 8          # large enough for the parallel emission path
+    assert np.array_equal(np.sort(s1), np.arange(300000))

@@ -87,6 +87,6 @@ if __name__ == "__main__":
     n = a.soup_min
     while want("C5") and n <= a.soup_max:
         sc, cam = S.triangle_soup(n << 20)
-        run(f"C5 triangle soup {n}Mi tris 3840x2160 64spp l1 m8, {gtag}", sc, cam, 8 if q else 64, 1, 8, reps=1)
+        run(f"C5 triangle soup {n}Mi tris 3840x2160 64spp l1 m8, {gtag}", sc, cam, 8 if q else 64, 1, 8, reps=2)
         del sc
         n *= 2

@@ -107,14 +107,13 @@ int dsrt_set_envmap(dsrt_ctx* ctx, int32_t width, int32_t height, const float* r
 int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t max_ray_depth, uint32_t seed);
 /* named knobs: "count_traversal" (0/1), "batch_spp" (camera samples per pixel per wavefront batch),
  * "stage_timing" (0/1: per-stage CUDA events), "postpone_min_lanes" (primitive tests wait until this many lanes
- * of a warp have some pending; 0 = test at once; default 20), "pool_batches" (how many consecutive batches share one
+ * of a warp have some pending; 0 = test at once; default 12), "pool_batches" (how many consecutive batches share one
  * deep-path pool: paths that survive depth 0 are gathered and advanced together; default 8, 1 = per batch),
  * "coop_min_pairs" (any-hit kernel: when a warp has at least this many pending (ray, primitive) pairs they are
  * dealt out one per lane; default 6, a huge value disables the cooperative test), "postpone_wait_mode" (0: primitives are
  * tested as soon as one lane has nothing else to do; 1: only when no lane opened a node; K >= 2: when K lanes wait),
- * "refill_busy_lanes" (a warp fetches new rays for its idle lanes when at most this many are busy; default 20),
- * "postpone_stack_groups" (postponed primitive groups a lane may park on its stack; default 6), "max_ctas_per_sm"
- * (caps the persistent grid; 0 = what fits), "skip_null_shadow" */
+ * "refill_busy_lanes" (a warp fetches new rays for its idle lanes when at most this many are busy; default 18),
+ * "max_ctas_per_sm" (caps the persistent grid; 0 = what fits), "skip_null_shadow" */
 int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value);
 
 /* Host SAH builder = BVHAccel::BVHAccel + buildBVH (src/bvh.cpp:21-202: 32 buckets, max leaf 4, with the

@@ -1,6 +1,6 @@
 // image_io.cpp -- OpenEXR / PFM readers (see image_io.h).  Written against the OpenEXR file layout document: magic,
-// version word, attribute list, line-offset table, chunks of 1 (NONE, RLE, ZIPS) or 16 (ZIP) scan lines; a compressed
-// chunk is zlib / run-length data of the byte-planar, delta-predicted pixel bytes.
+// version word, attribute list, line-offset table, chunks of 1 (NONE, RLE, ZIPS), 16 (ZIP) or 32 (PIZ) scan lines; a ZIP / RLE
+// chunk is zlib / run-length data of the byte-planar, delta-predicted pixel bytes, a PIZ chunk is Huffman-coded wavelet data.
 #include "image_io.h"
 
 #include <zlib.h>
@@ -56,6 +56,197 @@ bool rle_decode(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t 
   return out.size() == expect;
 }
 
+
+// ---- PIZ: 16-bit range compaction (bitmap + lookup table), 2-D Haar-like wavelet per channel, canonical Huffman coding
+// with a run-length symbol.  Restated from the OpenEXR file-format description (the layout ImfPizCompressor / ImfHuf / ImfWav
+// write); the reference reads such files through its vendored tinyexr.
+constexpr int kHufEncBits = 16, kHufDecBits = 14;
+constexpr int kHufEncSize = (1 << kHufEncBits) + 1, kHufDecSize = 1 << kHufDecBits, kHufDecMask = kHufDecSize - 1;
+constexpr int kShortZeroRun = 59, kLongZeroRun = 63, kShortestLongRun = 2 + kLongZeroRun - kShortZeroRun;
+
+struct BitReader {
+  const uint8_t* p; const uint8_t* end; uint64_t c = 0; int lc = 0; bool ok = true;
+  uint32_t get(int n) {
+    while (lc < n) { if (p >= end) { ok = false; return 0; } c = (c << 8) | *p++; lc += 8; }
+    lc -= n;
+    return (uint32_t)((c >> lc) & ((1ull << n) - 1));
+  }
+};
+
+struct HufDec { uint32_t len = 0, lit = 0; std::vector<uint32_t> longs; };
+
+bool huf_uncompress(const uint8_t* src, size_t n_src, std::vector<uint16_t>& out, size_t n_out) {
+  out.assign(n_out, 0);
+  if (n_src == 0) return n_out == 0;
+  if (n_src < 20) return false;
+  auto rd32 = [&](size_t o) { uint32_t v; std::memcpy(&v, src + o, 4); return v; };
+  uint32_t im = rd32(0); const uint32_t iM = rd32(4); const uint32_t n_bits = rd32(12);
+  if (im >= (uint32_t)kHufEncSize || iM >= (uint32_t)kHufEncSize) return false;
+  // code lengths, 6 bits each, with short / long runs of zero lengths
+  std::vector<uint64_t> code((size_t)kHufEncSize, 0);
+  BitReader br{src + 20, src + n_src};
+  for (uint32_t i = im; i <= iM; i++) {
+    const uint32_t l = br.get(6);
+    if (!br.ok) return false;
+    code[i] = l;
+    if (l == (uint32_t)kLongZeroRun || l >= (uint32_t)kShortZeroRun) {
+      uint32_t run = l == (uint32_t)kLongZeroRun ? br.get(8) + (uint32_t)kShortestLongRun : l - (uint32_t)kShortZeroRun + 2;
+      if (!br.ok || i + run > iM + 1) return false;
+      while (run--) code[i++] = 0;
+      i--;
+    }
+  }
+  const uint8_t* data = br.p;                             // the table ends on a byte boundary
+  if ((uint64_t)n_bits > 8ull * (uint64_t)(src + n_src - data)) return false;
+  // canonical codes from the lengths: code = length | (value << 6)
+  {
+    uint64_t n[59] = {0};
+    for (int i = 0; i < kHufEncSize; i++) { if (code[i] > 58) return false; n[code[i]]++; }
+    uint64_t c = 0;
+    for (int i = 58; i > 0; --i) { const uint64_t nc = (c + n[i]) >> 1; n[i] = c; c = nc; }
+    for (int i = 0; i < kHufEncSize; i++) { const uint64_t l = code[i]; if (l > 0) code[i] = l | (n[l]++ << 6); }
+  }
+  // decoding table: 14-bit primary index; longer codes are searched in a per-entry list
+  std::vector<HufDec> dec((size_t)kHufDecSize);
+  for (uint32_t i = im; i <= iM; i++) {
+    const uint64_t c = code[i] >> 6; const int l = (int)(code[i] & 63);
+    if (c >> l) return false;
+    if (l > kHufDecBits) {
+      HufDec& pl = dec[(size_t)(c >> (l - kHufDecBits))];
+      if (pl.len) return false;
+      pl.longs.push_back(i);
+    } else if (l) {
+      HufDec* pl = &dec[(size_t)(c << (kHufDecBits - l))];
+      for (uint64_t k = 1ull << (kHufDecBits - l); k > 0; k--, pl++) {
+        if (pl->len || !pl->longs.empty()) return false;
+        pl->len = (uint32_t)l; pl->lit = i;
+      }
+    }
+  }
+  // decode
+  const uint8_t* in = data; const uint8_t* ie = data + (n_bits + 7) / 8;
+  uint64_t c = 0; int lc = 0; size_t o = 0;
+  auto emit = [&](uint32_t sym) -> bool {
+    if (sym == iM) {                                      // run-length symbol: repeat the previous value `count` times
+      if (lc < 8) { if (in >= ie) return false; c = (c << 8) | *in++; lc += 8; }
+      lc -= 8;
+      uint32_t cs = (uint32_t)((c >> lc) & 0xff);
+      if (o + cs > n_out || o == 0) return false;
+      const uint16_t s = out[o - 1];
+      while (cs-- > 0) out[o++] = s;
+      return true;
+    }
+    if (o >= n_out) return false;
+    out[o++] = (uint16_t)sym;
+    return true;
+  };
+  while (in < ie) {
+    c = (c << 8) | *in++; lc += 8;
+    while (lc >= kHufDecBits) {
+      const HufDec& pl = dec[(size_t)((c >> (lc - kHufDecBits)) & (uint64_t)kHufDecMask)];
+      if (pl.len) { lc -= (int)pl.len; if (!emit(pl.lit)) return false; }
+      else {
+        if (pl.longs.empty()) return false;
+        size_t j = 0;
+        for (; j < pl.longs.size(); j++) {
+          const int l = (int)(code[pl.longs[j]] & 63);
+          while (lc < l && in < ie) { c = (c << 8) | *in++; lc += 8; }
+          if (lc >= l && (code[pl.longs[j]] >> 6) == ((c >> (lc - l)) & ((1ull << l) - 1))) {
+            lc -= l; if (!emit(pl.longs[j])) return false;
+            break;
+          }
+        }
+        if (j == pl.longs.size()) return false;
+      }
+    }
+  }
+  const int pad = (8 - (int)n_bits) & 7;                  // the last byte is padded with zero bits
+  c >>= pad; lc -= pad;
+  while (lc > 0) {
+    const HufDec& pl = dec[(size_t)((c << (kHufDecBits - lc)) & (uint64_t)kHufDecMask)];
+    if (!pl.len || (int)pl.len > lc) return false;
+    lc -= (int)pl.len; if (!emit(pl.lit)) return false;
+  }
+  return o == n_out;
+}
+
+inline void wdec14(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
+  const int hi = (int16_t)h;
+  const int ai = (int16_t)l + (hi & 1) + (hi >> 1);
+  a = (uint16_t)(int16_t)ai; b = (uint16_t)(int16_t)(ai - hi);
+}
+inline void wdec16(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
+  const int m = l, d = h;
+  const int bb = (m - (d >> 1)) & 0xffff;
+  const int aa = (d + bb - 0x8000) & 0xffff;
+  b = (uint16_t)bb; a = (uint16_t)aa;
+}
+// inverse 2-D wavelet on an nx x ny grid of 16-bit values with strides ox, oy; mx = largest value after range compaction
+void wav2_decode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t mx) {
+  const bool w14 = mx < (1 << 14);
+  const int n = nx > ny ? ny : nx;
+  int p = 1, p2;
+  while (p <= n) p <<= 1;
+  p >>= 1; p2 = p; p >>= 1;
+  auto dec = [&](uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) { if (w14) wdec14(l, h, a, b); else wdec16(l, h, a, b); };
+  while (p >= 1) {
+    uint16_t* py = in; uint16_t* ey = in + (ptrdiff_t)oy * (ny - p2);
+    const ptrdiff_t oy1 = (ptrdiff_t)oy * p, oy2 = (ptrdiff_t)oy * p2, ox1 = (ptrdiff_t)ox * p, ox2 = (ptrdiff_t)ox * p2;
+    uint16_t i00, i01, i10, i11;
+    for (; py <= ey; py += oy2) {
+      uint16_t* px = py; uint16_t* ex = py + (ptrdiff_t)ox * (nx - p2);
+      for (; px <= ex; px += ox2) {
+        uint16_t* p01 = px + ox1; uint16_t* p10 = px + oy1; uint16_t* p11 = p10 + ox1;
+        dec(*px, *p10, i00, i10); dec(*p01, *p11, i01, i11);
+        dec(i00, i01, *px, *p01); dec(i10, i11, *p10, *p11);
+      }
+      if (nx & p) { uint16_t* p10 = px + oy1; dec(*px, *p10, i00, *p10); *px = i00; }      // odd column
+    }
+    if (ny & p) {                                                                           // odd line
+      uint16_t* px = py; uint16_t* ex = py + (ptrdiff_t)ox * (nx - p2);
+      for (; px <= ex; px += ox2) { uint16_t* p01 = px + ox1; dec(*px, *p01, i00, *p01); *px = i00; }
+    }
+    p2 = p; p >>= 1;
+  }
+}
+
+// one PIZ chunk -> the same byte layout an uncompressed chunk has (per scan line, per channel, a row of samples)
+bool piz_decode(const uint8_t* src, size_t n_src, const std::vector<Channel>& chans, int64_t W, int64_t lines, std::vector<uint8_t>& raw) {
+  if (n_src < 4) return false;
+  uint16_t min_nz, max_nz; std::memcpy(&min_nz, src, 2); std::memcpy(&max_nz, src + 2, 2);
+  size_t p = 4;
+  std::vector<uint8_t> bitmap(8192, 0);
+  if (max_nz >= 8192) return false;
+  if (min_nz <= max_nz) {
+    const size_t nb = (size_t)max_nz - min_nz + 1;
+    if (p + nb > n_src) return false;
+    std::memcpy(&bitmap[min_nz], src + p, nb); p += nb;
+  }
+  std::vector<uint16_t> lut(65536, 0);
+  int k = 0;
+  for (int i = 0; i < 65536; i++) if (i == 0 || (bitmap[(size_t)i >> 3] & (1 << (i & 7)))) lut[(size_t)k++] = (uint16_t)i;
+  const uint16_t max_value = (uint16_t)(k - 1);
+  if (p + 4 > n_src) return false;
+  int32_t length; std::memcpy(&length, src + p, 4); p += 4;
+  if (length < 0 || p + (size_t)length > n_src) return false;
+  size_t total = 0; std::vector<size_t> start(chans.size()), words(chans.size());
+  for (size_t c = 0; c < chans.size(); c++) { words[c] = chans[c].type == 1 ? 1 : 2; start[c] = total; total += (size_t)W * (size_t)lines * words[c]; }
+  std::vector<uint16_t> tmp;
+  if (!huf_uncompress(src + p, (size_t)length, tmp, total)) return false;
+  for (size_t c = 0; c < chans.size(); c++)
+    for (size_t j = 0; j < words[c]; j++)
+      wav2_decode(&tmp[start[c] + j], (int)W, (int)words[c], (int)lines, (int)((size_t)W * words[c]), max_value);
+  for (uint16_t& v : tmp) v = lut[v];
+  raw.resize(total * 2);
+  uint8_t* o = raw.data(); std::vector<size_t> cur = start;
+  for (int64_t y = 0; y < lines; y++)
+    for (size_t c = 0; c < chans.size(); c++) {
+      const size_t n = (size_t)W * words[c];
+      std::memcpy(o, &tmp[cur[c]], n * 2); o += n * 2; cur[c] += n;
+    }
+  return true;
+}
+
 }  // namespace
 
 bool load_exr(const std::string& path, HDRImageBuffer& img, std::string& err) {
@@ -100,7 +291,7 @@ bool load_exr(const std::string& path, HDRImageBuffer& img, std::string& err) {
   switch (compression) {
     case 0: case 1: case 2: lines_per_chunk = 1; break;
     case 3: lines_per_chunk = 16; break;
-    case 4: err = "PIZ-compressed OpenEXR is not supported: re-save the map with ZIP, ZIPS, RLE or no compression"; return false;
+    case 4: lines_per_chunk = 32; break;
     default: err = "unsupported OpenEXR compression " + std::to_string(compression); return false;
   }
   int ci[3] = {-1, -1, -1};
@@ -131,6 +322,9 @@ bool load_exr(const std::string& path, HDRImageBuffer& img, std::string& err) {
     } else if (compression == 1) {
       if (!rle_decode(src, (size_t)sz, tmp, expect)) { err = "corrupt RLE data in OpenEXR chunk"; return false; }
       unpredict(tmp, raw); px = raw.data();
+    } else if (compression == 4) {
+      if (!piz_decode(src, (size_t)sz, chans, W, lines, raw) || raw.size() != expect) { err = "corrupt PIZ data in OpenEXR chunk"; return false; }
+      px = raw.data();
     } else {
       tmp.resize(expect); uLongf dst_len = (uLongf)expect;
       if (uncompress(tmp.data(), &dst_len, src, (uLong)sz) != Z_OK || dst_len != expect) { err = "corrupt zlib data in OpenEXR chunk"; return false; }

@@ -8,7 +8,7 @@
 namespace dsrt_host {
 
 // Scan-line OpenEXR, single part, channels R, G, B (HALF, FLOAT or UINT; other channels are ignored), compression
-// NONE, RLE, ZIPS or ZIP.  Rows are returned top first, which is the order EnvironmentLight indexes them
+// NONE, RLE, ZIPS, ZIP or PIZ.  Rows are returned top first, which is the order EnvironmentLight indexes them
 // (environment_light.cpp:24-27: row 0 = theta 0 = +y pole).  Kept quirk of the reference's tinyexr: a file whose lineOrder
 // is DECREASING_Y comes out mirrored vertically.
 bool load_exr(const std::string& path, HDRImageBuffer& img, std::string& err);

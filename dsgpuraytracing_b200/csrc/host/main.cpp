@@ -2,7 +2,7 @@
 //   -s <spp>  -l <area-light samples>  -m <max ray depth>  -t <threads, accepted and ignored>  -w <width>  -h <height>
 //   -f <cam_*.info>  -c (CPU render: refused, there is no CPU fallback)  -v (viewer: not part of this port)
 //   -e <environment map>: the reference declares -e but leaves it out of its getopt string (main.cpp:85, 99-101) and
-//      loads .exr through the vendored tinyexr; here -e works and reads scan-line OpenEXR (NONE / RLE / ZIPS / ZIP, host/image_io.cpp)
+//      loads .exr through the vendored tinyexr; here -e works and reads scan-line OpenEXR (NONE / RLE / ZIPS / ZIP / PIZ, host/image_io.cpp)
 //      or a binary .pfm (PF, little endian) lat-long map
 // additions: -g <number of GPUs>  -o <output.png>  -S <seed>  -r <raw float dump of the linear buffer>
 // As in the reference, -h is the frame HEIGHT and the default frame is 1000x1000 (main.cpp:79-80).

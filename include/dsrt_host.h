@@ -33,7 +33,7 @@ int dsrth_render_file(const char* dae_path, const char* cam_info, int32_t width,
                       char* err, int32_t err_len);
 
 /* Environment map of the -e option (reference src/main.cpp:30-67, 99-101: load_exr through tinyexr): scan-line OpenEXR
- * (NONE / RLE / ZIPS / ZIP; R, G, B channels of HALF / FLOAT / UINT) or .pfm.  Call with rgb == NULL to get the size, then
+ * (NONE / RLE / ZIPS / ZIP / PIZ; R, G, B channels of HALF / FLOAT / UINT) or .pfm.  Call with rgb == NULL to get the size, then
  * with a buffer of width*height*3 floats (top row first, the layout dsrt_set_envmap takes). */
 int dsrth_load_envmap(const char* path, int32_t* width, int32_t* height, float* rgb, int64_t rgb_capacity_floats,
                       char* err, int32_t err_len);

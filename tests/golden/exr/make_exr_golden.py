@@ -4,6 +4,7 @@
   * none_*.exr / zips_*.exr come from tests/exr_writer.py;
   * every <name>.npy is what the reference's load_exr path (tinyexr, restated in oracle/exr_ref.cpp) reads back from
     <name>.exr -- the product's reader must reproduce it bit for bit.
+  * piz_*.exr come from the writer's PIZ encoder (range compaction + wavelet + canonical Huffman); tinyexr decodes them;
 RLE is not supported by the reference's tinyexr: rle_half.exr is pinned by the writer's input array instead."""
 import os, subprocess, sys
 import numpy as np
@@ -40,6 +41,21 @@ if __name__ == "__main__":
     write_exr(os.path.join(HERE, "zip_half_decreasing.exr"), {"R": h16[..., 0], "G": h16[..., 1], "B": h16[..., 2]}, "zip", line_order=1)
     write_exr(os.path.join(HERE, "rle_half.exr"), {"R": h16[..., 0], "G": h16[..., 1], "B": h16[..., 2]}, "rle")
     np.save(os.path.join(HERE, "rle_half.npy"), h16.astype(np.float32))
-    for n in ("zip_half", "zip_float", "none_float", "zips_half", "zip_half_decreasing"):
+    # PIZ: quantised images (compress, 14-bit wavelet path) and a ramp of distinct codes (>= 2^14 distinct words: 16-bit path);
+    # the reference's tinyexr does not implement the format's "stored raw when not smaller" rule for PIZ, so both must shrink
+    y, x = np.mgrid[0:45, 0:37]
+    q = np.stack([np.round((0.3 + 0.3 * np.sin(0.2 * x + c) * np.cos(0.13 * y)) * 16) / 16 for c in range(3)], -1).astype(np.float32)
+    q[7, 20] = (1500, 1200, 900)
+    q16 = q.astype(np.float16)
+    write_exr(os.path.join(HERE, "piz_half.exr"), {"R": q16[..., 0], "G": q16[..., 1], "B": q16[..., 2]}, "piz")
+    # 17 280 distinct half codes in one 32-line block: the range table exceeds 2^14 entries -> 16-bit wavelet path
+    codes = (0x0400 + np.arange(32 * 180, dtype=np.uint16).reshape(32, 180))
+    ramp = {"R": codes.view(np.float16), "G": (codes + 5760).view(np.float16), "B": (codes + 11520).view(np.float16)}
+    write_exr(os.path.join(HERE, "piz_half_wide.exr"), ramp, "piz")
+    assert os.path.getsize(os.path.join(HERE, "piz_half_wide.exr")) < 0.9 * 32 * 180 * 6
+    f32 = np.stack([np.round(q[..., c] * 4) / 4 for c in range(3)], -1).astype(np.float32)
+    write_exr(os.path.join(HERE, "piz_float.exr"), {"R": f32[..., 0], "G": f32[..., 1], "B": f32[..., 2]}, "piz")
+    assert os.path.getsize(os.path.join(HERE, "piz_float.exr")) < 0.9 * f32.nbytes
+    for n in ("zip_half", "zip_float", "none_float", "zips_half", "zip_half_decreasing", "piz_half", "piz_float", "piz_half_wide"):
         np.save(os.path.join(HERE, n + ".npy"), ref_load(os.path.join(HERE, n + ".exr")))
     print("wrote", sorted(os.listdir(HERE)))

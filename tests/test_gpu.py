@@ -193,7 +193,7 @@ def test_arbitrary_rays_closest_any_and_fetch_counters(name, core, golden):
     assert abs(int(st.nodes_visited) - int(wc[3])) <= 2e-3 * wc[3]
     assert abs(int(st.prims_tested) - int(wc[4])) <= 2e-3 * wc[4]
     # postponed primitive tests (the default) change the visiting order, never the result
-    core.set_option("postpone_min_lanes", 20)
+    core.set_option("postpone_min_lanes", 12)
     core.set_option("coop_min_pairs", 6)
     rgb2, st2 = core.render()
     core.set_option("count_traversal", 0)
@@ -312,3 +312,13 @@ def test_cli_environment_map_from_exr(tmp_path, core):
     core.set_envmap(None)
     assert np.isfinite(got).all() and got.mean() > 0
     assert np.allclose(got, want, rtol=1e-4, atol=1e-5 * want.mean())
+
+
+def test_read_bandwidth_probe(core):
+    """dsrt_measure_read_bandwidth: the L2-resident sweep must beat the HBM sweep, and both must be plausible for a B200."""
+    l2 = core.measure_read_bandwidth(32 << 20, 20)
+    hbm = core.measure_read_bandwidth(1 << 30, 2)
+    assert 1000.0 < hbm < 9000.0, hbm
+    assert hbm < l2 < 40000.0, (hbm, l2)
+    with pytest.raises(D.DsrtError):
+        core.measure_read_bandwidth(8, 1)

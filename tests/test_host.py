@@ -227,7 +227,7 @@ def test_environment_light_float_pipeline_matches_oracle(name, golden):
 EXR_DIR = os.path.join(ROOT, "tests", "golden", "exr")
 
 
-@pytest.mark.parametrize("name", ["zip_half", "zip_float", "none_float", "zips_half", "zip_half_decreasing", "rle_half"])
+@pytest.mark.parametrize("name", ["zip_half", "zip_float", "none_float", "zips_half", "zip_half_decreasing", "rle_half", "piz_half", "piz_float", "piz_half_wide"])
 def test_exr_reader_matches_reference_tinyexr(name):
     """<name>.npy = what the reference's load_exr (vendored tinyexr) reads from <name>.exr (tests/golden/exr/make_exr_golden.py;
     zip_half / zip_float were also WRITTEN by tinyexr).  rle_half (not supported by that tinyexr) is pinned by the writer's input."""
@@ -255,7 +255,7 @@ def test_exr_reader_extra_channels_offsets_and_errors(tmp_path):
     with open(f, "wb") as fh:
         fh.write(b"PF\n23 19\n-1.0\n" + a[::-1, :, :3].tobytes())
     assert np.array_equal(D.load_envmap(f), a[..., :3])
-    # errors are returned, never exit(): missing file, not an image, truncated, unsupported compression (PIZ = 4), no RGB
+    # errors are returned, never exit(): missing file, not an image, truncated, zlib data labelled PIZ, no RGB
     raw = open(p, "rb").read()
     bad = {"trunc.exr": raw[: len(raw) // 2], "junk.exr": b"hello world, not an image", "piz.exr": raw.replace(b"compression\0compression\0\x01\0\0\0\x03", b"compression\0compression\0\x01\0\0\0\x04")}
     for nm, data in bad.items():
@@ -264,6 +264,11 @@ def test_exr_reader_extra_channels_offsets_and_errors(tmp_path):
             D.load_envmap(fp)
     with pytest.raises(D.DsrtError):
         D.load_envmap(str(tmp_path / "missing.exr"))
+    # PIZ round trip incl. a block the encoder had to store raw (noise does not compress) and odd sizes
+    n = rng.random((33, 17, 3)).astype(np.float16)
+    z = str(tmp_path / "noise_piz.exr")
+    write_exr(z, {"R": n[..., 0], "G": n[..., 1], "B": n[..., 2]}, "piz")
+    assert np.array_equal(D.load_envmap(z), n.astype(np.float32))
     g = str(tmp_path / "grey.exr")
     write_exr(g, {"Y": a[..., 0]}, "none")
     with pytest.raises(D.DsrtError):

@@ -30,6 +30,12 @@
 namespace dsrt {
 
 constexpr int kTraceThreads = 128;        // 4 warps per CTA
+#ifndef DSRT_PRIM_LD
+#define DSRT_PRIM_LD __ldg
+#endif
+#ifndef DSRT_RAY_LD
+#define DSRT_RAY_LD __ldg
+#endif
 #ifndef DSRT_SHADE_MIN_CTAS
 #define DSRT_SHADE_MIN_CTAS 6             // k_shade: 80 registers (unbounded it takes 159 and runs at 12 warps / SM); measured 3: 17.3, 4: 14.3, 5: 13.6, 6: 13.0 ms per 64 spp
 #endif
@@ -37,7 +43,13 @@ constexpr int kTraceThreads = 128;        // 4 warps per CTA
 #define DSRT_TRACE_MIN_CTAS 7             // resident CTAs per SM the traversal kernels are compiled for (register cap 72; measured best of 6, 7, 8)
 #endif
 constexpr int kRayBlock = 17;             // floats per lane published for the cooperative primitive test
-constexpr int kPairCap = 192;             // (ray, primitive) pairs one warp can deal out per round set
+#ifndef DSRT_PAIR_CAP
+#define DSRT_PAIR_CAP 192
+#endif
+#ifndef DSRT_STACK_SLACK
+#define DSRT_STACK_SLACK 1
+#endif
+constexpr int kPairCap = DSRT_PAIR_CAP;             // (ray, primitive) pairs one warp can deal out per round set
 constexpr int kMaxDepthSlots = 64;        // queue-size slots per batch (depth 0..63)
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -183,7 +195,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
       if (ANY) {
         if (hit_out) hit_out[item] = make_float4(hit.t, 0.f, 0.f, __int_as_float(hit.slot));
         if (accum && hit.slot < 0) {       // unoccluded: add this light sample's contribution
-          const float4 c = contrib[item];
+          const float4 c = DSRT_RAY_LD(contrib + item);
           float* px = accum + 3 * (size_t)__float_as_uint(c.w);
           if (c.x != 0.f) atomicAdd(px, c.x);
           if (c.y != 0.f) atomicAdd(px + 1, c.y);
@@ -204,7 +216,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
         const uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
         if (k < n) {
           item = queue ? queue[k] : k;
-          const float4 o = ray_o[item], d = ray_d[item];
+          const float4 o = DSRT_RAY_LD(ray_o + item), d = DSRT_RAY_LD(ray_d + item);
           ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.tmax = o.w;
           ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.src_slot = __float_as_int(d.w);
           fr = make_frame(ray);
@@ -288,19 +300,20 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
                 const uint32_t rb = s_blk_warp + s * 4u;
                 TraceRay r2; WatertightRay w2;
                 r2.ox = ldsf(rb + 0 * kBlkPitch); r2.oy = ldsf(rb + 1 * kBlkPitch); r2.oz = ldsf(rb + 2 * kBlkPitch);
-                r2.dx = ldsf(rb + 3 * kBlkPitch); r2.dy = ldsf(rb + 4 * kBlkPitch); r2.dz = ldsf(rb + 5 * kBlkPitch);
+                r2.dx = r2.dy = r2.dz = 0.f;       // the direction is only needed by the sphere test (loaded there)
                 w2.bxx = ldsf(rb + 6 * kBlkPitch); w2.bxy = ldsf(rb + 7 * kBlkPitch); w2.bxz = ldsf(rb + 8 * kBlkPitch);
                 w2.byx = ldsf(rb + 9 * kBlkPitch); w2.byy = ldsf(rb + 10 * kBlkPitch); w2.byz = ldsf(rb + 11 * kBlkPitch);
                 w2.bzx = ldsf(rb + 12 * kBlkPitch); w2.bzy = ldsf(rb + 13 * kBlkPitch); w2.bzz = ldsf(rb + 14 * kBlkPitch);
                 const float tmax2 = ldsf(rb + 15 * kBlkPitch); const int src2 = (int)lds32(rb + 16 * kBlkPitch);
                 if (COUNT) cnt.prims++;
                 const float4* pp = A.prims + (size_t)slot * 3;
-                const float4 a = __ldg(pp), b = __ldg(pp + 1);
+                const float4 a = DSRT_PRIM_LD(pp), b = DSRT_PRIM_LD(pp + 1);
                 float t, u, v; bool h;
                 if (b.w != 0.0f) {
-                  const float4 cc = __ldg(pp + 2);
+                  const float4 cc = DSRT_PRIM_LD(pp + 2);
                   h = (slot != src2) && hit_triangle(r2, w2, a, b, cc, tmax2, t, u, v);
                 } else {
+                  r2.dx = ldsf(rb + 3 * kBlkPitch); r2.dy = ldsf(rb + 4 * kBlkPitch); r2.dz = ldsf(rb + 5 * kBlkPitch);
                   h = hit_sphere(r2, a, b, slot == src2, true, tmax2, t);
                 }
                 if (h) sts8(s_flag_warp + s, 1u);
@@ -317,10 +330,10 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
             const int slot = (int)(tgroup.x + k);
             if (COUNT) cnt.prims++;
             const float4* pp = A.prims + (size_t)slot * 3;
-            const float4 a = __ldg(pp), b = __ldg(pp + 1);
+            const float4 a = DSRT_PRIM_LD(pp), b = DSRT_PRIM_LD(pp + 1);
             float t, u = 0.f, v = 0.f; bool h;
             if (b.w != 0.0f) {
-              const float4 c = __ldg(pp + 2);
+              const float4 c = DSRT_PRIM_LD(pp + 2);
               // the watertight basis lives in the lane's shared-memory ray block only (9 registers less in the loop)
               const uint32_t rb = s_blk_warp + lane * 4u;
               WatertightRay w2;
@@ -535,6 +548,7 @@ struct DevState {
   std::vector<Span> spans;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   uint32_t launches = 0, batches = 0;
+  int64_t carveout_set = -1;
 };
 
 struct dsrt_ctx {
@@ -554,7 +568,7 @@ struct dsrt_ctx {
   Camera cam{};
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
-  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 12, opt_refill = 18, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_max_ctas = 0;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 12, opt_refill = 18, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_max_ctas = 0, opt_carveout = -1;
   WideBVH wide;
   std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
   int env_w = 0, env_h = 0;
@@ -594,7 +608,7 @@ Accel make_accel(const dsrt_ctx* ctx, const DevState& D, bool parity) {
 }
 
 // shared-memory traversal stack: one node group per wide-BVH level per lane (whatever is not used stays L1 cache)
-int stack_entries(const dsrt_ctx* ctx) { return std::max(ctx->wide.max_depth, 1) + 1; }
+int stack_entries(const dsrt_ctx* ctx) { return std::max(ctx->wide.max_depth, 1) + DSRT_STACK_SLACK; }
 // dynamic shared memory of k_trace: traversal stacks + (any-hit kernel) ray blocks, pair tables, hit flags
 size_t stack_bytes(const dsrt_ctx* ctx) {
   return (size_t)stack_entries(ctx) * kTraceThreads * sizeof(uint2) + (size_t)kRayBlock * kTraceThreads * sizeof(float) +
@@ -603,6 +617,12 @@ size_t stack_bytes(const dsrt_ctx* ctx) {
 
 // persistent grid = resident CTAs per SM (registers / shared-memory stack) x SM count
 int size_trace_grid(dsrt_ctx* ctx, DevState& D) {
+  if (ctx->opt_carveout != D.carveout_set) {      // experiment knob: shared-memory carve-out (percent of the 228 KB maximum)
+    const int pct = (int)ctx->opt_carveout;
+    CK(cudaFuncSetAttribute(k_trace<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    CK(cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    D.carveout_set = ctx->opt_carveout;
+  }
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace<true, false>, kTraceThreads, stack_bytes(ctx)));
   if (ctx->opt_max_ctas > 0) per_sm = std::min(per_sm, (int)ctx->opt_max_ctas);
@@ -830,7 +850,8 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
   else if (n == "postpone_wait_mode") ctx->opt_wait_mode = value;
   else if (n == "pool_batches") ctx->opt_pool_batches = std::max<int64_t>(1, value);
   else if (n == "coop_min_pairs") ctx->opt_coop_min = value;
-  else if (n == "max_ctas_per_sm") ctx->opt_max_ctas = value;          // 0: whatever fits
+  else if (n == "max_ctas_per_sm") ctx->opt_max_ctas = value;
+  else if (n == "smem_carveout_pct") ctx->opt_carveout = value;        // -1: driver default          // 0: whatever fits
   else return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_option: unknown option " + n);
   return DSRT_OK;
 }

@@ -113,7 +113,8 @@ int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t
  * dealt out one per lane; default 6, a huge value disables the cooperative test), "postpone_wait_mode" (0: primitives are
  * tested as soon as one lane has nothing else to do; 1: only when no lane opened a node; K >= 2: when K lanes wait),
  * "refill_busy_lanes" (a warp fetches new rays for its idle lanes when at most this many are busy; default 18),
- * "max_ctas_per_sm" (caps the persistent grid; 0 = what fits), "skip_null_shadow" */
+ * "max_ctas_per_sm" (caps the persistent grid; 0 = what fits), "smem_carveout_pct" (shared-memory carve-out of the
+ * traversal kernels, -1 = driver default, which measured best), "skip_null_shadow" */
 int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value);
 
 /* Host SAH builder = BVHAccel::BVHAccel + buildBVH (src/bvh.cpp:21-202: 32 buckets, max leaf 4, with the

@@ -5,8 +5,7 @@ import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 LIBS = ["libdsrt.so"]
-OPTS = [{}, {"postpone_min_lanes": 0}, {"postpone_min_lanes": 8}, {"postpone_min_lanes": 12}, {"postpone_min_lanes": 16}, {"refill_busy_lanes": 16},
-        {"postpone_min_lanes": 16, "refill_busy_lanes": 16}, {"postpone_min_lanes": 16, "refill_busy_lanes": 18}, {"postpone_min_lanes": 16, "coop_min_pairs": 2}]
+OPTS = [{}, {"smem_carveout_pct": 100}, {"smem_carveout_pct": 86}, {"smem_carveout_pct": 72}, {"smem_carveout_pct": 58}, {"smem_carveout_pct": 44}]
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import numpy as np
@@ -16,7 +15,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     V, F = S.torus_knot(); V = V.astype(np.float32).astype(np.float64)
     sc = S.cb_mesh_scene(V, F); cam = S.cam_dragon(1920, 1080)
     core = D.Core(0); core.set_params(spp, 4, 8, 0); core.load(sc, camera=cam); core.set_option("stage_timing", 1)
-    defaults = {"max_ctas_per_sm": 0, "postpone_min_lanes": 12, "refill_busy_lanes": 18, "coop_min_pairs": 6, "postpone_wait_mode": 0, "pool_batches": 8, "batch_spp": 0}
+    defaults = {"max_ctas_per_sm": 0, "postpone_min_lanes": 12, "refill_busy_lanes": 18, "coop_min_pairs": 6, "postpone_wait_mode": 0, "pool_batches": 8, "batch_spp": 0, "smem_carveout_pct": -1}
     for o in OPTS:
         try:
             for k, v in {**defaults, **o}.items():

@@ -49,7 +49,8 @@ struct Collapse {
   struct DP { double c[8]; uint8_t split[8]; uint8_t kind1; };      // c[i], i = 1..7 roots; split[i] = roots given to the left child
   std::vector<DP> dp;                                                // kind1: 0 leaf, 1 internal wide node
   std::vector<double> c_int; std::vector<uint8_t> split8;
-  static constexpr double c_node = 1.0, c_prim = 1.0;   // measured on B200: flat optimum between 0.6 and 2.5 (primitive tests run at low lane occupancy)
+  static constexpr double c_node = 1.0;
+  double c_prim = 1.0;      // cost of one primitive test relative to one node visit (build_wide_bvh argument)
 
   Collapse(const dsrt_bvh2& b, const std::vector<Box3>& pb) : b2(b), pbox(pb) {}
 
@@ -234,7 +235,7 @@ struct Collapse {
 
 }  // namespace
 
-int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err) {
+int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err, double prim_cost) {
   out.nodes.clear(); out.slot_prim.clear(); out.max_depth = 0;
   if (b2.n_nodes <= 0 || n_prims <= 0) {
     // empty scene: a single node with no children
@@ -246,6 +247,7 @@ int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_pri
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = now();
   Collapse C(b2, pbox);
+  C.c_prim = prim_cost;
   std::vector<BNode>& T = C.T;
   // 1. working copy; leaves of more than one primitive are refined (each leaf's new nodes live in its own block of T)
   T.resize((size_t)b2.n_nodes);

@@ -114,7 +114,9 @@ int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t
  * tested as soon as one lane has nothing else to do; 1: only when no lane opened a node; K >= 2: when K lanes wait),
  * "refill_busy_lanes" (a warp fetches new rays for its idle lanes when at most this many are busy; default 18),
  * "max_ctas_per_sm" (caps the persistent grid; 0 = what fits), "smem_carveout_pct" (shared-memory carve-out of the
- * traversal kernels, -1 = driver default, which measured best), "skip_null_shadow" */
+ * traversal kernels, -1 = driver default, which measured best), "collapse_prim_cost_pct" (SAH cost of a primitive test
+ * relative to a wide-node visit in the collapse, percent; default 100; applies at the next dsrt_build_accel),
+ * "skip_null_shadow" */
 int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value);
 
 /* Host SAH builder = BVHAccel::BVHAccel + buildBVH (src/bvh.cpp:21-202: 32 buckets, max leaf 4, with the

@@ -1,14 +1,6 @@
-// dsrt_api.cu -- the C ABI (include/dsrt.h) and the sm_100a wavefront kernels behind it.
-//
-// Wavefront per batch of camera samples:
-//   k_generate : Camera::generate_ray + pixel jitter                       (pathtracer.cpp:571-577, camera.cpp:113-129)
-//   k_extend   : closest hit, persistent warps + dynamic ray fetch         (bvh.cpp:343-363)
-//   k_shade    : emission, light sampling -> shadow queue, BSDF::sample_f,
-//                Russian roulette -> next extend queue                     (pathtracer.cpp:435-552)
-//   k_connect  : any hit for shadow rays, accumulate unoccluded light      (pathtracer.cpp:501-519, bvh.cpp:331-341)
-//   k_resolve  : 1/ns_aa scale + HDRImageBuffer::toColor                   (pathtracer.cpp:579, image.h:174-189)
-// Queues are appended with warp-aggregated atomics; all queue sizes live in device memory, so a whole frame
-// is enqueued without a host round trip.
+// dsrt_api.cu -- the C ABI (include/dsrt.h): contexts, host copies of the inputs, flattening and upload of the scene, and the
+// launch sequence of the wavefront (render_impl).  The kernels are in kernels.cuh, the traversal / shading device code in
+// traverse.cuh / shade.cuh, the host builders in bvh2_sah.cpp / wide_bvh.cpp.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -21,504 +13,8 @@
 #include <vector>
 
 #include "../../include/dsrt.h"
-#include "layout.h"
-#include "rng.cuh"
-#include "shade.cuh"
-#include "traverse.cuh"
+#include "kernels.cuh"
 #include "wide_bvh.h"
-
-namespace dsrt {
-
-constexpr int kTraceThreads = 128;        // 4 warps per CTA
-#ifndef DSRT_PRIM_LD
-#define DSRT_PRIM_LD __ldg
-#endif
-#ifndef DSRT_RAY_LD
-#define DSRT_RAY_LD __ldg
-#endif
-#ifndef DSRT_SHADE_MIN_CTAS
-#define DSRT_SHADE_MIN_CTAS 6             // k_shade: 80 registers (unbounded it takes 159 and runs at 12 warps / SM); measured 3: 17.3, 4: 14.3, 5: 13.6, 6: 13.0 ms per 64 spp
-#endif
-#ifndef DSRT_TRACE_MIN_CTAS
-#define DSRT_TRACE_MIN_CTAS 7             // resident CTAs per SM the traversal kernels are compiled for (register cap 72; measured best of 6, 7, 8)
-#endif
-constexpr int kRayBlock = 17;             // floats per lane published for the cooperative primitive test
-#ifndef DSRT_PAIR_CAP
-#define DSRT_PAIR_CAP 192
-#endif
-#ifndef DSRT_STACK_SLACK
-#define DSRT_STACK_SLACK 1
-#endif
-constexpr int kPairCap = DSRT_PAIR_CAP;             // (ray, primitive) pairs one warp can deal out per round set
-constexpr int kMaxDepthSlots = 64;        // queue-size slots per batch (depth 0..63)
-constexpr unsigned kFull = 0xffffffffu;
-
-// ------------------------------------------------------------------------------------------------ device state
-struct PathState {
-  float4* ray_o;     // o.xyz, tmax
-  float4* ray_d;     // d.xyz, src_slot (int bits)
-  float4* hit;       // t, u, v, slot (int bits)
-  float4* thr;       // throughput rgb, (depth | includeLe << 8) (int bits)
-  uint32_t* pixel;   // y*W+x
-  uint32_t* sample;  // camera-sample index
-};
-struct ShadowQueue { float4* a; float4* b; float4* c; };   // (o, tmax) (d, src_slot) (contribution rgb, pixel)
-
-struct RenderParams {
-  Camera cam;
-  uint32_t seed;
-  int max_depth;
-  int spp_begin, spp_stride;
-  int batch_first_sample;   // index (within this call) of the first sample of the batch
-  int n_pix_padded, blocks_x;
-  int skip_null_shadow;
-};
-
-struct Counters {             // one block per batch, zeroed with a single memset
-  uint32_t q_count[kMaxDepthSlots];       // extend-queue size per depth
-  uint32_t s_count[kMaxDepthSlots];       // shadow-queue size per depth
-  uint32_t work_extend[kMaxDepthSlots];   // persistent-kernel fetch counters
-  uint32_t work_connect[kMaxDepthSlots];
-};
-// Deep-path pool (depth >= 1): survivors of several batches' depth-0 pass are gathered and advanced together, so the
-// short-queue iterations (a few % of the rays, but latency bound) run once per group of batches instead of once per batch.
-struct PoolCounters {
-  uint32_t q_count[kMaxDepthSlots];       // [0] = paths appended by the depth-0 passes; [i] = survivors entering iteration i
-  uint32_t s_count[kMaxDepthSlots];
-  uint32_t work_extend[kMaxDepthSlots];
-  uint32_t work_connect[kMaxDepthSlots];
-};
-struct Totals { unsigned long long camera, extend, shadow, nodes[2], prims[2]; };   // [0] extend, [1] connect
-
-// ------------------------------------------------------------------------------------------------ kernels
-__global__ void k_generate(PathState ps, RenderParams rp, int n_paths, uint32_t* queue, uint32_t* q_count, int aligned) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_paths) return;
-  if (aligned && i == 0) *q_count = (uint32_t)n_paths;   // identity queue
-  const int s_local = i / rp.n_pix_padded, rank = i - s_local * rp.n_pix_padded;
-  const int blk = rank >> 5, lane = rank & 31;
-  const int bx = blk % rp.blocks_x, by = blk / rp.blocks_x;
-  const int x = bx * 8 + (lane & 7), y = by * 4 + (lane >> 3);
-  const bool valid = x < rp.cam.width && y < rp.cam.height;
-  if (valid) {
-    const uint32_t pix = (uint32_t)(y * rp.cam.width + x);
-    const uint32_t smp = (uint32_t)(rp.spp_begin + (rp.batch_first_sample + s_local) * rp.spp_stride);
-    const float4 u = rng_block(rp.seed, pix, smp, 0u, kBlockCamera);
-    V3 o, d;
-    generate_ray(rp.cam, ((float)x + u.x) / (float)rp.cam.width, ((float)y + u.y) / (float)rp.cam.height, &o, &d);
-    ps.ray_o[i] = make_float4(o.x, o.y, o.z, kInfF);
-    ps.ray_d[i] = make_float4(d.x, d.y, d.z, __int_as_float(-1));
-    ps.thr[i] = make_float4(1.f, 1.f, 1.f, __int_as_float(0 | (1 << 8)));
-    ps.pixel[i] = pix;
-    ps.sample[i] = smp;
-  }
-  if (!aligned) {   // ragged frame: compact the valid paths into the depth-0 queue
-    const unsigned m = __ballot_sync(__activemask(), valid);
-    if (valid) {
-      const int lane_id = threadIdx.x & 31;
-      const int leader = __ffs(m) - 1;
-      uint32_t base = 0;
-      if (lane_id == leader) base = atomicAdd(q_count, (uint32_t)__popc(m));
-      base = __shfl_sync(m, base, leader);
-      queue[base + __popc(m & ((1u << lane_id) - 1u))] = (uint32_t)i;
-    }
-  }
-}
-
-// pixel-centre camera rays for dsrt_primary_hits(mode 0)
-__global__ void k_generate_centres(PathState ps, RenderParams rp, int n_paths) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_paths) return;
-  const int x = i % rp.cam.width, y = i / rp.cam.width;
-  V3 o, d;
-  generate_ray(rp.cam, ((float)x + 0.5f) / (float)rp.cam.width, ((float)y + 0.5f) / (float)rp.cam.height, &o, &d);
-  ps.ray_o[i] = make_float4(o.x, o.y, o.z, kInfF);
-  ps.ray_d[i] = make_float4(d.x, d.y, d.z, __int_as_float(-1));
-}
-
-// Persistent warps, one ray per lane.
-//  * dynamic fetch: a lane whose ray has finished idles until at most `refill_busy` lanes of its warp are still
-//    busy, then the warp fetches new rays for ALL idle lanes with one aggregated atomic (ballot + popc + shfl);
-//  * postponed primitive tests: a node visit leaves each lane with a group of pending primitives.  Testing them
-//    at once would run the (long) primitive test with the few lanes that happen to have reached a leaf.  Instead
-//    a lane keeps its pending group (older groups go onto the stack) and the WARP tests primitives only when at
-//    least `tri_min` lanes have some pending, or when a lane has nothing else left to do -- so the primitive test
-//    executes with many lanes active.  tri_min = 0 restores test-at-once order (used by the counter tests).
-
-// shared-memory accesses of k_trace by 32-bit shared-window address (no generic-address arithmetic in the hot loop)
-__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
-__device__ __forceinline__ void sts64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(a), "r"(v.x), "r"(v.y)); }
-__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ float ldsf(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)); }
-__device__ __forceinline__ void stsf(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v)); }
-__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v)); }
-
-constexpr uint32_t kStackPitch = kTraceThreads * 8;     // bytes between consecutive stack entries of one lane
-constexpr uint32_t kBlkPitch = kTraceThreads * 4;       // bytes between consecutive values of one lane's ray block
-constexpr int kOwnerShift = 27;                         // pair word = slot | owner lane << 27 (slots < 2^27)
-
-template <bool ANY, bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Accel A, const float4* __restrict__ ray_o, const float4* __restrict__ ray_d,
-                                                         const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
-                                                         uint32_t* work, float4* hit_out, const float4* __restrict__ contrib,
-                                                         float* accum, Totals* totals, int tri_min, int refill_busy, int wait_mode,
-                                                         int stack_entries, int coop_min) {
-  extern __shared__ uint2 smem_stack[];
-  const int lane = threadIdx.x & 31;
-  // shared memory: [stacks: entry-major, 8 B per lane -> conflict free][any-hit kernel only: per-lane ray blocks (kRayBlock
-  // floats, value-major so that lanes reading different owners hit different banks) | per-warp pair words | hit flags]
-  const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(smem_stack);
-  const uint32_t s_stack = s_base + threadIdx.x * 8u;                                      // entry e at s_stack + e * kStackPitch
-  const uint32_t s_blk0 = s_base + (uint32_t)stack_entries * kStackPitch;                   // ray blocks of the CTA
-  const uint32_t s_blk_warp = s_blk0 + (threadIdx.x & ~31u) * 4u;                           // ... of this warp's lane 0
-  const uint32_t s_pair = s_blk0 + kRayBlock * kBlkPitch + (threadIdx.x >> 5) * (kPairCap * 4u);
-  const uint32_t s_flag_warp = s_blk0 + kRayBlock * kBlkPitch + (kTraceThreads / 32) * (kPairCap * 4u) + (threadIdx.x & ~31u);
-  const uint32_t n = *n_ptr;
-  TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
-
-  // per-lane traversal state (kept across refills)
-  bool busy = false, exhausted = false;
-  uint32_t item = 0;
-  TraceRay ray; NodeFrame fr;
-  float tbest = 0.f; TraceHit hit;
-  uint32_t spa = s_stack;                          // address of the first free stack entry (== s_stack: empty)
-  uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
-  hit.slot = -1; hit.t = 0.f; hit.u = 0.f; hit.v = 0.f;
-
-  bool fin = false;                                // ray finished, result not written yet
-  while (true) {
-    // ---- write the results of the rays that finished since the last refill (together: more lanes per store / atomic)
-    if (fin) {
-      fin = false;
-      if (ANY) {
-        if (hit_out) hit_out[item] = make_float4(hit.t, 0.f, 0.f, __int_as_float(hit.slot));
-        if (accum && hit.slot < 0) {       // unoccluded: add this light sample's contribution
-          const float4 c = DSRT_RAY_LD(contrib + item);
-          float* px = accum + 3 * (size_t)__float_as_uint(c.w);
-          if (c.x != 0.f) atomicAdd(px, c.x);
-          if (c.y != 0.f) atomicAdd(px + 1, c.y);
-          if (c.z != 0.f) atomicAdd(px + 2, c.z);
-        }
-      } else {
-        hit_out[item] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.slot));
-      }
-    }
-    // ---- refill idle lanes
-    const unsigned idle = __ballot_sync(kFull, !busy);
-    if (idle && !exhausted) {
-      uint32_t base = 0;
-      const int leader = __ffs(idle) - 1;
-      if (lane == leader) base = atomicAdd(work, (uint32_t)__popc(idle));
-      base = __shfl_sync(kFull, base, leader);
-      if (!busy) {
-        const uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
-        if (k < n) {
-          item = queue ? queue[k] : k;
-          const float4 o = DSRT_RAY_LD(ray_o + item), d = DSRT_RAY_LD(ray_d + item);
-          ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.tmax = o.w;
-          ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.src_slot = __float_as_int(d.w);
-          fr = make_frame(ray);
-          const WatertightRay wr = make_watertight(ray);
-          tbest = ray.tmax; hit.slot = -1; hit.t = ray.tmax; hit.u = 0.f; hit.v = 0.f;
-          spa = s_stack; ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
-          busy = true;
-          const uint32_t rb = s_blk_warp + lane * 4u;
-          if (ANY) {
-            stsf(rb + 0 * kBlkPitch, ray.ox); stsf(rb + 1 * kBlkPitch, ray.oy); stsf(rb + 2 * kBlkPitch, ray.oz);
-            stsf(rb + 3 * kBlkPitch, ray.dx); stsf(rb + 4 * kBlkPitch, ray.dy); stsf(rb + 5 * kBlkPitch, ray.dz);
-            stsf(rb + 15 * kBlkPitch, ray.tmax); sts32(rb + 16 * kBlkPitch, (uint32_t)ray.src_slot);
-            sts8(s_flag_warp + lane, 0u);
-          }
-          {
-            stsf(rb + 6 * kBlkPitch, wr.bxx); stsf(rb + 7 * kBlkPitch, wr.bxy); stsf(rb + 8 * kBlkPitch, wr.bxz);
-            stsf(rb + 9 * kBlkPitch, wr.byx); stsf(rb + 10 * kBlkPitch, wr.byy); stsf(rb + 11 * kBlkPitch, wr.byz);
-            stsf(rb + 12 * kBlkPitch, wr.bzx); stsf(rb + 13 * kBlkPitch, wr.bzy); stsf(rb + 14 * kBlkPitch, wr.bzz);
-          }
-        }
-      }
-      if (base + (uint32_t)__popc(idle) >= n) exhausted = true;
-    }
-    if (!__any_sync(kFull, busy)) break;
-
-    // ---- traverse until the warp is due for a refill
-    while (true) {
-      bool done = false, did_node = false;
-      // (1) node step: open the highest-priority pending internal child, or take the next node group off the stack (at
-      // most one group per tree level).  A lane that still holds an untested primitive group waits for the warp's next test
-      // (parking such groups on the stack was measured: 2-3 % slower than this simpler loop).
-      if (busy && tgroup.y == 0u) {
-        if (ngroup.y <= 0x00ffffffu && spa != s_stack) { spa -= kStackPitch; ngroup = lds64(spa); }
-        if (ngroup.y > 0x00ffffffu) {
-          const uint32_t bit = 31u - (uint32_t)__clz(ngroup.y);
-          ngroup.y &= ~(1u << bit);
-          if (ngroup.y > 0x00ffffffu) { sts64(spa, ngroup); spa += kStackPitch; }
-          const uint32_t slot = (bit - 24u) ^ fr.octinv;
-          const uint32_t rel = __popc(ngroup.y & 0xffu & ((1u << slot) - 1u));
-          const uint4* np = A.nodes + (size_t)(ngroup.x + rel) * 5;
-          const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-          if (COUNT) cnt.nodes++;
-          const uint32_t m = test_children<false>(ray, fr, n0, n1, n2, n3, n4, tbest, 0.f, A.one_bits);
-          ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
-          tgroup = make_uint2(n1.y, m & 0x00ffffffu);
-          did_node = true;
-        }
-      }
-      // (2) primitive step, warp-wide decision
-      const bool pending = busy && tgroup.y != 0u;
-      const bool must = pending && !did_node;                          // this lane had no node to open: it needs its primitives now
-      const unsigned pm = __ballot_sync(kFull, pending);
-      // wait_mode 0: test as soon as ANY lane must; 1: only when no lane opened a node; K >= 2: when K lanes must (or no lane
-      // opened a node, so the warp always makes progress)
-      const bool trigger = wait_mode == 0 ? __any_sync(kFull, must)
-                         : (wait_mode == 1 ? !__any_sync(kFull, did_node)
-                                           : (__popc(__ballot_sync(kFull, must)) >= wait_mode || !__any_sync(kFull, did_node)));
-      if (pm && (trigger || __popc(pm) >= tri_min)) {
-        bool coop = false;
-        if (ANY) {
-          // Cooperative test: the pending (ray, primitive) pairs of the whole warp are dealt out one per lane, so the
-          // long watertight test runs with up to 32 lanes instead of the handful that happen to hold a group.
-          const int c = pending ? __popc(tgroup.y) : 0;
-          int incl = c;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
-          const int P = __shfl_sync(kFull, incl, 31);
-          if (P >= coop_min && P <= kPairCap) {
-            coop = true;
-            uint32_t pa = s_pair + (uint32_t)(incl - c) * 4u;
-            uint32_t m = pending ? tgroup.y : 0u;
-            const uint32_t tag = tgroup.x | ((uint32_t)lane << kOwnerShift);
-            while (m) { const uint32_t k = 31u - (uint32_t)__clz(m); m &= ~(1u << k); sts32(pa, tag + k); pa += 4u; }
-            if (pending) tgroup.y = 0u;
-            __syncwarp();
-            for (int base = 0; base < P; base += 32) {
-              const int j = base + lane;
-              if (j < P) {
-                const uint32_t pw = lds32(s_pair + (uint32_t)j * 4u);
-                const int slot = (int)(pw & ((1u << kOwnerShift) - 1u)); const uint32_t s = pw >> kOwnerShift;
-                const uint32_t rb = s_blk_warp + s * 4u;
-                TraceRay r2; WatertightRay w2;
-                r2.ox = ldsf(rb + 0 * kBlkPitch); r2.oy = ldsf(rb + 1 * kBlkPitch); r2.oz = ldsf(rb + 2 * kBlkPitch);
-                r2.dx = r2.dy = r2.dz = 0.f;       // the direction is only needed by the sphere test (loaded there)
-                w2.bxx = ldsf(rb + 6 * kBlkPitch); w2.bxy = ldsf(rb + 7 * kBlkPitch); w2.bxz = ldsf(rb + 8 * kBlkPitch);
-                w2.byx = ldsf(rb + 9 * kBlkPitch); w2.byy = ldsf(rb + 10 * kBlkPitch); w2.byz = ldsf(rb + 11 * kBlkPitch);
-                w2.bzx = ldsf(rb + 12 * kBlkPitch); w2.bzy = ldsf(rb + 13 * kBlkPitch); w2.bzz = ldsf(rb + 14 * kBlkPitch);
-                const float tmax2 = ldsf(rb + 15 * kBlkPitch); const int src2 = (int)lds32(rb + 16 * kBlkPitch);
-                if (COUNT) cnt.prims++;
-                const float4* pp = A.prims + (size_t)slot * 3;
-                const float4 a = DSRT_PRIM_LD(pp), b = DSRT_PRIM_LD(pp + 1);
-                float t, u, v; bool h;
-                if (b.w != 0.0f) {
-                  const float4 cc = DSRT_PRIM_LD(pp + 2);
-                  h = (slot != src2) && hit_triangle(r2, w2, a, b, cc, tmax2, t, u, v);
-                } else {
-                  r2.dx = ldsf(rb + 3 * kBlkPitch); r2.dy = ldsf(rb + 4 * kBlkPitch); r2.dz = ldsf(rb + 5 * kBlkPitch);
-                  h = hit_sphere(r2, a, b, slot == src2, true, tmax2, t);
-                }
-                if (h) sts8(s_flag_warp + s, 1u);
-              }
-            }
-            __syncwarp();
-            if (pending && lds8(s_flag_warp + lane)) { hit.slot = 0; hit.t = 0.f; done = true; }
-          }
-        }
-        if (!coop) {
-          while (pending && tgroup.y) {
-            const uint32_t k = 31u - (uint32_t)__clz(tgroup.y);
-            tgroup.y &= ~(1u << k);
-            const int slot = (int)(tgroup.x + k);
-            if (COUNT) cnt.prims++;
-            const float4* pp = A.prims + (size_t)slot * 3;
-            const float4 a = DSRT_PRIM_LD(pp), b = DSRT_PRIM_LD(pp + 1);
-            float t, u = 0.f, v = 0.f; bool h;
-            if (b.w != 0.0f) {
-              const float4 c = DSRT_PRIM_LD(pp + 2);
-              // the watertight basis lives in the lane's shared-memory ray block only (9 registers less in the loop)
-              const uint32_t rb = s_blk_warp + lane * 4u;
-              WatertightRay w2;
-              w2.bxx = ldsf(rb + 6 * kBlkPitch); w2.bxy = ldsf(rb + 7 * kBlkPitch); w2.bxz = ldsf(rb + 8 * kBlkPitch);
-              w2.byx = ldsf(rb + 9 * kBlkPitch); w2.byy = ldsf(rb + 10 * kBlkPitch); w2.byz = ldsf(rb + 11 * kBlkPitch);
-              w2.bzx = ldsf(rb + 12 * kBlkPitch); w2.bzy = ldsf(rb + 13 * kBlkPitch); w2.bzz = ldsf(rb + 14 * kBlkPitch);
-              h = (slot != ray.src_slot) && hit_triangle(ray, w2, a, b, c, tbest, t, u, v);
-            } else {
-              h = hit_sphere(ray, a, b, slot == ray.src_slot, ANY, tbest, t);
-            }
-            if (h) {
-              tbest = t; hit.slot = slot; hit.t = t; hit.u = u; hit.v = v;
-              if (ANY) { done = true; break; }
-            }
-          }
-        }
-      }
-      // (3) retire finished rays (their results are written at the next refill)
-      if (busy) {
-        if (!done && ngroup.y <= 0x00ffffffu && spa == s_stack && tgroup.y == 0u) done = true;
-        if (done) { busy = false; fin = true; tgroup.y = 0u; ngroup.y = 0u; spa = s_stack; }
-      }
-      const int nbusy = __popc(__ballot_sync(kFull, busy));
-      if (nbusy == 0 || (!exhausted && nbusy <= refill_busy)) break;
-    }
-  }
-  if (COUNT) {
-    unsigned long long a = cnt.nodes, b = cnt.prims;
-    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(kFull, a, o); b += __shfl_xor_sync(kFull, b, o); }
-    if (lane == 0) { atomicAdd(&totals->nodes[ANY ? 1 : 0], a); atomicAdd(&totals->prims[ANY ? 1 : 0], b); }
-  }
-}
-
-// parity kernel: one thread per pixel, double-precision rays supplied by the host (bit-identical to the
-// reference's Camera::generate_ray), production traversal with conservative slabs + fp64 leaf tests
-__global__ void __launch_bounds__(kTraceThreads) k_primary_parity(Accel A, const double* __restrict__ rays, int n, int32_t* slot_out,
-                                                                  double* t_out) {
-  extern __shared__ uint2 smem_stack[];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Ray64 r64; r64.ox = rays[6 * i]; r64.oy = rays[6 * i + 1]; r64.oz = rays[6 * i + 2];
-  r64.dx = rays[6 * i + 3]; r64.dy = rays[6 * i + 4]; r64.dz = rays[6 * i + 5];
-  TraceRay r; r.ox = (float)r64.ox; r.oy = (float)r64.oy; r.oz = (float)r64.oz;
-  r.dx = (float)r64.dx; r.dy = (float)r64.dy; r.dz = (float)r64.dz; r.tmax = kInfF; r.src_slot = -1;
-  TraceHit hit; double t64 = 0;
-  trace_ray<false, true, false>(A, r, &r64, smem_stack + threadIdx.x, blockDim.x, hit, &t64, nullptr);
-  slot_out[i] = hit.slot;
-  t_out[i] = hit.slot >= 0 ? t64 : (double)kInfF;
-}
-
-__device__ __forceinline__ void add_rgb(float* accum, uint32_t pix, V3 c) {
-  float* px = accum + 3 * (size_t)pix;
-  if (c.x != 0.f) atomicAdd(px, c.x);
-  if (c.y != 0.f) atomicAdd(px + 1, c.y);
-  if (c.z != 0.f) atomicAdd(px + 2, c.z);
-}
-
-// One thread per queued path: PathTracer::trace_ray after the closest-hit query (shade_path, shade.cuh)
-struct QueueSink {
-  ShadowQueue sq; uint32_t base; int nh, rank;
-  __device__ __forceinline__ void shadow(int j, float4 a, float4 b, float4 c) {
-    const uint32_t e = base + (uint32_t)(j * nh + rank);     // sample-major within the warp's block
-    sq.a[e] = a; sq.b[e] = b; sq.c[e] = c;
-  }
-};
-
-// dst == ps (in place): survivors keep their slot and are appended to next_queue (pool iterations).
-// dst != ps: survivors are COPIED into dst at an appended index (depth-0 pass of a batch -> the deep-path pool).
-__global__ void __launch_bounds__(128, DSRT_SHADE_MIN_CTAS) k_shade(PathState ps, const float4* __restrict__ prims, SceneDev sc, RenderParams rp,
-                                               const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
-                                               PathState dst, uint32_t* next_queue, uint32_t* next_count, uint32_t dst_cap,
-                                               ShadowQueue sq, uint32_t* s_count, float* accum) {
-  const uint32_t n = *n_ptr;
-  const int lane = threadIdx.x & 31;
-  const bool in_place = dst.ray_o == ps.ray_o;
-  for (uint32_t kb = blockIdx.x * blockDim.x; kb < n; kb += gridDim.x * blockDim.x) {
-    const uint32_t k = kb + threadIdx.x;
-    const bool live = k < n;
-    uint32_t p = 0;
-    PathIn in; in.hit = make_float4(0, 0, 0, __int_as_float(-1));
-    if (live) { p = queue ? queue[k] : k; in.hit = ps.hit[p]; }
-    const bool hitp = live && __float_as_int(in.hit.w) >= 0;
-    const unsigned hm = __ballot_sync(kFull, hitp);
-    QueueSink sink; sink.sq = sq; sink.base = 0; sink.nh = __popc(hm); sink.rank = __popc(hm & ((1u << lane) - 1u));
-    if (hm && sc.n_light_samples > 0) {
-      const int leader = __ffs(hm) - 1;
-      if (lane == leader) sink.base = atomicAdd(s_count, (uint32_t)(sink.nh * sc.n_light_samples));
-      sink.base = __shfl_sync(kFull, sink.base, leader);
-    }
-    PathOut out; out.cont = false;
-    if (live && !hitp && sc.env.w > 0) {                      // miss: envLight->sample_dir(r) if includeLe (pathtracer.cpp:421-423)
-      const float4 t4 = ps.thr[p];
-      if ((__float_as_int(t4.w) >> 8) & 1) {
-        const float4 d4 = ps.ray_d[p];
-        add_rgb(accum, ps.pixel[p], v3(t4.x, t4.y, t4.z) * env_sample_dir(sc.env, v3(d4.x, d4.y, d4.z)));
-      }
-    }
-    if (hitp) {
-      in.ray_o = ps.ray_o[p]; in.ray_d = ps.ray_d[p]; in.thr = ps.thr[p]; in.pix = ps.pixel[p]; in.smp = ps.sample[p];
-      const int depth = __float_as_int(in.thr.w) & 0xff;       // Ray::depth travels with the path
-      shade_path(in, prims, sc, rp.seed, rp.max_depth, depth, out, sink);
-      if (out.has_emission) add_rgb(accum, in.pix, out.emission);
-    }
-    const unsigned cm = __ballot_sync(kFull, out.cont);
-    if (cm) {
-      uint32_t base = 0;
-      const int leader = __ffs(cm) - 1;
-      if (lane == leader) base = atomicAdd(next_count, (uint32_t)__popc(cm));
-      base = __shfl_sync(kFull, base, leader);
-      if (out.cont) {
-        const uint32_t idx = base + __popc(cm & ((1u << lane) - 1u));
-        if (in_place) {
-          next_queue[idx] = p;
-          ps.ray_o[p] = out.new_o; ps.ray_d[p] = out.new_d; ps.thr[p] = out.new_thr;
-        } else if (idx < dst_cap) {
-          dst.ray_o[idx] = out.new_o; dst.ray_d[idx] = out.new_d; dst.thr[idx] = out.new_thr;
-          dst.pixel[idx] = in.pix; dst.sample[idx] = in.smp;
-        }
-      }
-    }
-  }
-}
-
-__global__ void k_tally(const Counters* c, Totals* t, uint32_t camera) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    t->camera += camera; t->extend += c->q_count[0]; t->shadow += c->s_count[0];   // depth 0 of one batch
-  }
-}
-__global__ void k_tally_pool(const PoolCounters* c, Totals* t, int iterations) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    unsigned long long e = 0, s = 0;
-    for (int d = 0; d < iterations; d++) { e += c->q_count[d]; s += c->s_count[d]; }
-    t->extend += e; t->shadow += s;
-  }
-}
-__global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
-
-// sampleBuffer = accum / ns_aa (pathtracer.cpp:579); optional toColor (image.h:174-189, 49-58)
-__global__ void k_resolve(const float* __restrict__ accum, float* rgb, uint32_t* rgba8, int n_pix, float inv_spp) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pix) return;
-  const float r = accum[3 * i] * inv_spp, g = accum[3 * i + 1] * inv_spp, b = accum[3 * i + 2] * inv_spp;
-  if (rgb) { rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b; }
-  if (rgba8) {
-    const float exposure = sqrtf(2.0f), og = 1.0f / 2.2f;
-    const float cr = fminf(1.0f, powf(r * exposure, og)), cg = fminf(1.0f, powf(g * exposure, og)), cb = fminf(1.0f, powf(b * exposure, og));
-    rgba8[i] = (uint32_t)(cr * 255.f) | ((uint32_t)(cg * 255.f) << 8) | ((uint32_t)(cb * 255.f) << 16) | (255u << 24);
-  }
-}
-
-// Fused reduce + resolve for the single-process multi-GPU path: device 0 reads every GPU's partial radiance sums
-// straight from peer memory over NVLink (P2P loads; staged copies when peer access is unavailable), adds them,
-// scales by 1/ns_aa and tone-maps -- one kernel, no separate collective pass.
-struct PeerPtrs { const float* p[16]; int n; };
-__global__ void k_resolve_peers(PeerPtrs src, float* rgb, uint32_t* rgba8, int n_pix, float inv_spp) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pix) return;
-  float r = 0.f, g = 0.f, b = 0.f;
-  for (int k = 0; k < src.n; k++) { const float* a = src.p[k]; r += a[3 * i]; g += a[3 * i + 1]; b += a[3 * i + 2]; }
-  r *= inv_spp; g *= inv_spp; b *= inv_spp;
-  if (rgb) { rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b; }
-  if (rgba8) {
-    const float exposure = sqrtf(2.0f), og = 1.0f / 2.2f;
-    const float cr = fminf(1.0f, powf(r * exposure, og)), cg = fminf(1.0f, powf(g * exposure, og)), cb = fminf(1.0f, powf(b * exposure, og));
-    rgba8[i] = (uint32_t)(cr * 255.f) | ((uint32_t)(cg * 255.f) << 8) | ((uint32_t)(cb * 255.f) << 16) | (255u << 24);
-  }
-}
-
-// read-bandwidth probe: every CTA sweeps the whole buffer (grid-stride over 128-bit words), `repeats` times
-__global__ void __launch_bounds__(256) k_read_sweep(const uint4* __restrict__ buf, size_t n_vec, int repeats, uint32_t* sink) {
-  uint32_t acc = 0;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (int r = 0; r < repeats; r++) {
-    // rotate the starting offset per repeat so that a CTA does not re-read the lines its own L1 just cached
-    const size_t rot = ((size_t)r * 977u * blockDim.x) % n_vec;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
-      size_t j = i + rot; if (j >= n_vec) j -= n_vec;
-      const uint4 v = __ldcg(buf + j);            // cache-global: L2 only, bypasses L1
-      acc ^= v.x ^ v.y ^ v.z ^ v.w;
-    }
-  }
-  if (acc == 0x9e3779b9u) *sink = acc;             // keeps the loads alive
-}
-
-}  // namespace dsrt
 
 // ================================================================================================ host side
 using namespace dsrt;

@@ -28,7 +28,7 @@ constexpr int kTraceThreads = 128;        // 4 warps per CTA
 #define DSRT_RAY_LD __ldg
 #endif
 #ifndef DSRT_SHADE_MIN_CTAS
-#define DSRT_SHADE_MIN_CTAS 6             // k_shade: 80 registers (unbounded it takes 159 and runs at 12 warps / SM); measured 3: 17.3, 4: 14.3, 5: 13.6, 6: 13.0 ms per 64 spp
+#define DSRT_SHADE_MIN_CTAS 8             // k_shade: 64 registers (unbounded it takes 159 and runs at 12 warps / SM); shade stage per 64 spp, ms: 3 CTAs 17.3, 4: 14.3, 6: 12.6, 8: 11.7, 10: 13.0, 12: 15.1
 #endif
 #ifndef DSRT_TRACE_MIN_CTAS
 #define DSRT_TRACE_MIN_CTAS 7             // resident CTAs per SM the traversal kernels are compiled for (register cap 72; measured best of 6, 7, 8)

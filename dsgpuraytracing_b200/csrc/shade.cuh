@@ -243,7 +243,7 @@ DSRT_HD void shade_path(const PathIn& in, const float4* __restrict__ prims, cons
   // direct lighting: one shadow ray per light sample (pathtracer.cpp:469-523)
   const V3 f_direct = bsdf_f(bs);
   for (int l = 0; l < sc.n_lights; l++) {
-    const Light L = sc.lights[l];
+    const Light& L = sc.lights[l];
     const float scale = 1.0f / (float)L.n_samples;
     for (int i = 0; i < L.n_samples; i++) {
       const int j = L.sample_base + i;

@@ -5,7 +5,7 @@ import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 LIBS = ["libdsrt.so"]
-OPTS = [{}, {"smem_carveout_pct": 100}, {"smem_carveout_pct": 86}, {"smem_carveout_pct": 72}, {"smem_carveout_pct": 58}, {"smem_carveout_pct": 44}]
+OPTS = [{}, {}]
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import numpy as np

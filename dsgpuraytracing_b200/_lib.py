@@ -276,7 +276,7 @@ class Core:
 
 
 # ---- host side (libdsrt_host.so): COLLADA import + the PathTracer mirror -------------------------------------------
-HOST_EXPORTED_SYMBOLS = ["dsrth_load_dae", "dsrth_free", "dsrth_get_scene", "dsrth_get_camera", "dsrth_render_file", "dsrth_load_envmap"]
+HOST_EXPORTED_SYMBOLS = ["dsrth_load_dae", "dsrth_free", "dsrth_get_scene", "dsrth_get_camera", "dsrth_render_file", "dsrth_load_envmap", "dsrth_set_loader_option"]
 _hostlib = None
 
 
@@ -319,6 +319,12 @@ def load_dae(path, width, height, cam_info=None):
         return out, cam
     finally:
         H.dsrth_free(h)
+
+
+def set_loader_option(name, value):
+    """Host loader options (dsrth_set_loader_option), e.g. ("direct_triangles", 1)."""
+    if load_host_library().dsrth_set_loader_option(name.encode(), int(value)):
+        raise DsrtError(f"unknown loader option {name}")
 
 
 def load_envmap(path):

@@ -71,6 +71,12 @@ int dsrth_render_file(const char* dae_path, const char* cam_info, int32_t width,
   return DSRT_OK;
 }
 
+int dsrth_set_loader_option(const char* name, int32_t value) {
+  if (!name) return DSRT_ERR_INVALID;
+  if (std::string(name) == "direct_triangles") { set_direct_triangle_fallback(value != 0); return DSRT_OK; }
+  return DSRT_ERR_INVALID;
+}
+
 int dsrth_load_envmap(const char* path, int32_t* width, int32_t* height, float* rgb, int64_t cap, char* err, int32_t err_len) {
   if (!path || !width || !height) { set_err(err, err_len, "bad arguments"); return DSRT_ERR_INVALID; }
   HDRImageBuffer img; std::string e;

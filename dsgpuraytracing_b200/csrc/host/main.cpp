@@ -5,6 +5,7 @@
 //      loads .exr through the vendored tinyexr; here -e works and reads scan-line OpenEXR (NONE / RLE / ZIPS / ZIP / PIZ, host/image_io.cpp)
 //      or a binary .pfm (PF, little endian) lat-long map
 // additions: -g <number of GPUs>  -o <output.png>  -S <seed>  -r <raw float dump of the linear buffer>
+//            -T tolerate non-manifold meshes (direct indexed-triangle import; the reference exit(1)s on them)
 // As in the reference, -h is the frame HEIGHT and the default frame is 1000x1000 (main.cpp:79-80).
 #include <unistd.h>
 
@@ -25,6 +26,7 @@ static void usage(const char* bin) {
   printf("  -w <INT>  frame width (default 1000)\n  -h <INT>  frame height (default 1000)\n  -f <FILE> camera .info file\n");
   printf("  -g <INT>  number of GPUs (default 1)\n  -o <FILE> output PNG (default \"Screen Shot GPU <time>.png\")\n");
   printf("  -e <FILE> lat-long environment map (.exr or .pfm)\n");
+  printf("  -T        import meshes the half-edge builder rejects (non-manifold ...) as plain indexed triangles\n");
   printf("  -S <INT>  Philox seed (default 0)\n  -r <FILE> also dump the linear float RGB buffer\n");
 }
 
@@ -35,7 +37,7 @@ int main(int argc, char** argv) {
   bool useCPU = false;
   std::string camFileName, outName, rawName, envName;
   int opt;
-  while ((opt = getopt(argc, argv, "s:l:t:m:f:w:h:g:o:S:r:e:vc")) != -1) {
+  while ((opt = getopt(argc, argv, "s:l:t:m:f:w:h:g:o:S:r:e:vcT")) != -1) {
     switch (opt) {
       case 's': ns_aa = (size_t)atoi(optarg); break;
       case 'l': ns_area_light = (size_t)atoi(optarg); break;
@@ -50,6 +52,7 @@ int main(int argc, char** argv) {
       case 'r': rawName = optarg; break;
       case 'e': envName = optarg; break;
       case 'c': useCPU = true; break;
+      case 'T': set_direct_triangle_fallback(true); break;
       case 'v': fprintf(stderr, "the interactive viewer is not part of this port\n"); return 1;
       default: usage(argv[0]); return 1;
     }

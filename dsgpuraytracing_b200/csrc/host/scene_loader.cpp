@@ -4,6 +4,7 @@
 #include "scene_loader.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -492,6 +493,8 @@ void box_grow(double lo[3], double hi[3], V3 p) {
 
 }  // namespace
 
+bool g_direct_triangles_storage = false;
+
 // ---- Camera --------------------------------------------------------------------------------------------------------
 void HostCamera::configure(double hFov_, double vFov_, double nClip_, double fClip_, size_t w, size_t h) {
   screenW = w; screenH = h; nClip = nClip_; fClip = fClip_; hFov = hFov_; vFov = vFov_;
@@ -534,7 +537,10 @@ bool HostCamera::load_info(const std::string& path, std::string& err) {
 }
 
 // ---- Application::load ---------------------------------------------------------------------------------------------
+void set_direct_triangle_fallback(bool on) { g_direct_triangles_storage = on; }
+
 bool load_collada(const std::string& path, size_t width, size_t height, FlatScene& out, HostCamera& camera, std::string& err) {
+  const bool g_direct_triangles = g_direct_triangles_storage;
   Parser P;
   if (!P.load(path)) { err = P.err; return false; }
   out = FlatScene();
@@ -601,7 +607,34 @@ bool load_collada(const std::string& path, size_t width, size_t height, FlatScen
         std::vector<V3> verts = in.vertices;
         for (V3& v : verts) v = projectTo3D(T * v4(v, 1));
         HalfedgeMesh hm; std::string e;
-        if (!hm.build(in.polygons, verts, e)) { err = "error converting polygons to halfedge mesh: " + e; return false; }
+        if (!hm.build(in.polygons, verts, e)) {
+          if (!g_direct_triangles) { err = "error converting polygons to halfedge mesh: " + e; return false; }
+          // Direct indexed-triangle import (opt-in, the reference exit(1)s here, halfEdgeMesh.cpp:165-175):
+          // polygons are fan-triangulated instead of truncated to their first three vertices (object.cpp:36-41), vertex
+          // normals are the normalised sums of cross(pj - pi, pk - pi) over the incident triangles -- the terms of
+          // Vertex::computeNormal without the manifold walk.
+          std::vector<V3> nrm(verts.size(), V3());
+          std::vector<std::array<size_t, 3>> tris;
+          for (const auto& poly : in.polygons) {
+            if (poly.size() < 3) { err = "each polygon must have at least three vertices"; return false; }
+            for (size_t q : poly) if (q >= verts.size()) { err = "polygon index out of range"; return false; }
+            for (size_t i = 1; i + 1 < poly.size(); i++) tris.push_back({poly[0], poly[i], poly[i + 1]});
+          }
+          for (const auto& t : tris)
+            for (int k = 0; k < 3; k++) {
+              const V3 pi = verts[t[k]], pj = verts[t[(k + 1) % 3]], pk = verts[t[(k + 2) % 3]];
+              nrm[t[k]] = nrm[t[k]] + cross(pj - pi, pk - pi);
+            }
+          int32_t b2 = -1;
+          for (const auto& t : tris) {
+            if (b2 < 0) b2 = add_bsdf(in);
+            out.prim_type.push_back(1); out.prim_bsdf.push_back(b2);
+            for (int k = 0; k < 3; k++) { const V3& p = verts[t[k]]; box_grow(lo, hi, p); out.tri_pos.push_back(p.x); out.tri_pos.push_back(p.y); out.tri_pos.push_back(p.z); }
+            for (int k = 0; k < 3; k++) { const V3 n = normalized(nrm[t[k]]); out.tri_nrm.push_back(n.x); out.tri_nrm.push_back(n.y); out.tri_nrm.push_back(n.z); }
+            for (int k = 0; k < 4; k++) out.sphere.push_back(0);
+          }
+          break;
+        }
         for (const V3& p : hm.v_pos) box_grow(lo, hi, p);
         int32_t b = -1;
         for (int f = 0; f < hm.n_faces; f++) {

@@ -44,5 +44,8 @@ struct FlatScene {
 // Loads `path`, sizes the camera for a width x height frame (main.cpp:158-161), places the default orbit camera
 // (application.cpp:267-291).  Returns false and fills err on failure (the reference exit()s).
 bool load_collada(const std::string& path, size_t width, size_t height, FlatScene& scene, HostCamera& camera, std::string& err);
+// Opt-in: meshes the half-edge builder rejects (non-manifold, inconsistently oriented, repeated indices) are imported as plain
+// indexed triangles (polygons fan-triangulated) instead of failing.  Off by default: the reference stops on such input.
+void set_direct_triangle_fallback(bool on);
 
 }  // namespace dsrt_host

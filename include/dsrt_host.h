@@ -32,6 +32,11 @@ int dsrth_render_file(const char* dae_path, const char* cam_info, int32_t width,
                       const char* png_path, dsrt_stats* stats, double* bvh_seconds, double* render_seconds,
                       char* err, int32_t err_len);
 
+/* Loader options: "direct_triangles" (0/1, default 0): meshes the half-edge builder rejects (non-manifold, inconsistently
+ * oriented; the reference exit(1)s, src/halfEdgeMesh.cpp:165-175) are imported as plain indexed triangles, polygons
+ * fan-triangulated.  Returns non-zero for an unknown option. */
+int dsrth_set_loader_option(const char* name, int32_t value);
+
 /* Environment map of the -e option (reference src/main.cpp:30-67, 99-101: load_exr through tinyexr): scan-line OpenEXR
  * (NONE / RLE / ZIPS / ZIP / PIZ; R, G, B channels of HALF / FLOAT / UINT) or .pfm.  Call with rgb == NULL to get the size, then
  * with a buffer of width*height*3 floats (top row first, the layout dsrt_set_envmap takes). */

@@ -142,6 +142,23 @@ def test_collada_loader_errors_and_procedural_scene(tmp_path):
     S.write_dae(str(tmp_path / "nm.dae"), [("m", V, F, 0)], [(0, (0.5,) * 3, (0,) * 3, 0)])
     with pytest.raises(D.DsrtError, match="halfedge"):
         D.load_dae(str(tmp_path / "nm.dae"), 8, 8)
+    # ... unless the direct indexed-triangle import is switched on: same triangles, summed-cross-product normals
+    D.set_loader_option("direct_triangles", 1)
+    try:
+        nm, _ = D.load_dae(str(tmp_path / "nm.dae"), 8, 8)
+        assert len(nm["prim_type"]) == 2 and np.allclose(nm["tri_pos"].reshape(2, 3, 3), V[F])
+        n0 = np.cross(V[1] - V[0], V[2] - V[0]) + np.cross(V[1] - V[0], V[3] - V[0])
+        assert np.allclose(nm["tri_nrm"].reshape(2, 3, 3)[0, 0], n0 / np.linalg.norm(n0))
+        # a manifold mesh still takes the reference's half-edge route with the option on
+        Vk, Fk = S.torus_knot(n_around=6, n_along=40); Vk = Vk.astype(np.float32).astype(np.float64)
+        S.write_cb_mesh_dae(str(tmp_path / "k2.dae"), Vk, Fk)
+        on, _ = D.load_dae(str(tmp_path / "k2.dae"), 8, 8)
+    finally:
+        D.set_loader_option("direct_triangles", 0)
+    off, _ = D.load_dae(str(tmp_path / "k2.dae"), 8, 8)
+    assert all(np.array_equal(on[k], off[k]) for k in on)
+    with pytest.raises(D.DsrtError):
+        D.set_loader_option("no_such_option", 1)
     # a procedural closed mesh written as .dae flows through the loader: same geometry as the flat-array route
     V, F = S.torus_knot(n_around=6, n_along=40)
     V = V.astype(np.float32).astype(np.float64)

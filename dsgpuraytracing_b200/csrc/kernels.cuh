@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           if (COUNT) cnt.nodes++;
           const uint32_t m = test_children<false>(ray, fr, n0, n1, n2, n3, n4, tbest, 0.f, A.one_bits);
           ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
-          tgroup = make_uint2(n1.y, m & 0x00ffffffu);
+          tgroup = make_uint2(n1.y, drop_source(m & 0x00ffffffu, n1.y, ray.src_slot));
           did_node = true;
         }
       }
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
                   h = (slot != src2) && hit_triangle(r2, w2, a, b, cc, tmax2, t, u, v);
                 } else {
                   r2.dx = ldsf(rb + 3 * kBlkPitch); r2.dy = ldsf(rb + 4 * kBlkPitch); r2.dz = ldsf(rb + 5 * kBlkPitch);
-                  h = hit_sphere(r2, a, b, slot == src2, true, tmax2, t);
+                  h = hit_sphere(r2, a, b, leaves_sphere(src2, slot), true, tmax2, t);
                 }
                 if (h) sts8(s_flag_warp + s, 1u);
               }
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
               w2.bzx = ldsf(rb + 12 * kBlkPitch); w2.bzy = ldsf(rb + 13 * kBlkPitch); w2.bzz = ldsf(rb + 14 * kBlkPitch);
               h = (slot != ray.src_slot) && hit_triangle(ray, w2, a, b, c, tbest, t, u, v);
             } else {
-              h = hit_sphere(ray, a, b, slot == ray.src_slot, ANY, tbest, t);
+              h = hit_sphere(ray, a, b, leaves_sphere(ray.src_slot, slot), ANY, tbest, t);
             }
             if (h) {
               tbest = t; hit.slot = slot; hit.t = t; hit.u = u; hit.v = v;

@@ -12,6 +12,7 @@
 #include "hd.h"
 #include "layout.h"
 #include "rng.cuh"
+#include "traverse.cuh"   // source_code()
 
 namespace dsrt {
 
@@ -220,6 +221,7 @@ DSRT_HD void shade_path(const PathIn& in, const float4* __restrict__ prims, cons
   const int include_le = (hd_f2i(in.thr.w) >> 8) & 1;
   const float4 a = hd_ldg(prims + 3 * (size_t)slot), b = hd_ldg(prims + 3 * (size_t)slot + 1), c = hd_ldg(prims + 3 * (size_t)slot + 2);
   const Bsdf bs = sc.bsdf[hd_f2i(c.w)];
+  const int src_code = source_code(slot, b.w != 0.0f);      // travels with every ray that leaves this primitive (traverse.cuh)
   V3 hit_p, n_sh;
   if (b.w != 0.0f) {
     // hit point from the barycentrics (stays on the triangle's plane to float precision);
@@ -263,7 +265,7 @@ DSRT_HD void shade_path(const PathIn& in, const float4* __restrict__ prims, cons
       const float cos_theta = fmaxf(0.0f, w_in.z);
       const V3 contrib = (cos_theta / pdf * scale) * (thr * (light_L * f_direct));
       const V3 so = L.is_delta ? hit_p + kEpsN * n_sh : hit_p;                                    // pathtracer.cpp:497-500
-      sink.shadow(j, make_float4(so.x, so.y, so.z, dist * 0.999f), make_float4(wi.x, wi.y, wi.z, hd_i2f(slot)),
+      sink.shadow(j, make_float4(so.x, so.y, so.z, dist * 0.999f), make_float4(wi.x, wi.y, wi.z, hd_i2f(src_code)),
                   make_float4(contrib.x, contrib.y, contrib.z, hd_u2f(in.pix)));
     }
   }
@@ -282,7 +284,7 @@ DSRT_HD void shade_path(const PathIn& in, const float4* __restrict__ prims, cons
       const int next_le = (bs.type == 1 || bs.type == 2 || bs.type == 3) ? 1 : 0;                 // BSDF::is_delta
       out.cont = true;
       out.new_o = make_float4(hit_p.x, hit_p.y, hit_p.z, kInfF);
-      out.new_d = make_float4(nd.x, nd.y, nd.z, hd_i2f(slot));
+      out.new_d = make_float4(nd.x, nd.y, nd.z, hd_i2f(src_code));
       out.new_thr = make_float4(nthr.x, nthr.y, nthr.z, hd_i2f((depth + 1) | (next_le << 8)));
     }
   }

@@ -28,8 +28,18 @@ constexpr int kStackEntries = 32;    // upper bound on the levels of wide nodes 
 struct TraceRay {
   float ox, oy, oz, dx, dy, dz;
   float tmax;
-  int src_slot;   // primitive slot the ray starts on, -1 for camera rays (see hit-point note in shade.cuh)
+  int src_slot;   // where the ray starts (see hit-point note in shade.cuh): -1 nowhere (camera rays), slot >= 0 of the TRIANGLE it
+                  // leaves (never tested: dropped from the leaf's hit mask), -(slot + 2) of the SPHERE it leaves (tested, near root resolved)
 };
+// source codes of rays that leave a primitive
+DSRT_HD int source_code(int slot, bool is_triangle) { return is_triangle ? slot : -(slot + 2); }
+DSRT_HD bool leaves_sphere(int src, int slot) { return src < -1 && slot == -(src + 2); }
+// removes the source triangle from a leaf hit mask (bits 23..0 = primitives prim_base + bit): a ray always passes the box of the
+// triangle it starts on, so without this every secondary ray would fetch and test its own source once
+DSRT_HD uint32_t drop_source(uint32_t prim_mask, uint32_t prim_base, int src) {
+  const uint32_t rel = (uint32_t)src - prim_base;     // wraps to a huge value for src < prim_base (incl. -1 and sphere codes)
+  return rel < 24u ? prim_mask & ~(1u << rel) : prim_mask;
+}
 struct TraceHit {
   float t, u, v;  // u,v = barycentric weights of p2,p3 (the reference's u,v, triangle.cpp:69-70)
   int slot;       // -1 = miss
@@ -286,7 +296,7 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
       if (COUNT) cnt->nodes++;
       const uint32_t m = test_children<PARITY>(ray, fr, n0, n1, n2, n3, n4, tbest, A.pad, A.one_bits);
       ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
-      tgroup = make_uint2(n1.y, m & 0x00ffffffu);
+      tgroup = make_uint2(n1.y, drop_source(m & 0x00ffffffu, n1.y, ray.src_slot));
     } else {
       tgroup = make_uint2(0u, 0u);
     }
@@ -310,7 +320,7 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
           const float4 c = hd_ldg(pp + 2);
           h = (slot != ray.src_slot) && hit_triangle(ray, wr, a, b, c, tbest, t, u, v);
         } else {
-          h = hit_sphere(ray, a, b, slot == ray.src_slot, ANY, tbest, t);
+          h = hit_sphere(ray, a, b, leaves_sphere(ray.src_slot, slot), ANY, tbest, t);
         }
         if (h) {
           if (ANY) { hit.slot = slot; hit.t = t; return; }

@@ -461,7 +461,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   const int npp = blocks_x * blocks_y * 32;
   const int aligned = (W % 8 == 0 && H % 4 == 0) ? 1 : 0;
   int batch_spp = (int)ctx->opt_batch_spp;
-  if (batch_spp <= 0) batch_spp = std::max(1, (int)((8u << 20) / (unsigned)npp));   // ~8M paths per batch
+  if (batch_spp <= 0) batch_spp = std::max(1, (int)((16u << 20) / (unsigned)npp));   // ~16M paths per batch (measured: 4 / 8 / 16 M paths -> 6.38 / 6.59 / 6.71 Grays/s)
   batch_spp = std::min(batch_spp, std::max(1, spp_count));
   const size_t P = (size_t)npp * batch_spp;
   const int nls = ctx->n_light_samples;

@@ -1,4 +1,4 @@
-"""Small driver for ncu captures: one wavefront batch (2 spp at 1080p, 4.1 M paths) of the bench workload, twice.
+"""Small driver for ncu captures: one wavefront batch (`spp` samples per pixel at 1080p; 4 spp = 8.3 M paths) of the bench workload, twice.
 k_trace launches per render: 9 depths x (extend, connect) = 18, so
   ncu --set full --import-source on -k regex:k_trace -s 18 -c 2 ... python profiles/profile_run.py
 captures the depth-0 extend and connect launches of the second (warm) render."""

@@ -127,14 +127,18 @@ __global__ void k_generate_centres(PathState ps, RenderParams rp, int n_paths) {
   ps.ray_d[i] = make_float4(d.x, d.y, d.z, __int_as_float(-1));
 }
 
-// Persistent warps, one ray per lane.
-//  * dynamic fetch: a lane whose ray has finished idles until at most `refill_busy` lanes of its warp are still
-//    busy, then the warp fetches new rays for ALL idle lanes with one aggregated atomic (ballot + popc + shfl);
-//  * postponed primitive tests: a node visit leaves each lane with a group of pending primitives.  Testing them
-//    at once would run the (long) primitive test with the few lanes that happen to have reached a leaf.  Instead
-//    a lane keeps its pending group (older groups go onto the stack) and the WARP tests primitives only when at
-//    least `tri_min` lanes have some pending, or when a lane has nothing else left to do -- so the primitive test
-//    executes with many lanes active.  tri_min = 0 restores test-at-once order (used by the counter tests).
+// k_trace: persistent warps, one ray per lane.
+//  * dynamic fetch: a lane whose ray has finished idles until at most `refill_busy` lanes of its warp are still busy, then
+//    the warp fetches new rays for ALL idle lanes with one aggregated atomic (ballot + popc + shfl) -- and only then writes
+//    the results of the lanes that finished since the last refill, so result stores / framebuffer atomics run with many lanes;
+//  * postponed primitive tests: a node visit leaves a lane with a group of pending primitives.  Testing them at once would
+//    run the (long) primitive test with the few lanes that happen to have reached a leaf.  Instead the lane keeps the group
+//    (and skips node steps) until at least `tri_min` lanes have one, or until some lane has nothing else left to do;
+//    tri_min = 0 restores test-at-once order (used by the counter tests);
+//  * cooperative any-hit test (ANY): the pending (ray, primitive) pairs of the whole warp are written to a per-warp table
+//    (slices reserved with one shared-memory atomic per lane) and dealt out one per lane; the per-ray data the test needs
+//    (origin, watertight basis, tmax, source) lives in a per-lane shared-memory block, a hit sets the owner's flag;
+//  * a ray never fetches the triangle it starts on: its bit is dropped from the leaf hit mask (drop_source, traverse.cuh).
 
 // shared-memory accesses of k_trace by 32-bit shared-window address (no generic-address arithmetic in the hot loop)
 __device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }

@@ -5,9 +5,10 @@ import os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 LIBS = ["libdsrt.so"]
-OPTS = [{}, {"postpone_min_lanes": 8}, {"postpone_min_lanes": 16}, {"postpone_min_lanes": 20}, {"refill_busy_lanes": 14}, {"refill_busy_lanes": 16},
-        {"refill_busy_lanes": 20}, {"refill_busy_lanes": 22}, {"coop_min_pairs": 2}, {"coop_min_pairs": 12}, {"pool_batches": 4}, {"pool_batches": 16},
-        {"batch_spp": 2}, {"batch_spp": 8}]
+# edit for the experiment at hand: LIBS = builds to compare (make ../libdsrt_x.so OUT=../libdsrt_x.so EXTRA="-DDSRT_...=..."),
+# OPTS = dsrt_set_option overrides per run (on top of `defaults` below)
+OPTS = [{}, {"postpone_min_lanes": 8}, {"postpone_min_lanes": 16}, {"refill_busy_lanes": 16}, {"refill_busy_lanes": 20},
+        {"coop_min_pairs": 2}, {"coop_min_pairs": 12}, {"pool_batches": 4}, {"pool_batches": 16}, {"batch_spp": 4}, {"batch_spp": 8}]
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import numpy as np

@@ -53,8 +53,8 @@ def workload_config(a, n_gpus):
                         "from the reference checkout), cam_dragon.info",
             "width": a.width, "height": a.height, "spp": a.spp, "light_samples": a.light_samples, "max_depth": a.depth,
             "triangles": 100024, "parallelism": f"sample-split x{n_gpus} + 1 NCCL reduce" if n_gpus > 1 else "single GPU",
-            "l2": "explicit 256 MiB L2 flush between steps; per-step wavefront state (~1 GB) streams through L2, the "
-                  "8 MB wide BVH is re-read within a step"}
+            "l2": "explicit 256 MiB L2 flush between steps; per-batch wavefront state (~4.4 GB, larger than L2) streams through "
+                  "L2, the 5.9 MB wide BVH + primitive records are re-read within a step (L2-resident by design)"}
 
 
 # ---------------------------------------------------------------------------------------------- clocks sampler

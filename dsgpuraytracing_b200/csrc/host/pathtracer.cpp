@@ -95,6 +95,9 @@ void PathTracer::start_raytracing() {
   if (useCPU) { fail("useCPU requested: this port has no CPU fallback (run the reference for -c)"); return; }
   state = RENDERING;
   sampleBuffer.clear(); frameBuffer.clear();
+  auto tp = std::chrono::steady_clock::now();
+  auto lap = [&tp]() { auto n = std::chrono::steady_clock::now(); double s = std::chrono::duration<double>(n - tp).count(); tp = n; return s; };
+  const bool first_use = !ctx || !accel_uploaded;
   if (!ctx) {
     std::vector<int> devs(n_gpus); for (int i = 0; i < n_gpus; i++) devs[i] = i;
     int rc = n_gpus > 1 ? dsrt_create_multi(n_gpus, devs.data(), &ctx) : dsrt_create(0, &ctx);
@@ -112,8 +115,10 @@ void PathTracer::start_raytracing() {
     if (envMap && dsrt_set_envmap(ctx, (int)envMap->w, (int)envMap->h, envMap->data.data())) { fail("dsrt_set_envmap"); state = READY; return; }
     if (dsrt_set_bvh(ctx, &b)) { fail("dsrt_set_bvh"); state = READY; return; }
   }
+  const double t_ctx = lap();
   if (dsrt_set_params(ctx, (int)ns_aa, (int)ns_area_light, (int)max_ray_depth, seed)) { fail("dsrt_set_params"); state = READY; return; }
   if (!accel_uploaded) { if (dsrt_build_accel(ctx)) { fail("dsrt_build_accel"); state = READY; return; } accel_uploaded = true; }
+  if (first_use) fprintf(stdout, "[PathTracer] GPU context + scene copy %.4f sec, wide-BVH collapse + upload %.4f sec\n", t_ctx, lap());
   // generate_ray reads the camera's own screenW/H/screenDist (camera.cpp:113-129); the buffers have the frame size
   if (camera->screenW != sampleBuffer.w || camera->screenH != sampleBuffer.h) {
     fprintf(stderr, "[PathTracer] warning: camera is configured for %zux%zu, frame is %zux%zu (scene without a camera node?)\n",

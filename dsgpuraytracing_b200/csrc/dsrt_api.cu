@@ -89,6 +89,14 @@ template <typename T> int dev_alloc(dsrt_ctx* ctx, T** p, size_t n) {
 }
 void dev_free(void* p) { if (p) cudaFree(p); }
 
+// scratch device allocations / events of one API call: released on every return path
+struct Scratch {
+  std::vector<void*> ptrs; std::vector<cudaEvent_t> events;
+  ~Scratch() { for (void* p : ptrs) cudaFree(p); for (cudaEvent_t e : events) cudaEventDestroy(e); }
+  template <typename T> cudaError_t alloc(T** p, size_t bytes) { cudaError_t e = cudaMalloc((void**)p, bytes); if (e == cudaSuccess) ptrs.push_back(*p); return e; }
+  cudaError_t event(cudaEvent_t* ev) { cudaError_t e = cudaEventCreate(ev); if (e == cudaSuccess) events.push_back(*ev); return e; }
+};
+
 cudaEvent_t next_event(DevState& D) {
   if (D.ev_used == D.ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); D.ev_pool.push_back(e); }
   return D.ev_pool[D.ev_used++];
@@ -696,17 +704,17 @@ int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) 
     }
     std::vector<double> rays((size_t)n * 6);
     for (int y = 0; y < H; y++) for (int x = 0; x < W; x++) host_generate_ray64(ctx->cam, (x + 0.5) / W, (y + 0.5) / H, &rays[6 * ((size_t)y * W + x)]);
+    Scratch tmp;
     double* d_rays = nullptr; int32_t* d_slot = nullptr; double* d_t = nullptr;
-    CK(cudaMalloc((void**)&d_rays, rays.size() * sizeof(double)));
-    CK(cudaMalloc((void**)&d_slot, n * sizeof(int32_t)));
-    CK(cudaMalloc((void**)&d_t, n * sizeof(double)));
+    CK(tmp.alloc(&d_rays, rays.size() * sizeof(double)));
+    CK(tmp.alloc(&d_slot, n * sizeof(int32_t)));
+    CK(tmp.alloc(&d_t, n * sizeof(double)));
     CK(cudaMemcpyAsync(d_rays, rays.data(), rays.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     k_primary_parity<<<(n + kTraceThreads - 1) / kTraceThreads, kTraceThreads, stack_bytes(ctx), st>>>(make_accel(ctx, D, true), d_rays, n, d_slot, d_t);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(slots.data(), d_slot, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ts.data(), d_t, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    cudaFree(d_rays); cudaFree(d_slot); cudaFree(d_t);
   } else {
     int rc = ensure_wavefront(ctx, D, (size_t)n, 1);
     if (rc) return rc;
@@ -780,20 +788,20 @@ int dsrt_measure_read_bandwidth(dsrt_ctx* ctx, int64_t bytes, int32_t repeats, d
   DevState& D = ctx->devs[0];
   CK(cudaSetDevice(D.device));
   const size_t n_vec = (size_t)bytes / 16;
+  Scratch tmp;
   uint4* d_buf = nullptr; uint32_t* d_sink = nullptr;
-  CK(cudaMalloc((void**)&d_buf, n_vec * 16));
-  CK(cudaMalloc((void**)&d_sink, 16));
+  CK(tmp.alloc(&d_buf, n_vec * 16));
+  CK(tmp.alloc(&d_sink, 16));
   CK(cudaMemsetAsync(d_buf, 1, n_vec * 16, D.stream));
   const int grid = D.sm_count * 8;                 // 8 CTAs of 256 threads per SM: the full 2048 resident threads
   k_read_sweep<<<grid, 256, 0, D.stream>>>(d_buf, n_vec, 1, d_sink);          // warm: pulls the buffer into L2
-  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  cudaEvent_t e0, e1; CK(tmp.event(&e0)); CK(tmp.event(&e1));
   CK(cudaEventRecord(e0, D.stream));
   k_read_sweep<<<grid, 256, 0, D.stream>>>(d_buf, n_vec, repeats, d_sink);
   CK(cudaEventRecord(e1, D.stream));
   CK(cudaGetLastError());
   CK(cudaEventSynchronize(e1));
   float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_buf); cudaFree(d_sink);
   *gb_per_s = ms > 0 ? (double)n_vec * 16.0 * repeats / ((double)ms * 1e-3) / 1e9 : 0.0;
   return DSRT_OK;
 }
@@ -802,14 +810,14 @@ int dsrt_tonemap(dsrt_ctx* ctx, const float* rgb, int64_t n_pixels, uint32_t* rg
   if (!ctx || !rgb || !rgba8 || n_pixels < 0) return DSRT_ERR_INVALID;
   DevState& D = ctx->devs[0];
   CK(cudaSetDevice(D.device));
+  Scratch tmp;
   float* d_in = nullptr; uint32_t* d_out = nullptr;
-  CK(cudaMalloc((void**)&d_in, (size_t)n_pixels * 3 * sizeof(float) + 16));
-  CK(cudaMalloc((void**)&d_out, (size_t)n_pixels * sizeof(uint32_t) + 16));
+  CK(tmp.alloc(&d_in, (size_t)n_pixels * 3 * sizeof(float) + 16));
+  CK(tmp.alloc(&d_out, (size_t)n_pixels * sizeof(uint32_t) + 16));
   CK(cudaMemcpyAsync(d_in, rgb, (size_t)n_pixels * 3 * sizeof(float), cudaMemcpyHostToDevice, D.stream));
   k_resolve<<<(unsigned)((n_pixels + 255) / 256), 256, 0, D.stream>>>(d_in, nullptr, d_out, (int)n_pixels, 1.0f);
   CK(cudaMemcpyAsync(rgba8, d_out, (size_t)n_pixels * sizeof(uint32_t), cudaMemcpyDeviceToHost, D.stream));
   CK(cudaStreamSynchronize(D.stream));
-  cudaFree(d_in); cudaFree(d_out);
   return DSRT_OK;
 }
 

@@ -57,7 +57,7 @@ class Stats(C.Structure):
                 ("extend_nodes", C.c_uint64), ("extend_prims", C.c_uint64),
                 ("connect_nodes", C.c_uint64), ("connect_prims", C.c_uint64), ("gpu_seconds", C.c_double),
                 ("extend_seconds", C.c_double), ("connect_seconds", C.c_double), ("shade_seconds", C.c_double),
-                ("kernel_launches", C.c_uint32), ("batches", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("batches", C.c_uint32), ("null_shadow_rays", C.c_uint64)]
 
     @property
     def segments(self):

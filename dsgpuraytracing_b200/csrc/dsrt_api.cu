@@ -64,12 +64,13 @@ struct dsrt_ctx {
   Camera cam{};
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
-  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 12, opt_refill = 18, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_max_ctas = 0, opt_carveout = -1, opt_prim_cost = 100;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 12, opt_refill = 18, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_max_ctas = 0, opt_carveout = -1, opt_prim_cost = 100, opt_mem_budget_mb = 0;
   WideBVH wide;
   std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
   int env_w = 0, env_h = 0;
   std::vector<float> env_rgb, env_tp, env_t, env_pgt;
   double scene_diag = 1.0;
+  float bsphere[4] = {0.f, 0.f, 0.f, 0.f};   // centre + radius of a sphere around all primitives (Accel::bcx..brad)
   int n_lights = 0, n_light_samples = 0;
 };
 
@@ -108,6 +109,7 @@ Accel make_accel(const dsrt_ctx* ctx, const DevState& D, bool parity) {
   A.prims64 = (const double*)D.d_prims64;
   A.pad = parity ? (float)(1e-5 * ctx->scene_diag) : 0.f;
   A.one_bits = 0x3f800000u;
+  A.bcx = ctx->bsphere[0]; A.bcy = ctx->bsphere[1]; A.bcz = ctx->bsphere[2]; A.brad = ctx->bsphere[3];
   return A;
 }
 
@@ -256,14 +258,23 @@ const char* dsrt_last_error(const dsrt_ctx* ctx) { return ctx ? ctx->err.c_str()
 
 int dsrt_set_scene(dsrt_ctx* ctx, const dsrt_scene* s) {
   if (!ctx || !s) return DSRT_ERR_INVALID;
+  // a failed call must not leave a half-updated context usable: nothing is valid until this call succeeds, and every
+  // input is checked before the first byte of ctx changes
+  ctx->have_scene = false; ctx->have_bvh = false; ctx->have_accel = false;
   if (s->n_prims < 0 || s->n_bsdf < 0 || s->n_lights < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: negative count");
   if (s->n_prims > 0 && (!s->prim_type || !s->prim_bsdf || !s->tri_pos || !s->tri_nrm || !s->sphere))
     return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: null primitive array");
+  if (s->n_bsdf > 0 && (!s->bsdf_type || !s->bsdf_param)) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: null BSDF array");
+  if (s->n_lights > 0 && (!s->light_type || !s->light_param)) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: null light array");
   const size_t n = (size_t)s->n_prims;
   for (size_t i = 0; i < n; i++) {
     if (s->prim_bsdf[i] < 0 || s->prim_bsdf[i] >= s->n_bsdf) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: prim_bsdf out of range");
     if (s->prim_type[i] != 0 && s->prim_type[i] != 1) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: prim_type must be 0 or 1");
   }
+  for (int i = 0; i < s->n_bsdf; i++)
+    if (s->bsdf_type[i] < 0 || s->bsdf_type[i] > 4) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: unknown BSDF type");
+  for (int i = 0; i < s->n_lights; i++)
+    if (s->light_type[i] < 0 || s->light_type[i] > 3) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: unsupported light type (spot/sphere/mesh lights are empty stubs in the reference, light.cpp:61-115)");
   ctx->n_prims = s->n_prims;
   ctx->prim_type.assign(s->prim_type, s->prim_type + n);
   ctx->prim_bsdf.assign(s->prim_bsdf, s->prim_bsdf + n);
@@ -275,20 +286,27 @@ int dsrt_set_scene(dsrt_ctx* ctx, const dsrt_scene* s) {
     Bsdf& b = ctx->bsdfs[i]; const float* q = s->bsdf_param + 8 * i;
     for (int k = 0; k < 3; k++) { b.a[k] = q[k]; b.b[k] = q[3 + k]; }
     b.ior = q[6]; b.type = s->bsdf_type[i];
-    if (b.type < 0 || b.type > 4) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: unknown BSDF type");
   }
   ctx->light_type.assign(s->light_type, s->light_type + s->n_lights);
   ctx->light_param.assign(s->light_param, s->light_param + 28 * (size_t)s->n_lights);
-  for (int i = 0; i < s->n_lights; i++)
-    if (s->light_type[i] < 0 || s->light_type[i] > 3) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_scene: unsupported light type (spot/sphere/mesh lights are empty stubs in the reference, light.cpp:61-115)");
-  ctx->have_scene = true; ctx->have_bvh = false; ctx->have_accel = false;
+  ctx->have_scene = true;
   return DSRT_OK;
 }
 
 int dsrt_set_bvh(dsrt_ctx* ctx, const dsrt_bvh2* b) {
   if (!ctx || !b) return DSRT_ERR_INVALID;
   if (!ctx->have_scene) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_bvh: call dsrt_set_scene first");
+  ctx->have_bvh = false; ctx->have_accel = false;
   if (b->n_nodes < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_bvh: negative node count");
+  if (b->n_nodes > 0 && (!b->node_bbox || !b->node_start || !b->node_range || !b->node_left || !b->node_right))
+    return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_bvh: null node array");
+  if (ctx->n_prims > 0 && !b->prim_order) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_bvh: null prim_order");
+  std::vector<char> seen(ctx->n_prims, 0);
+  for (int i = 0; i < ctx->n_prims; i++) {
+    const int p = b->prim_order[i];
+    if (p < 0 || p >= ctx->n_prims || seen[p]) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_bvh: prim_order is not a permutation");
+    seen[p] = 1;
+  }
   const size_t m = (size_t)b->n_nodes;
   ctx->node_bbox.assign(b->node_bbox, b->node_bbox + 6 * m);
   ctx->node_start.assign(b->node_start, b->node_start + m);
@@ -296,13 +314,7 @@ int dsrt_set_bvh(dsrt_ctx* ctx, const dsrt_bvh2* b) {
   ctx->node_left.assign(b->node_left, b->node_left + m);
   ctx->node_right.assign(b->node_right, b->node_right + m);
   ctx->prim_order.assign(b->prim_order, b->prim_order + ctx->n_prims);
-  std::vector<char> seen(ctx->n_prims, 0);
-  for (int i = 0; i < ctx->n_prims; i++) {
-    int p = ctx->prim_order[i];
-    if (p < 0 || p >= ctx->n_prims || seen[p]) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_bvh: prim_order is not a permutation");
-    seen[p] = 1;
-  }
-  ctx->have_bvh = true; ctx->have_accel = false;
+  ctx->have_bvh = true;
   return DSRT_OK;
 }
 
@@ -356,6 +368,7 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
   else if (n == "coop_min_pairs") ctx->opt_coop_min = value;
   else if (n == "max_ctas_per_sm") ctx->opt_max_ctas = value;
   else if (n == "collapse_prim_cost_pct") { ctx->opt_prim_cost = std::max<int64_t>(1, value); ctx->have_accel = false; }   // takes effect at the next dsrt_build_accel
+  else if (n == "wavefront_budget_mb") ctx->opt_mem_budget_mb = value;   // 0: 80 % of the free device memory; > 0: additional cap (tests)
   else if (n == "smem_carveout_pct") ctx->opt_carveout = value;        // -1: driver default          // 0: whatever fits
   else return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_option: unknown option " + n);
   return DSRT_OK;
@@ -378,6 +391,7 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
   Box3 all; all.reset(); for (const Box3& p : pbox) all.grow(p);
   double dg = 0; for (int k = 0; k < 3; k++) { double e = ctx->n_prims ? all.hi[k] - all.lo[k] : 0; double m = ctx->n_prims ? std::fmax(std::fabs(all.lo[k]), std::fabs(all.hi[k])) : 0; dg += (e + m) * (e + m); }
   ctx->scene_diag = std::sqrt(dg) + 1.0;
+  bounding_sphere(all, ctx->n_prims, ctx->bsphere);
 
   flatten_records(s, ctx->wide, ctx->recs, ctx->shd);
   ctx->r64.clear(); ctx->r64.shrink_to_fit();     // fp64 records: built and uploaded by the first dsrt_primary_hits(mode 1)
@@ -471,8 +485,29 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   int batch_spp = (int)ctx->opt_batch_spp;
   if (batch_spp <= 0) batch_spp = std::max(1, (int)((16u << 20) / (unsigned)npp));   // ~16M paths per batch (measured: 4 / 8 / 16 M paths -> 6.38 / 6.59 / 6.71 Grays/s)
   batch_spp = std::min(batch_spp, std::max(1, spp_count));
-  const size_t P = (size_t)npp * batch_spp;
   const int nls = ctx->n_light_samples;
+  // Wavefront + pool memory = paths x (80 B state and queues + 48 B per light sample) x (1 + pooled batches).  The reference
+  // accepts any -l / frame size, so the batch and the pool group shrink until the working set fits in what the device has
+  // free (plus what this context already holds); only a single-sample batch that still does not fit is an error.
+  int pool_group = (int)ctx->opt_pool_batches;
+  {
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const double held = (double)D.cap_paths * 80.0 + (double)D.cap_shadow * 48.0 + (double)D.cap_pool * 80.0 + (double)D.cap_pool_shadow * 48.0;
+    double budget = 0.8 * ((double)free_b + held);
+    if (ctx->opt_mem_budget_mb > 0) budget = std::min(budget, (double)ctx->opt_mem_budget_mb * 1048576.0);
+    const double per_path = 80.0 + 48.0 * (double)std::max(nls, 1);
+    auto need = [&](int bspp, int grp) { return (double)npp * bspp * per_path * (1.0 + (ctx->max_depth > 0 ? grp : 0)); };
+    while (need(batch_spp, pool_group) > budget) {
+      if (pool_group > 2) pool_group = (pool_group + 1) / 2;
+      else if (batch_spp > 1) batch_spp = (batch_spp + 1) / 2;
+      else if (pool_group > 1) pool_group = 1;
+      else return fail(ctx, DSRT_ERR_LIMIT, "dsrt_render: one sample per pixel of this frame with " + std::to_string(nls) +
+                       " light samples needs " + std::to_string((long long)(need(1, 1) / 1048576.0)) + " MiB of wavefront state; the device has " +
+                       std::to_string((long long)(budget / 1048576.0)) + " MiB available");
+    }
+  }
+  const size_t P = (size_t)npp * batch_spp;
   int rc = ensure_wavefront(ctx, D, P, P * (size_t)std::max(nls, 1));
   if (rc) return rc;
   const int n_batches = (spp_count + batch_spp - 1) / batch_spp;
@@ -500,7 +535,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   auto span_end = [&]() { if (timing) { D.spans.back().e1 = D.ev_used; cudaEventRecord(next_event(D), st); } };
 
   // pool: survivors of up to `group` consecutive batches (worst case: every path survives, e.g. a mirror box)
-  const int group = std::max(1, std::min(n_batches, (int)ctx->opt_pool_batches));
+  const int group = std::max(1, std::min(n_batches, pool_group));
   const int n_groups = (n_batches + group - 1) / group;
   const size_t pool_cap = P * (size_t)group;
   if (ctx->max_depth > 0) {
@@ -539,7 +574,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
     trace(false, D.ps.ray_o, D.ps.ray_d, q0, &C->q_count[0], &C->work_extend[0], D.ps.hit, nullptr);
     span_begin(2);
     k_shade<<<(n_paths + 127) / 128, 128, 0, st>>>(D.ps, (const float4*)D.d_prims, sc, rp, q0, &C->q_count[0], D.pool, nullptr,
-                                                   PC ? &PC->q_count[0] : &C->q_count[1], (uint32_t)pool_cap, D.sq, &C->s_count[0], d_accum);
+                                                   PC ? &PC->q_count[0] : &C->q_count[1], (uint32_t)pool_cap, D.sq, &C->s_count[0], d_accum, D.d_totals);
     span_end();
     D.launches++;
     if (nls > 0) trace(true, D.sq.a, D.sq.b, nullptr, &C->s_count[0], &C->work_connect[0], nullptr, D.sq.c);
@@ -554,7 +589,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
         trace(false, D.pool.ray_o, D.pool.ray_d, q, &PC->q_count[it], &PC->work_extend[it], D.pool.hit, nullptr);
         span_begin(2);
         k_shade<<<pgrid, 128, 0, st>>>(D.pool, (const float4*)D.d_prims, sc, rp, q, &PC->q_count[it], D.pool, D.pool_queue[cur ^ 1],
-                                       &PC->q_count[it + 1], 0u, D.pool_sq, &PC->s_count[it], d_accum);
+                                       &PC->q_count[it + 1], 0u, D.pool_sq, &PC->s_count[it], d_accum, D.d_totals);
         span_end();
         D.launches++;
         if (nls > 0) trace(true, D.pool_sq.a, D.pool_sq.b, nullptr, &PC->s_count[it], &PC->work_connect[it], nullptr, D.pool_sq.c);
@@ -580,6 +615,7 @@ int dsrt_collect_stats(dsrt_ctx* ctx, dsrt_stats* stats) {
     Totals t;
     CK(cudaMemcpy(&t, D.d_totals, sizeof(t), cudaMemcpyDeviceToHost));
     stats->camera_samples += t.camera; stats->extend_rays += t.extend; stats->shadow_rays += t.shadow;
+    stats->null_shadow_rays += t.null_shadow;
     stats->extend_nodes += t.nodes[0]; stats->extend_prims += t.prims[0]; stats->connect_nodes += t.nodes[1]; stats->connect_prims += t.prims[1];
     float ms = 0; CK(cudaEventElapsedTime(&ms, D.ev_begin, D.ev_end));
     stats->gpu_seconds = std::max(stats->gpu_seconds, (double)ms * 1e-3);

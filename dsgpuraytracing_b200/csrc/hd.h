@@ -22,6 +22,15 @@ DSRT_HD float hd_fma(float a, float b, float c) {
   return fmaf(a, b, c);
 #endif
 }
+// fma with the result clamped to [0, 1] (NaN -> 0): one FFMA.SAT on the device
+DSRT_HD float hd_fma_sat(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+  return __saturatef(__fmaf_rn(a, b, c));
+#else
+  const float r = fmaf(a, b, c);
+  return r > 0.0f ? (r < 1.0f ? r : 1.0f) : 0.0f;      // NaN compares false: 0
+#endif
+}
 DSRT_HD float hd_mul(float a, float b) {
 #ifdef __CUDA_ARCH__
   return __fmul_rn(a, b);

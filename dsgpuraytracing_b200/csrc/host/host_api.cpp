@@ -1,5 +1,7 @@
 // host_api.cpp -- C wrappers declared in include/dsrt_host.h
 #include <cstring>
+#include <exception>
+#include <memory>
 #include <string>
 
 #include "../../../include/dsrt_host.h"
@@ -15,17 +17,27 @@ static void set_err(char* err, int32_t n, const std::string& m) {
   if (err && n > 0) { std::strncpy(err, m.c_str(), (size_t)n - 1); err[n - 1] = 0; }
 }
 
+// No C++ exception may cross the C boundary (a ctypes / cgo caller would be terminated): every entry point that parses
+// files or allocates from file-supplied sizes runs its body through guard().
+template <class F> static int guard(char* err, int32_t err_len, F&& body) {
+  try { return body(); }
+  catch (const std::exception& e) { set_err(err, err_len, std::string("exception: ") + e.what()); return DSRT_ERR_INVALID; }
+  catch (...) { set_err(err, err_len, "unknown exception"); return DSRT_ERR_INVALID; }
+}
+
 extern "C" {
 
 int dsrth_load_dae(const char* path, int32_t width, int32_t height, const char* cam_info, dsrth_scene** out, char* err, int32_t err_len) {
   if (!path || !out || width <= 0 || height <= 0) { set_err(err, err_len, "bad arguments"); return DSRT_ERR_INVALID; }
   *out = nullptr;
-  dsrth_scene* s = new dsrth_scene();
-  std::string e;
-  if (!load_collada(path, (size_t)width, (size_t)height, s->scene, s->camera, e)) { set_err(err, err_len, e); delete s; return DSRT_ERR_INVALID; }
-  if (cam_info && *cam_info && !s->camera.load_info(cam_info, e)) { set_err(err, err_len, e); delete s; return DSRT_ERR_INVALID; }
-  *out = s;
-  return DSRT_OK;
+  return guard(err, err_len, [&]() -> int {
+    std::unique_ptr<dsrth_scene> s(new dsrth_scene());
+    std::string e;
+    if (!load_collada(path, (size_t)width, (size_t)height, s->scene, s->camera, e)) { set_err(err, err_len, e); return DSRT_ERR_INVALID; }
+    if (cam_info && *cam_info && !s->camera.load_info(cam_info, e)) { set_err(err, err_len, e); return DSRT_ERR_INVALID; }
+    *out = s.release();
+    return DSRT_OK;
+  });
 }
 
 void dsrth_free(dsrth_scene* s) { delete s; }
@@ -53,6 +65,7 @@ int dsrth_render_file(const char* dae_path, const char* cam_info, int32_t width,
                       int32_t max_ray_depth, int32_t n_gpus, uint32_t seed, float* rgb_out, const char* png_path, dsrt_stats* stats,
                       double* bvh_seconds, double* render_seconds, char* err, int32_t err_len) {
   if (!dae_path || width <= 0 || height <= 0) { set_err(err, err_len, "bad arguments"); return DSRT_ERR_INVALID; }
+  return guard(err, err_len, [&]() -> int {
   FlatScene scene; HostCamera camera; std::string e;
   if (!load_collada(dae_path, (size_t)width, (size_t)height, scene, camera, e)) { set_err(err, err_len, e); return DSRT_ERR_INVALID; }
   PathTracer pt((size_t)ns_aa, (size_t)max_ray_depth, (size_t)ns_area_light, 1, 1, 1, 1, nullptr);
@@ -69,6 +82,7 @@ int dsrth_render_file(const char* dae_path, const char* cam_info, int32_t width,
   if (render_seconds) *render_seconds = pt.render_seconds;
   if (png_path && *png_path && !pt.save_image(png_path)) { set_err(err, err_len, pt.last_error()); return DSRT_ERR_INVALID; }
   return DSRT_OK;
+  });
 }
 
 int dsrth_set_loader_option(const char* name, int32_t value) {
@@ -79,6 +93,7 @@ int dsrth_set_loader_option(const char* name, int32_t value) {
 
 int dsrth_load_envmap(const char* path, int32_t* width, int32_t* height, float* rgb, int64_t cap, char* err, int32_t err_len) {
   if (!path || !width || !height) { set_err(err, err_len, "bad arguments"); return DSRT_ERR_INVALID; }
+  return guard(err, err_len, [&]() -> int {
   HDRImageBuffer img; std::string e;
   if (!load_envmap(path, img, e)) { set_err(err, err_len, e); return DSRT_ERR_INVALID; }
   *width = (int32_t)img.w; *height = (int32_t)img.h;
@@ -87,6 +102,7 @@ int dsrth_load_envmap(const char* path, int32_t* width, int32_t* height, float* 
     std::memcpy(rgb, img.data.data(), img.data.size() * sizeof(float));
   }
   return DSRT_OK;
+  });
 }
 
 }  // extern "C"

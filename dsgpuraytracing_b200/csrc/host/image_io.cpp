@@ -1,4 +1,5 @@
-// image_io.cpp -- OpenEXR / PFM readers (see image_io.h).  Written against the OpenEXR file layout document: magic,
+// image_io.cpp -- OpenEXR / PFM readers (see image_io.h).  Scope is frozen (scan-line NONE / RLE / ZIPS / ZIP / PIZ): the -e
+// option is off the render hot path.  Written against the OpenEXR file layout document: magic,
 // version word, attribute list, line-offset table, chunks of 1 (NONE, RLE, ZIPS), 16 (ZIP) or 32 (PIZ) scan lines; a ZIP / RLE
 // chunk is zlib / run-length data of the byte-planar, delta-predicted pixel bytes, a PIZ chunk is Huffman-coded wavelet data.
 #include "image_io.h"
@@ -16,7 +17,8 @@ namespace {
 struct Reader {
   const std::vector<uint8_t>& b; size_t p = 0; bool ok = true;
   explicit Reader(const std::vector<uint8_t>& bytes) : b(bytes) {}
-  bool need(size_t n) { if (p + n > b.size()) { ok = false; return false; } return true; }
+  // p and n can both come from untrusted 64-bit file fields: compare without forming p + n (which could wrap)
+  bool need(size_t n) { if (p > b.size() || n > b.size() - p) { ok = false; return false; } return true; }
   uint8_t u8() { if (!need(1)) return 0; return b[p++]; }
   uint32_t u32() { if (!need(4)) return 0; uint32_t v; std::memcpy(&v, &b[p], 4); p += 4; return v; }
   int32_t i32() { return (int32_t)u32(); }
@@ -58,8 +60,10 @@ bool rle_decode(const uint8_t* src, size_t n, std::vector<uint8_t>& out, size_t 
 
 
 // ---- PIZ: 16-bit range compaction (bitmap + lookup table), 2-D Haar-like wavelet per channel, canonical Huffman coding
-// with a run-length symbol.  Restated from the OpenEXR file-format description (the layout ImfPizCompressor / ImfHuf / ImfWav
-// write); the reference reads such files through its vendored tinyexr.
+// with a run-length symbol.  The algorithms are those of OpenEXR's ImfPizCompressor / ImfHuf / ImfWav (Industrial Light & Magic,
+// BSD-3-Clause), which the file format fixes bit for bit; the reference reads such files through its vendored tinyexr
+// (CMU462/include/CMU462/tinyexr.h, BSD-3-Clause, itself derived from the ILM sources).  This is a re-implementation of
+// those published algorithms for this reader, checked against tinyexr's output (tests/golden/exr), not original design.
 constexpr int kHufEncBits = 16, kHufDecBits = 14;
 constexpr int kHufEncSize = (1 << kHufEncBits) + 1, kHufDecSize = 1 << kHufDecBits, kHufDecMask = kHufDecSize - 1;
 constexpr int kShortZeroRun = 59, kLongZeroRun = 63, kShortestLongRun = 2 + kLongZeroRun - kShortZeroRun;
@@ -170,43 +174,38 @@ bool huf_uncompress(const uint8_t* src, size_t n_src, std::vector<uint16_t>& out
   return o == n_out;
 }
 
-inline void wdec14(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
-  const int hi = (int16_t)h;
-  const int ai = (int16_t)l + (hi & 1) + (hi >> 1);
-  a = (uint16_t)(int16_t)ai; b = (uint16_t)(int16_t)(ai - hi);
+// The PIZ wavelet is fixed by the OpenEXR file format (ILM's ImfWav.cpp, BSD-3-Clause; the reference vendors a copy inside
+// CMU462/include/CMU462/tinyexr.h:7213-7470).  Each step undoes one "average / difference" pair (lo, hi) -> (a, b): the
+// 14-bit form when the range-compacted data fits in 14 bits, otherwise the modulo-2^16 form.
+inline void unpair14(uint16_t lo, uint16_t hi, uint16_t& a, uint16_t& b) {
+  const int d = (int16_t)hi, s = (int16_t)lo + (d & 1) + (d >> 1);
+  a = (uint16_t)(int16_t)s; b = (uint16_t)(int16_t)(s - d);
 }
-inline void wdec16(uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) {
-  const int m = l, d = h;
-  const int bb = (m - (d >> 1)) & 0xffff;
-  const int aa = (d + bb - 0x8000) & 0xffff;
-  b = (uint16_t)bb; a = (uint16_t)aa;
+inline void unpair16(uint16_t lo, uint16_t hi, uint16_t& a, uint16_t& b) {
+  const int y = ((int)lo - ((int)hi >> 1)) & 0xffff;
+  b = (uint16_t)y; a = (uint16_t)(((int)hi + y - 0x8000) & 0xffff);
 }
-// inverse 2-D wavelet on an nx x ny grid of 16-bit values with strides ox, oy; mx = largest value after range compaction
-void wav2_decode(uint16_t* in, int nx, int ox, int ny, int oy, uint16_t mx) {
-  const bool w14 = mx < (1 << 14);
-  const int n = nx > ny ? ny : nx;
-  int p = 1, p2;
-  while (p <= n) p <<= 1;
-  p >>= 1; p2 = p; p >>= 1;
-  auto dec = [&](uint16_t l, uint16_t h, uint16_t& a, uint16_t& b) { if (w14) wdec14(l, h, a, b); else wdec16(l, h, a, b); };
-  while (p >= 1) {
-    uint16_t* py = in; uint16_t* ey = in + (ptrdiff_t)oy * (ny - p2);
-    const ptrdiff_t oy1 = (ptrdiff_t)oy * p, oy2 = (ptrdiff_t)oy * p2, ox1 = (ptrdiff_t)ox * p, ox2 = (ptrdiff_t)ox * p2;
-    uint16_t i00, i01, i10, i11;
-    for (; py <= ey; py += oy2) {
-      uint16_t* px = py; uint16_t* ex = py + (ptrdiff_t)ox * (nx - p2);
-      for (; px <= ex; px += ox2) {
-        uint16_t* p01 = px + ox1; uint16_t* p10 = px + oy1; uint16_t* p11 = p10 + ox1;
-        dec(*px, *p10, i00, i10); dec(*p01, *p11, i01, i11);
-        dec(i00, i01, *px, *p01); dec(i10, i11, *p10, *p11);
+// inverse 2-D wavelet, in place, on an nx x ny grid of 16-bit values (element (x, y) at v[x * sx + y * sy]); max_value =
+// largest value after range compaction.  Levels run from the coarsest cell size (largest power of two <= min(nx, ny))
+// down to 2; a level first undoes the 2x2 cells, then the left-over column / row when the size has that bit set.
+void wav2_decode(uint16_t* v, int nx, int sx, int ny, int sy, uint16_t max_value) {
+  const bool small = max_value < (1 << 14);
+  auto at = [&](int x, int y) -> uint16_t& { return v[(ptrdiff_t)x * sx + (ptrdiff_t)y * sy]; };
+  auto unpair = [&](uint16_t lo, uint16_t hi, uint16_t& a, uint16_t& b) { if (small) unpair14(lo, hi, a, b); else unpair16(lo, hi, a, b); };
+  int cell = 1;
+  while (cell * 2 <= (nx < ny ? nx : ny)) cell *= 2;
+  for (int half = cell / 2; half >= 1; cell = half, half /= 2) {
+    const int x_end = ((nx - cell) / cell + 1) * cell, y_end = ((ny - cell) / cell + 1) * cell;   // extent covered by whole cells
+    for (int y = 0; y < y_end; y += cell) {
+      for (int x = 0; x < x_end; x += cell) {
+        uint16_t t00, t01, t10, t11;
+        unpair(at(x, y), at(x, y + half), t00, t10); unpair(at(x + half, y), at(x + half, y + half), t01, t11);   // columns
+        unpair(t00, t01, at(x, y), at(x + half, y)); unpair(t10, t11, at(x, y + half), at(x + half, y + half));     // rows
       }
-      if (nx & p) { uint16_t* p10 = px + oy1; dec(*px, *p10, i00, *p10); *px = i00; }      // odd column
+      if (nx & half) { uint16_t t; unpair(at(x_end, y), at(x_end, y + half), t, at(x_end, y + half)); at(x_end, y) = t; }
     }
-    if (ny & p) {                                                                           // odd line
-      uint16_t* px = py; uint16_t* ex = py + (ptrdiff_t)ox * (nx - p2);
-      for (; px <= ex; px += ox2) { uint16_t* p01 = px + ox1; dec(*px, *p01, i00, *p01); *px = i00; }
-    }
-    p2 = p; p >>= 1;
+    if (ny & half)
+      for (int x = 0; x < x_end; x += cell) { uint16_t t; unpair(at(x, y_end), at(x + half, y_end), t, at(x + half, y_end)); at(x, y_end) = t; }
   }
 }
 
@@ -310,6 +309,7 @@ bool load_exr(const std::string& path, HDRImageBuffer& img, std::string& err) {
   img.resize((size_t)W, (size_t)H);
   std::vector<uint8_t> tmp, raw; std::vector<char> seen((size_t)H, 0);
   for (int64_t i = 0; i < n_chunks; i++) {
+    if (offsets[(size_t)i] >= (uint64_t)bytes.size()) { err = "corrupt OpenEXR chunk offset"; return false; }
     Reader c(bytes); c.p = (size_t)offsets[(size_t)i];
     const int32_t y0 = c.i32(); const int32_t sz = c.i32();
     if (!c.ok || sz < 0 || !c.need((size_t)sz) || y0 < dw[1] || y0 > dw[3]) { err = "corrupt OpenEXR chunk"; return false; }

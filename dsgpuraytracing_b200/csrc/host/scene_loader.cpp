@@ -214,6 +214,11 @@ struct Parser {
     return true;
   }
 
+  // a `count` attribute is untrusted: it must be non-negative and cannot exceed what the element's text could hold
+  // (one character per value plus a separator); anything else is a corrupt file, not an allocation request
+  static bool plausible_count(long long count, const char* text) {
+    return count >= 0 && (unsigned long long)count <= (text ? (unsigned long long)strlen(text) / 2 + 1 : 0ull);
+  }
   static bool read_floats(const char* s, size_t n, std::vector<float>& out) {
     out.clear(); out.reserve(n);
     if (!s) return n == 0;
@@ -244,7 +249,10 @@ struct Parser {
     for (XmlElement* s = e_mesh->FirstChildElement("source"); s; s = s->NextSiblingElement("source")) {
       const char* sid = s->Attribute("id");
       XmlElement* fa = s->FirstChildElement("float_array");
-      if (sid && fa) { std::vector<float> f; read_floats(fa->GetText(), (size_t)fa->IntAttribute("count"), f); arr[sid] = f; }
+      if (sid && fa) {
+        if (!plausible_count(fa->IntAttribute("count"), fa->GetText())) return fail("implausible float_array count in geometry");
+        std::vector<float> f; read_floats(fa->GetText(), (size_t)fa->IntAttribute("count"), f); arr[sid] = f;
+      }
     }
     XmlElement* e_vertices = e_mesh->FirstChildElement("vertices");
     if (!e_vertices || !e_vertices->Attribute("id")) return fail("no vertices defined in geometry");
@@ -266,6 +274,7 @@ struct Parser {
       const char* sem = in->Attribute("semantic"); const char* src = in->Attribute("source");
       if (!sem || !src) return fail("polylist input without semantic/source");
       std::string semantic = sem, source = src + 1;
+      if (in->IntAttribute("offset") < 0 || in->IntAttribute("offset") > 16) return fail("implausible polylist input offset");
       size_t offset = (size_t)in->IntAttribute("offset");
       if (semantic == "VERTEX") {
         hv = true; vo = offset;
@@ -275,14 +284,21 @@ struct Parser {
       if (semantic == "NORMAL") { hn = true; if (arr.find(source) == arr.end()) return fail("undefined source for NORMAL semantic: " + source); }
       if (semantic == "TEXCOORD") { ht = true; if (arr.find(source) == arr.end()) return fail("undefined source for TEXCOORD semantic: " + source); }
     }
-    const size_t num_polygons = (size_t)pl->IntAttribute("count");
     const size_t stride = (hv ? 1 : 0) + (hn ? 1 : 0) + (ht ? 1 : 0);
     XmlElement* e_vcount = pl->FirstChildElement("vcount");
     if (!e_vcount) return fail("polygon sizes undefined in geometry");
+    if (!plausible_count(pl->IntAttribute("count"), e_vcount->GetText())) return fail("implausible polylist count in geometry");
+    const size_t num_polygons = (size_t)pl->IntAttribute("count");
     std::vector<size_t> sizes; read_sizes(e_vcount->GetText(), num_polygons, sizes);
-    size_t num_indices = 0; for (size_t s : sizes) num_indices += s * stride;
     XmlElement* e_p = pl->FirstChildElement("p");
     if (!e_p) return fail("no index array defined in geometry");
+    const size_t index_text = e_p->GetText() ? strlen(e_p->GetText()) : 0;
+    size_t num_indices = 0;
+    for (size_t s : sizes) {
+      if (s > index_text) return fail("implausible polygon size in geometry");
+      num_indices += s * stride;
+      if (num_indices > index_text + 1) return fail("index array too short in geometry");
+    }
     std::vector<size_t> indices; read_sizes(e_p->GetText(), num_indices, indices);
     pm.polygons.assign(num_polygons, {});
     if (hv) {

@@ -34,6 +34,16 @@ struct Box3 {
   double centre(int k) const { return 0.5 * (lo[k] + hi[k]); }
 };
 
+// sphere (centre xyz, radius) around a box, rounded outwards in float: bounds how far a ray with tmax = inf can reach
+inline void bounding_sphere(const Box3& b, int n_prims, float out[4]) {
+  out[0] = out[1] = out[2] = out[3] = 0.f;
+  if (n_prims <= 0) return;
+  double r2 = 0;
+  for (int k = 0; k < 3; k++) { out[k] = (float)(0.5 * (b.lo[k] + b.hi[k])); }
+  for (int k = 0; k < 3; k++) { const double e = std::max(std::fabs(b.hi[k] - (double)out[k]), std::fabs(b.lo[k] - (double)out[k])); r2 += e * e; }
+  out[3] = (float)(std::sqrt(r2) * 1.000001 + 1e-30);
+}
+
 // worker threads of the host-side builders; DSRT_HOST_THREADS overrides the core count (the results never depend on it)
 inline int host_threads() {
   if (const char* e = std::getenv("DSRT_HOST_THREADS")) { const int n = std::atoi(e); if (n >= 1) return n; }

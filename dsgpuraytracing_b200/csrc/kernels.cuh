@@ -33,7 +33,10 @@ constexpr int kTraceThreads = 128;        // 4 warps per CTA
 #ifndef DSRT_TRACE_MIN_CTAS
 #define DSRT_TRACE_MIN_CTAS 7             // resident CTAs per SM the traversal kernels are compiled for (register cap 72; measured best of 6, 7, 8)
 #endif
-constexpr int kRayBlock = 17;             // floats per lane published for the cooperative primitive test
+#ifndef DSRT_NODE_STEPS
+#define DSRT_NODE_STEPS 1                 // node steps a lane may take between two warp-wide primitive-test decisions
+#endif
+constexpr int kRayBlock = DSRT_TRI_FAST ? 20 : 17;   // floats per lane published for the cooperative primitive test
 #ifndef DSRT_PAIR_CAP
 #define DSRT_PAIR_CAP 192
 #endif
@@ -79,7 +82,7 @@ struct PoolCounters {
   uint32_t work_extend[kMaxDepthSlots];
   uint32_t work_connect[kMaxDepthSlots];
 };
-struct Totals { unsigned long long camera, extend, shadow, nodes[2], prims[2]; };   // [0] extend, [1] connect
+struct Totals { unsigned long long camera, extend, shadow, nodes[2], prims[2], null_shadow; };   // [0] extend, [1] connect
 
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void k_generate(PathState ps, RenderParams rp, int n_paths, uint32_t* queue, uint32_t* q_count, int aligned) {
@@ -214,10 +217,14 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
         const uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
         if (k < n) {
           item = queue ? queue[k] : k;
-          const float4 o = DSRT_RAY_LD(ray_o + item), d = DSRT_RAY_LD(ray_d + item);
+          const float4 o = DSRT_RAY_LD(ray_o + item);
+          if (ANY && o.w < 0.f) {          // "skip_null_shadow": a shadow ray whose contribution is zero was queued with tmax = -1
+            if (hit_out) hit_out[item] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+          } else {
+          const float4 d = DSRT_RAY_LD(ray_d + item);
           ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.tmax = o.w;
           ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.src_slot = __float_as_int(d.w);
-          fr = make_frame(ray);
+          fr = make_frame(ray, (ANY && DSRT_SAT_SLAB) ? any_hit_scale(A, ray) : 1.0f);
           const WatertightRay wr = make_watertight(ray);
           tbest = ray.tmax; hit.slot = -1; hit.t = ray.tmax; hit.u = 0.f; hit.v = 0.f;
           spa = s_stack; ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
@@ -227,12 +234,18 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
             stsf(rb + 0 * kBlkPitch, ray.ox); stsf(rb + 1 * kBlkPitch, ray.oy); stsf(rb + 2 * kBlkPitch, ray.oz);
             stsf(rb + 3 * kBlkPitch, ray.dx); stsf(rb + 4 * kBlkPitch, ray.dy); stsf(rb + 5 * kBlkPitch, ray.dz);
             stsf(rb + 15 * kBlkPitch, ray.tmax); sts32(rb + 16 * kBlkPitch, (uint32_t)ray.src_slot);
+            if (DSRT_TRI_FAST) {
+              stsf(rb + 17 * kBlkPitch, -(ray.ox * wr.bxx + ray.oy * wr.bxy + ray.oz * wr.bxz));
+              stsf(rb + 18 * kBlkPitch, -(ray.ox * wr.byx + ray.oy * wr.byy + ray.oz * wr.byz));
+              stsf(rb + 19 * kBlkPitch, -(ray.ox * wr.bzx + ray.oy * wr.bzy + ray.oz * wr.bzz));
+            }
             sts8(s_flag_warp + lane, 0u);
           }
           {
             stsf(rb + 6 * kBlkPitch, wr.bxx); stsf(rb + 7 * kBlkPitch, wr.bxy); stsf(rb + 8 * kBlkPitch, wr.bxz);
             stsf(rb + 9 * kBlkPitch, wr.byx); stsf(rb + 10 * kBlkPitch, wr.byy); stsf(rb + 11 * kBlkPitch, wr.byz);
             stsf(rb + 12 * kBlkPitch, wr.bzx); stsf(rb + 13 * kBlkPitch, wr.bzy); stsf(rb + 14 * kBlkPitch, wr.bzz);
+          }
           }
         }
       }
@@ -246,6 +259,8 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
       // (1) node step: open the highest-priority pending internal child, or take the next node group off the stack (at
       // most one group per tree level).  A lane that still holds an untested primitive group waits for the warp's next test
       // (parking such groups on the stack was measured: 2-3 % slower than this simpler loop).
+#pragma unroll
+      for (int step = 0; step < DSRT_NODE_STEPS; step++)
       if (busy && tgroup.y == 0u) {
         if (ngroup.y <= 0x00ffffffu && spa != s_stack) { spa -= kStackPitch; ngroup = lds64(spa); }
         if (ngroup.y > 0x00ffffffu) {
@@ -257,7 +272,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           const uint4* np = A.nodes + (size_t)(ngroup.x + rel) * 5;
           const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
           if (COUNT) cnt.nodes++;
-          const uint32_t m = test_children<false>(ray, fr, n0, n1, n2, n3, n4, tbest, 0.f, A.one_bits);
+          const uint32_t m = test_children<false, ANY && DSRT_SAT_SLAB>(ray, fr, n0, n1, n2, n3, n4, tbest, 0.f, A.one_bits);
           ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
           tgroup = make_uint2(n1.y, drop_source(m & 0x00ffffffu, n1.y, ray.src_slot));
           did_node = true;
@@ -302,8 +317,8 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
                 const int slot = (int)(pw & ((1u << kOwnerShift) - 1u)); const uint32_t s = pw >> kOwnerShift;
                 const uint32_t rb = s_blk_warp + s * 4u;
                 TraceRay r2; WatertightRay w2;
-                r2.ox = ldsf(rb + 0 * kBlkPitch); r2.oy = ldsf(rb + 1 * kBlkPitch); r2.oz = ldsf(rb + 2 * kBlkPitch);
-                r2.dx = r2.dy = r2.dz = 0.f;       // the direction is only needed by the sphere test (loaded there)
+                if (!DSRT_TRI_FAST) { r2.ox = ldsf(rb + 0 * kBlkPitch); r2.oy = ldsf(rb + 1 * kBlkPitch); r2.oz = ldsf(rb + 2 * kBlkPitch); }
+                r2.dx = r2.dy = r2.dz = 0.f;       // origin (fast triangle test) / direction are only needed by the sphere test (loaded there)
                 w2.bxx = ldsf(rb + 6 * kBlkPitch); w2.bxy = ldsf(rb + 7 * kBlkPitch); w2.bxz = ldsf(rb + 8 * kBlkPitch);
                 w2.byx = ldsf(rb + 9 * kBlkPitch); w2.byy = ldsf(rb + 10 * kBlkPitch); w2.byz = ldsf(rb + 11 * kBlkPitch);
                 w2.bzx = ldsf(rb + 12 * kBlkPitch); w2.bzy = ldsf(rb + 13 * kBlkPitch); w2.bzz = ldsf(rb + 14 * kBlkPitch);
@@ -314,8 +329,10 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
                 float t, u, v; bool h;
                 if (b.w != 0.0f) {
                   const float4 cc = DSRT_PRIM_LD(pp + 2);
-                  h = (slot != src2) && hit_triangle(r2, w2, a, b, cc, tmax2, t, u, v);
+                  if (DSRT_TRI_FAST) h = (slot != src2) && hit_triangle_any(ldsf(rb + 17 * kBlkPitch), ldsf(rb + 18 * kBlkPitch), ldsf(rb + 19 * kBlkPitch), w2, a, b, cc, tmax2);
+                  else h = (slot != src2) && hit_triangle(r2, w2, a, b, cc, tmax2, t, u, v);
                 } else {
+                  if (DSRT_TRI_FAST) { r2.ox = ldsf(rb + 0 * kBlkPitch); r2.oy = ldsf(rb + 1 * kBlkPitch); r2.oz = ldsf(rb + 2 * kBlkPitch); }
                   r2.dx = ldsf(rb + 3 * kBlkPitch); r2.dy = ldsf(rb + 4 * kBlkPitch); r2.dz = ldsf(rb + 5 * kBlkPitch);
                   h = hit_sphere(r2, a, b, leaves_sphere(src2, slot), true, tmax2, t);
                 }
@@ -343,7 +360,8 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
               w2.bxx = ldsf(rb + 6 * kBlkPitch); w2.bxy = ldsf(rb + 7 * kBlkPitch); w2.bxz = ldsf(rb + 8 * kBlkPitch);
               w2.byx = ldsf(rb + 9 * kBlkPitch); w2.byy = ldsf(rb + 10 * kBlkPitch); w2.byz = ldsf(rb + 11 * kBlkPitch);
               w2.bzx = ldsf(rb + 12 * kBlkPitch); w2.bzy = ldsf(rb + 13 * kBlkPitch); w2.bzz = ldsf(rb + 14 * kBlkPitch);
-              h = (slot != ray.src_slot) && hit_triangle(ray, w2, a, b, c, tbest, t, u, v);
+              if (ANY && DSRT_TRI_FAST) { h = (slot != ray.src_slot) && hit_triangle_any(ldsf(rb + 17 * kBlkPitch), ldsf(rb + 18 * kBlkPitch), ldsf(rb + 19 * kBlkPitch), w2, a, b, c, tbest); t = 0.f; }
+              else h = (slot != ray.src_slot) && hit_triangle(ray, w2, a, b, c, tbest, t, u, v);
             } else {
               h = hit_sphere(ray, a, b, leaves_sphere(ray.src_slot, slot), ANY, tbest, t);
             }
@@ -396,9 +414,12 @@ __device__ __forceinline__ void add_rgb(float* accum, uint32_t pix, V3 c) {
 
 // One thread per queued path: PathTracer::trace_ray after the closest-hit query (shade_path, shade.cuh)
 struct QueueSink {
-  ShadowQueue sq; uint32_t base; int nh, rank;
+  ShadowQueue sq; uint32_t base; int nh, rank; int skip_null; uint32_t nulls;
   __device__ __forceinline__ void shadow(int j, float4 a, float4 b, float4 c) {
     const uint32_t e = base + (uint32_t)(j * nh + rank);     // sample-major within the warp's block
+    // "skip_null_shadow" (off by default: the reference traces every shadow ray before it looks at the BSDF / cosine,
+    // pathtracer.cpp:497-504): a ray that cannot add light keeps its queue slot but is marked with tmax = -1, k_trace drops it
+    if (skip_null && c.x == 0.f && c.y == 0.f && c.z == 0.f) { a.w = -1.f; nulls++; }
     sq.a[e] = a; sq.b[e] = b; sq.c[e] = c;
   }
 };
@@ -408,8 +429,9 @@ struct QueueSink {
 __global__ void __launch_bounds__(128, DSRT_SHADE_MIN_CTAS) k_shade(PathState ps, const float4* __restrict__ prims, SceneDev sc, RenderParams rp,
                                                const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
                                                PathState dst, uint32_t* next_queue, uint32_t* next_count, uint32_t dst_cap,
-                                               ShadowQueue sq, uint32_t* s_count, float* accum) {
+                                               ShadowQueue sq, uint32_t* s_count, float* accum, Totals* totals) {
   const uint32_t n = *n_ptr;
+  uint32_t nulls = 0;
   const int lane = threadIdx.x & 31;
   const bool in_place = dst.ray_o == ps.ray_o;
   for (uint32_t kb = blockIdx.x * blockDim.x; kb < n; kb += gridDim.x * blockDim.x) {
@@ -421,6 +443,7 @@ __global__ void __launch_bounds__(128, DSRT_SHADE_MIN_CTAS) k_shade(PathState ps
     const bool hitp = live && __float_as_int(in.hit.w) >= 0;
     const unsigned hm = __ballot_sync(kFull, hitp);
     QueueSink sink; sink.sq = sq; sink.base = 0; sink.nh = __popc(hm); sink.rank = __popc(hm & ((1u << lane) - 1u));
+    sink.skip_null = rp.skip_null_shadow; sink.nulls = 0;
     if (hm && sc.n_light_samples > 0) {
       const int leader = __ffs(hm) - 1;
       if (lane == leader) sink.base = atomicAdd(s_count, (uint32_t)(sink.nh * sc.n_light_samples));
@@ -439,6 +462,7 @@ __global__ void __launch_bounds__(128, DSRT_SHADE_MIN_CTAS) k_shade(PathState ps
       const int depth = __float_as_int(in.thr.w) & 0xff;       // Ray::depth travels with the path
       shade_path(in, prims, sc, rp.seed, rp.max_depth, depth, out, sink);
       if (out.has_emission) add_rgb(accum, in.pix, out.emission);
+      nulls += sink.nulls;
     }
     const unsigned cm = __ballot_sync(kFull, out.cont);
     if (cm) {
@@ -457,6 +481,10 @@ __global__ void __launch_bounds__(128, DSRT_SHADE_MIN_CTAS) k_shade(PathState ps
         }
       }
     }
+  }
+  if (rp.skip_null_shadow) {
+    for (int o = 16; o; o >>= 1) nulls += __shfl_xor_sync(kFull, nulls, o);
+    if (lane == 0 && nulls) atomicAdd(&totals->null_shadow, (unsigned long long)nulls);
   }
 }
 

@@ -106,6 +106,36 @@ DSRT_HD bool hit_triangle(const TraceRay& r, const WatertightRay& w, const float
   return true;
 }
 
+// Any-hit form of the same test for the cooperative shadow-ray path (DSRT_TRI_FAST): the translation by the ray origin is
+// folded into the start of each FMA chain (po = -(o . basis row), computed once per ray), which removes the nine subtractions
+// per triangle, and the division is replaced by a sign-corrected comparison 0 < T sgn(det) < tmax |det|.  A vertex still maps
+// to the same (x, y) whichever triangle it is reached through, and the edge products are still rounded separately, so
+// adjacent triangles stay crack-free; only (t, u, v), which an any-hit query does not return, lose the benefit of the
+// exact vertex - origin difference.
+DSRT_HD bool hit_triangle_any(float pox, float poy, float poz, const WatertightRay& w, const float4 a, const float4 b,
+                              const float4 c, float tmax) {
+  const float Ax = hd_fma(a.z, w.bxz, hd_fma(a.y, w.bxy, hd_fma(a.x, w.bxx, pox))), Ay = hd_fma(a.z, w.byz, hd_fma(a.y, w.byy, hd_fma(a.x, w.byx, poy)));
+  const float Bx = hd_fma(b.z, w.bxz, hd_fma(b.y, w.bxy, hd_fma(b.x, w.bxx, pox))), By = hd_fma(b.z, w.byz, hd_fma(b.y, w.byy, hd_fma(b.x, w.byx, poy)));
+  const float Cx = hd_fma(c.z, w.bxz, hd_fma(c.y, w.bxy, hd_fma(c.x, w.bxx, pox))), Cy = hd_fma(c.z, w.byz, hd_fma(c.y, w.byy, hd_fma(c.x, w.byx, poy)));
+  float U = hd_sub(hd_mul(Cx, By), hd_mul(Cy, Bx));
+  float V = hd_sub(hd_mul(Ax, Cy), hd_mul(Ay, Cx));
+  float W = hd_sub(hd_mul(Bx, Ay), hd_mul(By, Ax));
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    U = (float)hd_dsub(hd_dmul((double)Cx, (double)By), hd_dmul((double)Cy, (double)Bx));
+    V = (float)hd_dsub(hd_dmul((double)Ax, (double)Cy), hd_dmul((double)Ay, (double)Cx));
+    W = (float)hd_dsub(hd_dmul((double)Bx, (double)Ay), hd_dmul((double)By, (double)Ax));
+  }
+  if (fminf(fminf(U, V), W) < 0.0f && fmaxf(fmaxf(U, V), W) > 0.0f) return false;
+  const float det = U + V + W;
+  if (det == 0.0f) return false;
+  const float Az = hd_fma(a.z, w.bzz, hd_fma(a.y, w.bzy, hd_fma(a.x, w.bzx, poz)));
+  const float Bz = hd_fma(b.z, w.bzz, hd_fma(b.y, w.bzy, hd_fma(b.x, w.bzx, poz)));
+  const float Cz = hd_fma(c.z, w.bzz, hd_fma(c.y, w.bzy, hd_fma(c.x, w.bzx, poz)));
+  const float T = U * Az + V * Bz + W * Cz;
+  const float Ts = hd_u2f(hd_f2u(T) ^ (hd_f2u(det) & 0x80000000u));     // T * sgn(det)
+  return Ts > 0.0f && Ts < tmax * fabsf(det);
+}
+
 // Sphere::test / intersect semantics (sphere.cpp:10-77) in float.  A ray that STARTS on this sphere (src)
 // has one root at ~0: the reference rejects it with t > min_t thanks to its 1e-11 origin offset; in float
 // that root is resolved analytically (inward -> far root 2b, outward -> miss).
@@ -185,13 +215,15 @@ struct NodeFrame {   // per-ray constants
   bool nx, ny, nz;       // direction component is negative: the near plane of a slab is its HIGH plane
 };
 
-DSRT_HD NodeFrame make_frame(const TraceRay& r) {
+// t_scale != 1: the node test then works in units of 1 / t_scale (the saturating any-hit test uses t_scale = 1 / tmax, so
+// that the ray's valid range [0, tmax] becomes [0, 1])
+DSRT_HD NodeFrame make_frame(const TraceRay& r, float t_scale = 1.0f) {
   NodeFrame f;
   const float eps = 1.0e-24f;
   const float dx = fabsf(r.dx) > eps ? r.dx : copysignf(eps, r.dx);
   const float dy = fabsf(r.dy) > eps ? r.dy : copysignf(eps, r.dy);
   const float dz = fabsf(r.dz) > eps ? r.dz : copysignf(eps, r.dz);
-  f.idx = hd_rcp(dx); f.idy = hd_rcp(dy); f.idz = hd_rcp(dz);
+  f.idx = hd_rcp(dx) * t_scale; f.idy = hd_rcp(dy) * t_scale; f.idz = hd_rcp(dz) * t_scale;
   f.nx = dx < 0.0f; f.ny = dy < 0.0f; f.nz = dz < 0.0f;
   const uint32_t oct = (f.nx ? 1u : 0u) | (f.ny ? 2u : 0u) | (f.nz ? 4u : 0u);
   f.octinv = 7u - oct;
@@ -216,7 +248,14 @@ DSRT_HD float byte_unit(uint32_t w, int i, uint32_t one) {
 // min/max).  Float rounding of the dequantised planes (<= 2^-9 quantum) is covered by the 1/64-quantum margin the
 // host puts on every quantised plane (wide_bvh.cpp), so no widening is needed here; empty slots need no test
 // because their meta byte contributes no bits.  pad > 0 only in parity mode (extra conservative slabs).
-template <bool PARITY>
+//
+// SAT (any-hit rays, DSRT_SAT_SLAB): the frame is pre-scaled by 1 / tmax (make_frame's t_scale), so the ray's valid range is
+// [0, 1] and every plane distance is evaluated with ONE saturating FMA: the clamp to [0, 1] replaces max(near, 0) and
+// min(far, tmax), i.e. two of the five min/max/compare instructions per child (the ALU pipe is the busiest pipe of k_trace).
+// The comparison becomes strict (near < far): a box entirely behind the origin (far clamps to 0) or entirely beyond tmax
+// (near clamps to 1) then fails as it must.  Strictness cannot lose a real hit: every quantised box contains its exact box
+// with >= 1/64 quantum to spare on each side, so a ray that touches the contents has near < far by >= 1/32 quantum of t.
+template <bool PARITY, bool SAT = false>
 DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uint4 n0, const uint4 n1,
                                                   const uint4 n2, const uint4 n3, const uint4 n4, float tmax, float pad, uint32_t one) {
   const float ox = hd_u2f(n0.x), oy = hd_u2f(n0.y), oz = hd_u2f(n0.z);
@@ -251,12 +290,21 @@ DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uin
     const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const float ax = hd_fma(byte_unit(nearx, i, one), sx, bnx), bx = hd_fma(byte_unit(farx, i, one), sfx, bfx);
-      const float ay = hd_fma(byte_unit(neary, i, one), sy, bny), by = hd_fma(byte_unit(fary, i, one), sfy, bfy);
-      const float az = hd_fma(byte_unit(nearz, i, one), sz, bnz), bz = hd_fma(byte_unit(farz, i, one), sfz, bfz);
-      const float tn = fmaxf(fmaxf(ax, ay), fmaxf(az, 0.0f));
-      const float tf = fminf(fminf(bx, by), fminf(bz, tmax));
-      if (tn <= tf) mask |= ((child_bits4 >> (8 * i)) & 0xffu) << ((bit_index4 >> (8 * i)) & 0xffu);
+      bool hit;
+      if (SAT && !PARITY) {
+        const float ax = hd_fma_sat(byte_unit(nearx, i, one), sx, bnx), bx = hd_fma_sat(byte_unit(farx, i, one), sfx, bfx);
+        const float ay = hd_fma_sat(byte_unit(neary, i, one), sy, bny), by = hd_fma_sat(byte_unit(fary, i, one), sfy, bfy);
+        const float az = hd_fma_sat(byte_unit(nearz, i, one), sz, bnz), bz = hd_fma_sat(byte_unit(farz, i, one), sfz, bfz);
+        hit = fmaxf(fmaxf(ax, ay), az) < fminf(fminf(bx, by), bz);
+      } else {
+        const float ax = hd_fma(byte_unit(nearx, i, one), sx, bnx), bx = hd_fma(byte_unit(farx, i, one), sfx, bfx);
+        const float ay = hd_fma(byte_unit(neary, i, one), sy, bny), by = hd_fma(byte_unit(fary, i, one), sfy, bfy);
+        const float az = hd_fma(byte_unit(nearz, i, one), sz, bnz), bz = hd_fma(byte_unit(farz, i, one), sfz, bfz);
+        const float tn = fmaxf(fmaxf(ax, ay), fmaxf(az, 0.0f));
+        const float tf = fminf(fminf(bx, by), fminf(bz, tmax));
+        hit = tn <= tf;
+      }
+      if (hit) mask |= ((child_bits4 >> (8 * i)) & 0xffu) << ((bit_index4 >> (8 * i)) & 0xffu);
     }
   }
   return mask;
@@ -271,13 +319,34 @@ struct Accel {
   const double* __restrict__ prims64;      // 12 doubles per slot (parity only)
   float pad;                               // parity slab padding
   uint32_t one_bits;                       // 0x3f800000, see byte_unit()
+  float bcx, bcy, bcz, brad;               // sphere around the root box: bounds the reach of rays with tmax = inf
 };
+
+#ifndef DSRT_TRI_FAST
+#define DSRT_TRI_FAST 1                    // any-hit triangle test with the origin folded into the FMA chains (hit_triangle_any)
+#endif
+#ifndef DSRT_SAT_SLAB
+#define DSRT_SAT_SLAB 1                    // saturating node test for any-hit rays (see test_children)
+#endif
+// 1 / (effective tmax) of an any-hit ray: tmax itself, or the far side of the scene's bounding sphere when tmax is infinite
+// (directional / hemisphere / environment lights).  A ray with tmax <= 0 gets a huge scale: every box then clamps to a miss.
+DSRT_HD float any_hit_scale(const Accel& A, const TraceRay& r) {
+  const float cx = A.bcx - r.ox, cy = A.bcy - r.oy, cz = A.bcz - r.oz;
+  // in units of |d| (directions handed to dsrt_trace_any need not be normalised)
+  const float reach = (sqrtf(cx * cx + cy * cy + cz * cz) + A.brad) * hd_rsqrt(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz) * 1.0001f;
+  return hd_rcp(fmaxf(fminf(r.tmax, reach), 1.0e-30f));
+}
 
 template <bool ANY, bool PARITY, bool COUNT>
 DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, uint2* stack, int stride,
                                           TraceHit& hit, double* t64_out, TraceCounters* cnt) {
-  const NodeFrame fr = make_frame(ray);
+  constexpr bool SAT = ANY && !PARITY && DSRT_SAT_SLAB;
+  const NodeFrame fr = make_frame(ray, SAT ? any_hit_scale(A, ray) : 1.0f);
   const WatertightRay wr = make_watertight(ray);
+  constexpr bool FAST = ANY && !PARITY && DSRT_TRI_FAST;
+  const float pox = FAST ? -(ray.ox * wr.bxx + ray.oy * wr.bxy + ray.oz * wr.bxz) : 0.f;
+  const float poy = FAST ? -(ray.ox * wr.byx + ray.oy * wr.byy + ray.oz * wr.byz) : 0.f;
+  const float poz = FAST ? -(ray.ox * wr.bzx + ray.oy * wr.bzy + ray.oz * wr.bzz) : 0.f;
   float tbest = ray.tmax;
   double tbest64 = PARITY ? (double)ray.tmax : 0.0;
   hit.slot = -1; hit.t = ray.tmax; hit.u = 0.f; hit.v = 0.f;
@@ -294,7 +363,7 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
       const uint4* np = A.nodes + (size_t)(ngroup.x + rel) * 5;
       const uint4 n0 = hd_ldg(np), n1 = hd_ldg(np + 1), n2 = hd_ldg(np + 2), n3 = hd_ldg(np + 3), n4 = hd_ldg(np + 4);
       if (COUNT) cnt->nodes++;
-      const uint32_t m = test_children<PARITY>(ray, fr, n0, n1, n2, n3, n4, tbest, A.pad, A.one_bits);
+      const uint32_t m = test_children<PARITY, SAT>(ray, fr, n0, n1, n2, n3, n4, tbest, A.pad, A.one_bits);
       ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
       tgroup = make_uint2(n1.y, drop_source(m & 0x00ffffffu, n1.y, ray.src_slot));
     } else {
@@ -318,7 +387,8 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
         float t, u = 0.f, v = 0.f; bool h;
         if (b.w != 0.0f) {
           const float4 c = hd_ldg(pp + 2);
-          h = (slot != ray.src_slot) && hit_triangle(ray, wr, a, b, c, tbest, t, u, v);
+          if (FAST) { h = (slot != ray.src_slot) && hit_triangle_any(pox, poy, poz, wr, a, b, c, tbest); t = 0.f; }
+          else h = (slot != ray.src_slot) && hit_triangle(ray, wr, a, b, c, tbest, t, u, v);
         } else {
           h = hit_sphere(ray, a, b, leaves_sphere(ray.src_slot, slot), ANY, tbest, t);
         }

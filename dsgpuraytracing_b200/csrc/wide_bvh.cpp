@@ -257,10 +257,19 @@ int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_pri
       BNode& n = T[i];
       for (int k = 0; k < 3; k++) { n.box.lo[k] = b2.node_bbox[6 * i + k]; n.box.hi[k] = b2.node_bbox[6 * i + 3 + k]; }
       n.start = b2.node_start[i]; n.range = b2.node_range[i]; n.l = b2.node_left[i]; n.r = b2.node_right[i];
-      if (n.start < 0 || n.range < 0 || n.start + n.range > n_prims || n.l >= b2.n_nodes || n.r >= b2.n_nodes) bad.store((int)i);
+      if (n.start < 0 || n.range < 0 || (int64_t)n.start + (int64_t)n.range > (int64_t)n_prims || n.l >= b2.n_nodes || n.r >= b2.n_nodes) bad.store((int)i);
+      // a child always has a larger index than its parent (pre-order numbering of the builder and of the reference's dump):
+      // no node can then be its own ancestor, so every walk below terminates; children split the parent's range in two
+      else if (n.l >= 0 || n.r >= 0) {
+        if (n.l <= (int)i || n.r <= (int)i) bad.store((int)i);
+        else {
+          const int64_t ls = b2.node_start[n.l], lr = b2.node_range[n.l], rs = b2.node_start[n.r], rr = b2.node_range[n.r];
+          if (ls != n.start || lr < 0 || rr < 0 || rs != ls + lr || lr + rr != n.range) bad.store((int)i);
+        }
+      }
     }
   });
-  if (bad.load() >= 0) { err = "dsrt_set_bvh: node " + std::to_string(bad.load()) + " is out of range"; return DSRT_ERR_INVALID; }
+  if (bad.load() >= 0) { err = "dsrt_set_bvh: node " + std::to_string(bad.load()) + " is out of range, is not numbered after its parent, or its children do not partition its primitives"; return DSRT_ERR_INVALID; }
   {
     std::vector<int> leaves; std::vector<size_t> base;
     size_t total = T.size();

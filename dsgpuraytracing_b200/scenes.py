@@ -125,10 +125,21 @@ def mesh_arrays(V, F):
     return V[F].reshape(-1, 9), N[F].reshape(-1, 9)
 
 
+def _as_loaded(tri):
+    """What the .dae route does to a triangle list (n, 9): positions pass through a float32 text field (collada.cpp:621-636),
+    and the half-edge mesh hands each face back starting from its LAST file vertex (v2, v0, v1)."""
+    t = np.asarray(tri, float).reshape(-1, 3, 3)
+    return np.roll(t, 1, axis=1).reshape(-1, 9)
+
+
 def cb_mesh_scene(V, F, mesh_bsdf=(0, (0.5, 0.5, 0.5), (0, 0, 0), 0.0)):
-    """Cornell box + one mesh object (the mesh comes first, as in CBbunny.dae / CBdragon.dae)."""
+    """Cornell box + one mesh object (the mesh comes first, as in CBbunny.dae / CBdragon.dae).  Same primitive order,
+    vertex rotation and positions as write_cb_mesh_dae() + the .dae loader give (tests/test_host.py checks positions for
+    equality and the half-edge vertex normals to 1 ulp); V must already be float32-representable."""
     mp, mn = mesh_arrays(V, F)
     bp, bn, bb, bt, bpar, lt, lp = cornell_box()
+    mp, mn, bn = _as_loaded(mp), _as_loaded(mn), _as_loaded(bn)
+    bp = _as_loaded(np.asarray(bp, np.float32).astype(np.float64))
     nm = len(mp)
     btype, a, b, ior = mesh_bsdf
     bsdf_type = np.concatenate([[btype], bt]).astype(np.int32)
@@ -147,14 +158,46 @@ def cbdragon_standin(W=1920, H=1080):
     """Stand-in for BASELINE.json configs[1] (CBdragon.dae is missing from the checkout): Cornell box + a
     100 012-triangle closed diffuse mesh, cam_dragon.info.  Returns (scene arrays, camera)."""
     V, F = torus_knot()
+    V = V.astype(np.float32).astype(np.float64)         # what survives the .dae's float text fields
     return cb_mesh_scene(V, F), cam_dragon(W, H)
 
 
 def cblucy_standin(W=1920, H=1080):
     """Stand-in for configs[2] (CBlucy.dae missing): 133 796 triangles = 22 x 3041 tube... uses glass (ior 1.45)."""
     V, F = torus_knot(n_around=26, n_along=2573, tube=0.05)      # 133 796 triangles
+    V = V.astype(np.float32).astype(np.float64)
     sc = cb_mesh_scene(V, F, mesh_bsdf=(3, (1, 1, 1), (1, 1, 1), 1.45))
     return sc, cam_dragon(W, H)
+
+
+STANDINS = {
+    # name: (mesh generator kwargs, mesh BSDF (type, a, b, ior))
+    "cbdragon_standin": (dict(), (0, (0.5, 0.5, 0.5), (0, 0, 0), 0.0)),
+    "cblucy_standin": (dict(n_around=26, n_along=2573, tube=0.05), (3, (1, 1, 1), (1, 1, 1), 1.45)),
+}
+
+
+def write_standin(name, directory, W=1920, H=1080):
+    """Writes <directory>/<name>.dae + cam_dragon.info for a stand-in scene; returns (dae path, camera-file path).
+    Both arms of bench.py and the parity tests start from these two files: the reference through its own ColladaParser,
+    the product through csrc/host/scene_loader.cpp."""
+    import os
+    kw, bsdf = STANDINS[name]
+    V, F = torus_knot(**kw)
+    V = V.astype(np.float32).astype(np.float64)
+    dae = os.path.join(directory, name + ".dae"); cam = os.path.join(directory, "cam_dragon.info")
+    write_cb_mesh_dae(dae, V, F, mesh_bsdf=bsdf)
+    write_cam_info(cam, cam_dragon(W, H))
+    return dae, cam
+
+
+def load_standin(name, W=1920, H=1080):
+    """Stand-in scene through the .dae import path (product loader): (scene arrays, camera)."""
+    import tempfile
+    from . import load_dae
+    with tempfile.TemporaryDirectory() as td:
+        dae, cam = write_standin(name, td, W, H)
+        return load_dae(dae, W, H, cam)
 
 
 def triangle_soup(n_tris, seed=0x5EED, W=3840, H=2160):

@@ -77,6 +77,8 @@ typedef struct {
   double shade_seconds;       /* summed CUDA-event time of generate + shade launches */
   uint32_t kernel_launches;   /* kernels launched by this call */
   uint32_t batches;
+  uint64_t null_shadow_rays;  /* option "skip_null_shadow": shadow rays (counted in shadow_rays) that were NOT traced because
+                               * their contribution is exactly zero; 0 when the option is off (the reference traces them) */
 } dsrt_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------------------ */
@@ -116,7 +118,11 @@ int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t
  * "max_ctas_per_sm" (caps the persistent grid; 0 = what fits), "smem_carveout_pct" (shared-memory carve-out of the
  * traversal kernels, -1 = driver default, which measured best), "collapse_prim_cost_pct" (SAH cost of a primitive test
  * relative to a wide-node visit in the collapse, percent; default 100; applies at the next dsrt_build_accel),
- * "skip_null_shadow" */
+ * "skip_null_shadow" (0/1, default 0: the reference traces every shadow ray before it evaluates the BSDF and the cosine,
+ * src/pathtracer.cpp:497-519; 1 = shadow rays whose contribution is exactly zero -- light behind the surface, non-diffuse
+ * BSDF, emitter facing away -- keep their queue slot but are not traced; the image is identical, dsrt_stats.null_shadow_rays
+ * says how many), "wavefront_budget_mb" (cap on the wavefront + pool memory, 0 = 80 % of the free device memory: the batch
+ * and the pool group shrink to fit, whatever -l asks for) */
 int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value);
 
 /* Host SAH builder = BVHAccel::BVHAccel + buildBVH (src/bvh.cpp:21-202: 32 buckets, max leaf 4, with the

@@ -26,6 +26,7 @@ struct Walk {
   int n_light_samples = 0;
   int env_w = 0, env_h = 0; std::vector<float> env_rgb, env_tp, env_t, env_pgt;
   double scene_diag = 1;
+  float bsphere[4] = {0, 0, 0, 0};
   Camera cam;
   std::string err;
 };
@@ -33,6 +34,7 @@ struct Walk {
 static Accel accel_of(const Walk* w, bool parity) {
   Accel A; A.nodes = (const uint4*)w->wide.nodes.data(); A.prims = (const float4*)w->recs.data();
   A.prims64 = (const double*)w->r64.data(); A.pad = parity ? (float)(1e-5 * w->scene_diag) : 0.f; A.one_bits = 0x3f800000u;
+  A.bcx = w->bsphere[0]; A.bcy = w->bsphere[1]; A.bcz = w->bsphere[2]; A.brad = w->bsphere[3];
   return A;
 }
 
@@ -50,6 +52,7 @@ Walk* cw_create(const dsrt_scene* s, const dsrt_bvh2* b, int ns_area_light, int 
   Box3 all; all.reset(); for (auto& p : pbox) all.grow(p);
   double dg = 0; for (int k = 0; k < 3; k++) { double e = s->n_prims ? all.hi[k] - all.lo[k] : 0, m = s->n_prims ? fmax(fabs(all.lo[k]), fabs(all.hi[k])) : 0; dg += (e + m) * (e + m); }
   w->scene_diag = sqrt(dg) + 1.0;
+  bounding_sphere(all, s->n_prims, w->bsphere);
   return w;
 }
 void cw_destroy(Walk* w) { delete w; }

@@ -20,3 +20,23 @@ ID_RES = (240, 180)        # primary-hit id maps
 SMALL_RES = (96, 72)       # bit-exact rand()-driven render, 2 spp, seed 1
 RMSE_RES = (160, 120)      # 1024-spp reference renders for the image gate
 RMSE_SPP = 1024
+
+# ---- the MEASURED workloads (bench.py, profiles/r2_configs.md): stand-ins for the scene files that are missing from the
+# reference checkout (dsgpuraytracing_b200/scenes.py) -> fixtures tests/golden/standin_<name>.npz (make_golden_standin.py)
+STANDIN_CONFIGS = {
+    "cbdragon_standin": dict(nl=4, depth=8),      # BASELINE.json configs[1]: the bench workload
+    "cblucy_standin": dict(nl=4, depth=8),        # configs[2]: glass mesh
+}
+STANDIN_ID_RES = (480, 270)
+
+
+def scene_sha(arrays):
+    """sha256 over the flat scene arrays (dtype-normalised) -- pins that two routes produced the SAME scene, bit for bit."""
+    import hashlib
+    import numpy as np
+    h = hashlib.sha256()
+    for k, dt in (("prim_type", np.int32), ("prim_bsdf", np.int32), ("tri_pos", np.float64), ("tri_nrm", np.float64),
+                  ("sphere", np.float64), ("bsdf_type", np.int32), ("bsdf_param", np.float32), ("light_type", np.int32),
+                  ("light_param", np.float64)):
+        h.update(np.ascontiguousarray(arrays[k], dtype=dt).tobytes())
+    return h.hexdigest()

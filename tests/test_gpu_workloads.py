@@ -1,0 +1,256 @@
+"""Parity on the workloads that are actually MEASURED (bench.py, profiles/r2_configs.md): the CBdragon / CBlucy stand-ins
+(through the .dae both arms start from), BASELINE configs[0] at its own 480x360, the 1 Mi-triangle soup, plus the memory
+sizing of the wavefront.  Fixtures: tests/golden/standin_*.npz, c1_fullres.npz, soup1m.npz (tests/golden/make_golden_standin.py,
+from the compiled reference and the pinned oracle port).  Everything goes through the C ABI; the oracle only checks.
+
+Set DSRT_PARITY_LOG=<file> to append one JSON line per gate with the measured figures (profiles/r2_parity.md is built from it)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import dsgpuraytracing_b200 as D
+from dsgpuraytracing_b200 import scenes as S
+from oracle import oracle as O
+from tests.scenes import CONFIGS, RMSE_RES, RMSE_SPP, SMALL_RES, STANDIN_CONFIGS, STANDIN_ID_RES, scene_sha
+from tests.util import images_match
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STANDINS = list(STANDIN_CONFIGS)
+
+
+def plog(**kw):
+    p = os.environ.get("DSRT_PARITY_LOG")
+    if p:
+        with open(p, "a") as f:
+            f.write(json.dumps(kw) + "\n")
+
+
+def fixture(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+_scene_cache = {}
+
+
+def standin(name):
+    if name not in _scene_cache:
+        _scene_cache[name] = S.load_standin(name, *STANDIN_ID_RES)[0]
+    return _scene_cache[name]
+
+
+def block_mean(a, k):
+    H, W, _ = a.shape
+    return a[:H // k * k, :W // k * k].reshape(H // k, k, W // k, k, 3).mean(axis=(1, 3))
+
+
+# ---- CPU: both arms render the SAME scene ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", STANDINS)
+def test_standin_scene_is_bit_identical_on_both_arms(name, tmp_path):
+    """The .dae written for the reference arm, loaded by the PRODUCT loader, hashes to what the REFERENCE's ColladaParser +
+    half-edge mesh produced from the same file when the fixture was made (primitive order, vertex rotation, positions,
+    vertex normals, BSDFs, light); the flat-array generator agrees in order / rotation / positions and to 1 ulp in normals."""
+    fx = fixture("standin_" + name)
+    sc = standin(name)
+    assert scene_sha(sc) == bytes(fx["scene_sha"]).decode()
+    flat = (S.cbdragon_standin if name == "cbdragon_standin" else S.cblucy_standin)(*STANDIN_ID_RES)[0]
+    for k in ("prim_type", "prim_bsdf", "tri_pos", "sphere", "bsdf_type", "bsdf_param", "light_type", "light_param"):
+        assert np.array_equal(np.asarray(sc[k]).reshape(-1), np.asarray(flat[k]).reshape(-1)), k
+    assert np.abs(np.asarray(sc["tri_nrm"]).reshape(-1) - np.asarray(flat["tri_nrm"]).reshape(-1)).max() <= 4.5e-16
+    if O.have_reference():      # live: the compiled reference on the freshly written file
+        dae, cam = S.write_standin(name, str(tmp_path), *STANDIN_ID_RES)
+        d = O.run_reference(dae, *STANDIN_ID_RES, cam=cam, dump_scene=True)
+        assert scene_sha(d) == bytes(fx["scene_sha"]).decode()
+        assert np.array_equal(d["camera"], fx["camera"])
+
+
+# ---- gate 1 on the measured scenes ------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", STANDINS)
+def test_standin_primary_ids_bit_exact(name, core):
+    fx = fixture("standin_" + name); cfg = STANDIN_CONFIGS[name]
+    sc = standin(name)
+    core.set_params(1, cfg["nl"], cfg["depth"], 0)
+    core.load(sc, camera=fx["camera"])
+    ids, ts = core.primary_hits(mode=1)
+    ok = ~fx["hit_tie"].astype(bool)
+    assert np.array_equal(ids[ok], fx["hit_id"][ok]), f"{(ids != fx['hit_id'])[ok].sum()} id mismatches"
+    assert np.array_equal(ts[ok], fx["hit_t"][ok])
+    ids0, ts0 = core.primary_hits(mode=0)             # production float kernel: bounded, and recorded
+    flips = int((ids0 != fx["hit_id"]).sum())
+    plog(gate="ids", scene=name, res=list(STANDIN_ID_RES), parity_kernel_mismatches=0, ties=int(fx["hit_tie"].sum()),
+         production_float_kernel_mismatches=flips, pixels=int(ids.size))
+    assert flips <= 2e-4 * ids.size, flips
+    # one full 1920x1080 map
+    core.set_camera(fx["camera_full"])
+    idf, tf = core.primary_hits(mode=1)
+    bad = np.argwhere(idf != fx["hit_id_full"])
+    if len(bad):        # only an exact tie may differ: brute-force those pixels
+        o = O.Scene(dict(sc, camera=fx["camera_full"]))
+        for (y, x) in bad[:50]:
+            ro, rd = O.generate_ray(fx["camera_full"], (x + 0.5) / 1920, (y + 0.5) / 1080)
+            pid, t = o.closest_hit_brute(ro, rd)
+            assert tf[y, x] == t, (y, x, idf[y, x], fx["hit_id_full"][y, x])
+        assert len(bad) <= 50
+    else:
+        assert hashlib.sha256(np.ascontiguousarray(tf).tobytes()).hexdigest() == bytes(fx["hit_t_full_sha"]).decode()
+    plog(gate="ids_full", scene=name, res=[1920, 1080], mismatches=int(len(bad)), pixels=int(idf.size))
+
+
+@pytest.mark.gpu
+def test_c1_at_its_baseline_resolution(core):
+    """BASELINE.json configs[0] as quoted: CBspheres_lambertian 480x360, 16 spp, 4 light samples, depth 5."""
+    fx = fixture("c1_fullres"); g = fixture("CBspheres_lambertian"); cfg = CONFIGS["CBspheres_lambertian"]
+    core.set_params(16, cfg["nl"], cfg["depth"], 7)
+    core.load(g, camera=fx["camera"])
+    ids, ts = core.primary_hits(mode=1)
+    ok = ~fx["hit_tie"].astype(bool)
+    assert np.array_equal(ids[ok], fx["hit_id"][ok]) and np.array_equal(ts[ok], fx["hit_t"][ok])
+    ids0, _ = core.primary_hits(mode=0)
+    rgb, st = core.render()
+    ref, cnt = O.Scene(g).with_camera(fx["camera"]).render(480, 360, 16, cfg["nl"], cfg["depth"], rng="philox", seed=7)
+    okimg, info = images_match(rgb, ref)
+    plain = float((np.sqrt(((rgb - ref) ** 2).mean(axis=(0, 1))) / ref.mean(axis=(0, 1))).max())
+    plog(gate="c1_480x360_16spp", production_float_kernel_mismatches=int((ids0 != fx["hit_id"]).sum()), plain_rel_rmse=plain, **info,
+         extend=[int(st.extend_rays), int(cnt[0])], shadow=[int(st.shadow_rays), int(cnt[1])])
+    assert okimg, info
+    assert abs(int(st.extend_rays) - int(cnt[0])) <= 2e-4 * cnt[0] + 2 and abs(int(st.shadow_rays) - int(cnt[1])) <= 2e-4 * cnt[1] + 8
+
+
+@pytest.mark.gpu
+def test_soup_1mi_primary_ids(core):
+    """Config 5's generator at 1 Mi triangles: closest-hit ids / t of the production wide BVH (parity kernel) == the oracle
+    port's BVHAccel::intersect restatement on its own reference-order SAH tree (fixture soup1m.npz)."""
+    fx = fixture("soup1m")
+    W, H = STANDIN_ID_RES
+    sc, cam = S.triangle_soup(1 << 20, W=W, H=H)
+    assert np.array_equal(cam, fx["camera"])
+    core.set_params(1, 1, 8, 0)
+    core.load(sc, camera=cam)
+    ids, ts = core.primary_hits(mode=1)
+    bad = np.argwhere(ids != fx["hit_id"])
+    plog(gate="ids", scene="soup1m", res=[W, H], parity_kernel_mismatches=int(len(bad)), pixels=int(ids.size),
+         production_float_kernel_mismatches=int((core.primary_hits(mode=0)[0] != fx["hit_id"]).sum()))
+    assert len(bad) <= 4                          # exact ties only (the fixture carries no brute-force tie mask at this size)
+    same = ids == fx["hit_id"]
+    assert np.array_equal(ts[same], fx["hit_t"][same])
+    for (y, x) in bad:
+        assert ts[y, x] == fx["hit_t"][y, x]      # a tie: same t, different primitive
+
+
+# ---- gate 2 on the measured scenes ------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", STANDINS)
+def test_standin_render_matches_oracle_path_by_path(name, core):
+    fx = fixture("standin_" + name); cfg = STANDIN_CONFIGS[name]
+    sc = standin(name)
+    W, H = 240, 135
+    cam = fx["camera"].copy(); cam[14] *= H / cam[13]; cam[12], cam[13] = W, H
+    ref, cnt = O.Scene(dict(sc, camera=cam)).render(W, H, 8, cfg["nl"], cfg["depth"], rng="philox", seed=11)
+    core.set_params(8, cfg["nl"], cfg["depth"], 11)
+    core.load(sc, camera=cam)
+    rgb, st = core.render()
+    ok, info = images_match(rgb, ref)
+    plog(gate="philox_8spp", scene=name, res=[W, H], **info, extend=[int(st.extend_rays), int(cnt[0])], shadow=[int(st.shadow_rays), int(cnt[1])])
+    assert ok, info
+    assert abs(int(st.extend_rays) - int(cnt[0])) <= 2e-4 * cnt[0] + 2
+    assert abs(int(st.shadow_rays) - int(cnt[1])) <= 2e-4 * cnt[1] + 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", STANDINS)
+def test_standin_image_gate_1024spp(name, core):
+    """north_star gate 2 on the bench scene: per-channel RMSE < 1 % of mean radiance at 1024 spp.  The plain figure, the
+    flipped-pixel count, the masked figure and the reference-vs-reference floor are all recorded."""
+    fx = fixture("standin_" + name); cfg = STANDIN_CONFIGS[name]
+    sc = standin(name)
+    core.set_params(RMSE_SPP, cfg["nl"], cfg["depth"], 0)
+    core.load(sc, camera=fx["ref_camera"])
+    rgb, st = core.render()
+    ref = fx["philox_rgb"].astype(np.float64)
+    ok, info = images_match(rgb, ref, pixel_tol=0.05, max_bad_fraction=5e-4, rmse_tol=0.01)
+    plain = np.sqrt(((rgb - ref) ** 2).mean(axis=(0, 1))) / ref.mean(axis=(0, 1))
+    a, b = fx["ref_rgb"].astype(np.float64), fx["ref_rgb_b"].astype(np.float64)
+    floor_px = np.sqrt(((a - b) ** 2).mean(axis=(0, 1))) / a.mean(axis=(0, 1))
+    vs_ref_px = np.sqrt(((rgb - a) ** 2).mean(axis=(0, 1))) / a.mean(axis=(0, 1))
+    k = 20
+    floor = float(np.sqrt(((block_mean(a, k) - block_mean(b, k)) ** 2).mean()))
+    got = float(np.sqrt(((block_mean(rgb.astype(np.float64), k) - block_mean(a, k)) ** 2).mean()))
+    mean_dev = float(np.max(np.abs(rgb.mean(axis=(0, 1)) - a.mean(axis=(0, 1))) / a.mean(axis=(0, 1))))
+    mean_floor = float(np.max(np.abs(a.mean(axis=(0, 1)) - b.mean(axis=(0, 1))) / a.mean(axis=(0, 1))))
+    plog(gate="rmse_1024spp", scene=name, res=list(RMSE_RES), plain_rel_rmse_vs_philox_oracle=[float(x) for x in plain],
+         flipped_pixels=info["n_bad"], masked_rel_rmse=info["rel_rmse_of_matching_pixels"],
+         per_pixel_rel_rmse_vs_reference_rand=[float(x) for x in vs_ref_px], reference_vs_reference_per_pixel_rel_rmse=[float(x) for x in floor_px],
+         block20_rmse_vs_reference=got, block20_rmse_reference_vs_reference=floor, mean_dev=mean_dev, mean_dev_reference_vs_reference=mean_floor,
+         extend=[int(st.extend_rays), int(fx["philox_cnt"][0])], shadow=[int(st.shadow_rays), int(fx["philox_cnt"][1])])
+    assert ok, info
+    assert abs(int(st.extend_rays) - int(fx["philox_cnt"][0])) <= 2e-4 * fx["philox_cnt"][0]
+    assert abs(int(st.shadow_rays) - int(fx["philox_cnt"][1])) <= 2e-4 * fx["philox_cnt"][1]
+    assert mean_dev < 0.01 + 3 * mean_floor
+    assert got < 1.6 * floor + 1e-4, (got, floor)
+
+
+# ---- memory sizing / options -------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_many_light_samples_and_small_budgets_still_render(core, golden):
+    """-l 32 at 1080p (worst-case queues of the old fixed 16 M-path batch: > 180 GB) and a 1.5 GB wavefront budget both
+    return the frame an unconstrained context renders (Philox: the image does not depend on the batching)."""
+    g = golden("CBspheres_lambertian")
+    cam = g["camera"].copy(); cam[14] *= 1080 / cam[13]; cam[12], cam[13] = 1920, 1080
+    core.set_params(2, 32, 8, 3)
+    core.load(g, camera=cam)
+    rgb, st = core.render()
+    assert np.isfinite(rgb).all() and rgb.mean() > 0 and st.shadow_rays % 32 == 0
+    core.set_option("wavefront_budget_mb", 1500)
+    small, st2 = core.render()
+    core.set_option("wavefront_budget_mb", 0)
+    assert st2.batches > st.batches
+    assert st2.extend_rays == st.extend_rays and st2.shadow_rays == st.shadow_rays
+    assert np.allclose(small, rgb, rtol=1e-4, atol=1e-5 * rgb.mean())
+    core.set_option("wavefront_budget_mb", 1)
+    with pytest.raises(D.DsrtError, match="wavefront state"):
+        core.render()
+    core.set_option("wavefront_budget_mb", 0)
+
+
+@pytest.mark.gpu
+def test_mirror_box_every_path_survives(core):
+    """Cornell box with perfect mirrors on every wall: Russian roulette never terminates (illum(f) >= 1), so the deep-path
+    pool runs at its worst-case fill through all max_depth bounces.  Checked against the oracle at a small size and run at 1080p."""
+    tp, tn, pb, bt, bpar, lt, lp = S.cornell_box()
+    bt = bt.copy(); bpar = bpar.copy()
+    for i in (0, 2, 3, 4, 5):
+        bt[i] = 1; bpar[i, :3] = 1.0
+    sc = {"prim_type": np.ones(12, np.int32), "prim_bsdf": pb, "tri_pos": tp, "tri_nrm": tn, "sphere": np.zeros((12, 4)),
+          "bsdf_type": bt, "bsdf_param": bpar, "light_type": lt, "light_param": lp}
+    cam = S.cam_dragon(96, 54)
+    ref, cnt = O.Scene(dict(sc, camera=cam)).render(96, 54, 4, 2, 8, rng="philox", seed=2)
+    core.set_params(4, 2, 8, 2)
+    core.load(sc, camera=cam)
+    rgb, st = core.render()
+    ok, info = images_match(rgb, ref)
+    assert ok, info
+    assert abs(int(st.extend_rays) - int(cnt[0])) <= 4
+    cam = S.cam_dragon(1920, 1080)
+    core.set_params(16, 2, 8, 2)
+    core.load(sc, camera=cam)
+    big, stb = core.render()
+    assert np.isfinite(big).all()
+    assert stb.extend_rays > 0.75 * 9 * stb.camera_samples       # rays that do not leave through the open front all reach depth 8
+
+
+@pytest.mark.gpu
+def test_skip_null_shadow_changes_the_ray_count_not_the_image(core, golden):
+    g = golden("CBgems"); cfg = CONFIGS["CBgems"]
+    core.set_params(4, cfg["nl"], cfg["depth"], 5)
+    core.load(g, camera=g["small_camera"])
+    a, sa = core.render()
+    core.set_option("skip_null_shadow", 1)
+    b, sb = core.render()
+    core.set_option("skip_null_shadow", 0)
+    assert sa.null_shadow_rays == 0 and 0 < sb.null_shadow_rays < sb.shadow_rays
+    assert sb.shadow_rays == sa.shadow_rays and sb.extend_rays == sa.extend_rays
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-6 * a.mean())

@@ -1,7 +1,7 @@
 """A/B of differently compiled builds of libdsrt.so (DSRT_LIB) x run-time knobs on the bench workload.
   python tools/sweeps/sweep_variants.py [spp]            # parent: one subprocess per library
 Each line: library, option set, Mrays/s and per-stage seconds of a 64-spp render (second of two)."""
-import os, subprocess, sys
+import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 LIBS = ["libdsrt.so"]
@@ -9,6 +9,11 @@ LIBS = ["libdsrt.so"]
 # OPTS = dsrt_set_option overrides per run (on top of `defaults` below)
 OPTS = [{}, {"postpone_min_lanes": 8}, {"postpone_min_lanes": 16}, {"refill_busy_lanes": 16}, {"refill_busy_lanes": 20},
         {"coop_min_pairs": 2}, {"coop_min_pairs": 12}, {"pool_batches": 4}, {"pool_batches": 16}, {"batch_spp": 4}, {"batch_spp": 8}]
+# or from the environment: SWEEP_LIBS="libdsrt.so,libdsrt_x.so" SWEEP_OPTS='[{}, {"refill_busy_lanes": 16}]'
+if os.environ.get("SWEEP_LIBS"):
+    LIBS = os.environ["SWEEP_LIBS"].split(",")
+if os.environ.get("SWEEP_OPTS"):
+    OPTS = json.loads(os.environ["SWEEP_OPTS"])
 
 if len(sys.argv) > 1 and sys.argv[1] == "child":
     import numpy as np

@@ -118,7 +118,7 @@ int stack_entries(const dsrt_ctx* ctx) { return std::max(ctx->wide.max_depth, 1)
 // dynamic shared memory of k_trace: traversal stacks + (any-hit kernel) ray blocks, pair tables, hit flags
 size_t stack_bytes(const dsrt_ctx* ctx) {
   return (size_t)stack_entries(ctx) * kTraceThreads * sizeof(uint2) + (size_t)kRayBlock * kTraceThreads * sizeof(float) +
-         (size_t)(kTraceThreads / 32) * kPairCap * sizeof(uint32_t) + kTraceThreads + (kTraceThreads / 32) * sizeof(uint32_t);
+         (size_t)(kTraceThreads / 32) * kPairCap * kPairBytes + kTraceThreads + (kTraceThreads / 32) * sizeof(uint32_t);
 }
 
 // persistent grid = resident CTAs per SM (registers / shared-memory stack) x SM count

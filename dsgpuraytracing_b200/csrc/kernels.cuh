@@ -33,6 +33,12 @@ constexpr int kTraceThreads = 128;        // 4 warps per CTA
 #ifndef DSRT_TRACE_MIN_CTAS
 #define DSRT_TRACE_MIN_CTAS 7             // resident CTAs per SM the traversal kernels are compiled for (register cap 72; measured best of 6, 7, 8)
 #endif
+#ifndef DSRT_PREFETCH_AHEAD
+#define DSRT_PREFETCH_AHEAD 16384         // queue positions between a refill's loads and the L2 prefetches it issues (0 = off)
+#endif
+#ifndef DSRT_ONEHOT_PAIRS
+#define DSRT_ONEHOT_PAIRS 1               // pair table entries = (slot base | owner, one-hot primitive bit): the bit scan runs in the test, 32 lanes wide
+#endif
 #ifndef DSRT_NODE_STEPS
 #define DSRT_NODE_STEPS 1                 // node steps a lane may take between two warp-wide primitive-test decisions
 #endif
@@ -43,6 +49,7 @@ constexpr int kRayBlock = DSRT_TRI_FAST ? 20 : 17;   // floats per lane publishe
 #ifndef DSRT_STACK_SLACK
 #define DSRT_STACK_SLACK 1
 #endif
+constexpr uint32_t kPairBytes = DSRT_ONEHOT_PAIRS ? 8u : 4u;
 constexpr int kPairCap = DSRT_PAIR_CAP;             // (ray, primitive) pairs one warp can deal out per round set
 constexpr int kMaxDepthSlots = 64;        // queue-size slots per batch (depth 0..63)
 constexpr unsigned kFull = 0xffffffffu;
@@ -144,6 +151,7 @@ __global__ void k_generate_centres(PathState ps, RenderParams rp, int n_paths) {
 //  * a ray never fetches the triangle it starts on: its bit is dropped from the leaf hit mask (drop_source, traverse.cuh).
 
 // shared-memory accesses of k_trace by 32-bit shared-window address (no generic-address arithmetic in the hot loop)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void sts64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" :: "r"(a), "r"(v.x), "r"(v.y)); }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
@@ -171,9 +179,9 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
   const uint32_t s_stack = s_base + threadIdx.x * 8u;                                      // entry e at s_stack + e * kStackPitch
   const uint32_t s_blk0 = s_base + (uint32_t)stack_entries * kStackPitch;                   // ray blocks of the CTA
   const uint32_t s_blk_warp = s_blk0 + (threadIdx.x & ~31u) * 4u;                           // ... of this warp's lane 0
-  const uint32_t s_pair = s_blk0 + kRayBlock * kBlkPitch + (threadIdx.x >> 5) * (kPairCap * 4u);
-  const uint32_t s_flag_warp = s_blk0 + kRayBlock * kBlkPitch + (kTraceThreads / 32) * (kPairCap * 4u) + (threadIdx.x & ~31u);
-  const uint32_t s_cnt = s_blk0 + kRayBlock * kBlkPitch + (kTraceThreads / 32) * (kPairCap * 4u) + kTraceThreads + (threadIdx.x >> 5) * 4u;
+  const uint32_t s_pair = s_blk0 + kRayBlock * kBlkPitch + (threadIdx.x >> 5) * (kPairCap * kPairBytes);
+  const uint32_t s_flag_warp = s_blk0 + kRayBlock * kBlkPitch + (kTraceThreads / 32) * (kPairCap * kPairBytes) + (threadIdx.x & ~31u);
+  const uint32_t s_cnt = s_blk0 + kRayBlock * kBlkPitch + (kTraceThreads / 32) * (kPairCap * kPairBytes) + kTraceThreads + (threadIdx.x >> 5) * 4u;
   if (lane == 0) sts32(s_cnt, 0u);
   __syncwarp();
   const uint32_t n = *n_ptr;
@@ -217,11 +225,17 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
         const uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
         if (k < n) {
           item = queue ? queue[k] : k;
-          const float4 o = DSRT_RAY_LD(ray_o + item);
+          const float4 o = DSRT_RAY_LD(ray_o + item), d = DSRT_RAY_LD(ray_d + item);
+          // The ray records stream from HBM (a batch's queue is far larger than L2), and a refill stalls the whole warp on
+          // them.  Queue positions are handed out in order, so every lane also asks L2 for the records kPrefetchAhead positions
+          // further on: each record is requested exactly once, about a DRAM latency before some warp's refill reads it.
+          if (DSRT_PREFETCH_AHEAD > 0 && !queue && k + DSRT_PREFETCH_AHEAD < n) {
+            prefetch_l2(ray_o + k + DSRT_PREFETCH_AHEAD); prefetch_l2(ray_d + k + DSRT_PREFETCH_AHEAD);
+            if (ANY && contrib) prefetch_l2(contrib + k + DSRT_PREFETCH_AHEAD);
+          }
           if (ANY && o.w < 0.f) {          // "skip_null_shadow": a shadow ray whose contribution is zero was queued with tmax = -1
             if (hit_out) hit_out[item] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
           } else {
-          const float4 d = DSRT_RAY_LD(ray_d + item);
           ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.tmax = o.w;
           ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.src_slot = __float_as_int(d.w);
           fr = make_frame(ray, (ANY && DSRT_SAT_SLAB) ? any_hit_scale(A, ray) : 1.0f);
@@ -304,16 +318,28 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           const int incl = (int)excl + c;
           if (P >= coop_min && P <= kPairCap) {
             coop = true;
-            uint32_t pa = s_pair + (uint32_t)(incl - c) * 4u;
             uint32_t m = pending ? tgroup.y : 0u;
             const uint32_t tag = tgroup.x | ((uint32_t)lane << kOwnerShift);
+#if DSRT_ONEHOT_PAIRS
+            // the owner only peels one-hot bits off its mask (two dependent ALU operations per primitive); turning a bit into
+            // a slot number (a bit scan on the slow XU pipe) is left to the testing lane, where it runs 32 lanes wide
+            uint32_t pa = s_pair + (uint32_t)(incl - c) * 8u;
+            while (m) { const uint32_t rest = m & (m - 1u); sts64(pa, make_uint2(tag, m ^ rest)); m = rest; pa += 8u; }
+#else
+            uint32_t pa = s_pair + (uint32_t)(incl - c) * 4u;
             while (m) { const uint32_t k = 31u - (uint32_t)__clz(m); m &= ~(1u << k); sts32(pa, tag + k); pa += 4u; }
+#endif
             if (pending) tgroup.y = 0u;
             __syncwarp();
             for (int base = 0; base < P; base += 32) {
               const int j = base + lane;
               if (j < P) {
+#if DSRT_ONEHOT_PAIRS
+                const uint2 pw2 = lds64(s_pair + (uint32_t)j * 8u);
+                const uint32_t pw = pw2.x + (31u - (uint32_t)__clz(pw2.y));
+#else
                 const uint32_t pw = lds32(s_pair + (uint32_t)j * 4u);
+#endif
                 const int slot = (int)(pw & ((1u << kOwnerShift) - 1u)); const uint32_t s = pw >> kOwnerShift;
                 const uint32_t rb = s_blk_warp + s * 4u;
                 TraceRay r2; WatertightRay w2;

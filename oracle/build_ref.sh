@@ -59,6 +59,21 @@ pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 
 $CXX "$OUT"/obj/*.o -o "$OUT/ref_driver" -lpthread -Wl,--unresolved-symbols=ignore-all
+
+# The reference-side binding, compiled against the reference's real PathTracer: integration/cuda_path_tracer_shim.{h,cpp}
+# (drop-in for cuda_src/setup.{h,cu}) + integration/ref_gpu_driver.cpp (Application::startGPURayTracing restated) + the same
+# reference objects, linked against the product's libdsrt.so.  -fno-access-control only for EnvironmentLight::envMap
+# (environment_light.h:50, private); everything else the shim reads is public in the reference's headers.
+REPO="$(cd "$HERE/.." && pwd)"
+if [ -f "$REPO/dsgpuraytracing_b200/libdsrt.so" ]; then
+  mkdir -p "$OUT/obj_gpu"
+  $CXX $FLAGS -fno-access-control -I"$REPO/include" -c "$REPO/integration/cuda_path_tracer_shim.cpp" -o "$OUT/obj_gpu/shim.o"
+  $CXX $FLAGS -fno-access-control -I"$REPO/include" -c "$REPO/integration/ref_gpu_driver.cpp" -o "$OUT/obj_gpu/ref_gpu_driver.o"
+  REFOBJS=$(ls "$OUT"/obj/*.o | grep -v "ref_driver.o")
+  $CXX "$OUT/obj_gpu/shim.o" "$OUT/obj_gpu/ref_gpu_driver.o" $REFOBJS -o "$OUT/ref_gpu_driver" -lpthread \
+       -L"$REPO/dsgpuraytracing_b200" -ldsrt -Wl,-rpath,'$ORIGIN/../../dsgpuraytracing_b200' -Wl,--unresolved-symbols=ignore-all
+  echo "[build_ref] built $OUT/ref_gpu_driver (reference PathTracer -> CUDAPathTracer shim -> libdsrt.so)"
+fi
 # the reference's vendored tinyexr behind a tiny command-line tool: pins the product's own OpenEXR reader
 $CXX -std=gnu++11 -O2 -w -fpermissive -I$REF/CMU462/include/CMU462 "$HERE/exr_ref.cpp" -o "$OUT/exr_ref"
 

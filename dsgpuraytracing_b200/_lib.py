@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 EXPORTED_SYMBOLS = [
     "dsrt_create", "dsrt_create_multi", "dsrt_device_count", "dsrt_destroy", "dsrt_last_error", "dsrt_version", "dsrt_set_scene", "dsrt_set_bvh",
     "dsrt_set_camera", "dsrt_set_params", "dsrt_set_envmap", "dsrt_set_option", "dsrt_build_bvh2", "dsrt_build_accel",
-    "dsrt_accel_info", "dsrt_upload_accel", "dsrt_accel_bytes", "dsrt_render", "dsrt_render_device", "dsrt_resolve_device", "dsrt_sync",
+    "dsrt_accel_info", "dsrt_upload_accel", "dsrt_accel_bytes", "dsrt_render", "dsrt_render_tonemapped", "dsrt_cancel", "dsrt_render_device", "dsrt_resolve_device", "dsrt_sync",
     "dsrt_collect_stats", "dsrt_primary_hits", "dsrt_trace_closest", "dsrt_trace_any", "dsrt_tonemap", "dsrt_measure_read_bandwidth",
 ]
 
@@ -207,15 +207,28 @@ class Core:
         if camera is not None:
             self.set_camera(camera)
 
-    def render(self, spp_begin=0, spp_count=None, spp_stride=1, out=None):
-        """Host-buffer render (H2D of nothing, D2H of the frame): returns (rgb[H,W,3], Stats)."""
+    def render(self, spp_begin=0, spp_count=None, spp_stride=1, out=None, rgba8=False):
+        """Host-buffer render (H2D of nothing, D2H of the frame): returns (rgb[H,W,3], Stats), or (rgb, rgba8[H,W] uint32,
+        Stats) with rgba8=True.  A render stopped by cancel() returns normally with self.cancelled = True."""
         if spp_count is None:
             spp_count = self.ns_aa
         rgb = out if out is not None else np.zeros((self.height, self.width, 3), np.float32)
         st = Stats()
-        self._ck(self.L.dsrt_render(self.ctx, int(spp_begin), int(spp_count), int(spp_stride),
-                                    C.c_void_p(rgb.ctypes.data), C.byref(st)), "dsrt_render")
-        return rgb, st
+        if rgba8:
+            img = np.zeros((self.height, self.width), np.uint32)
+            rc = self.L.dsrt_render_tonemapped(self.ctx, int(spp_begin), int(spp_count), int(spp_stride),
+                                               C.c_void_p(rgb.ctypes.data), C.c_void_p(img.ctypes.data), C.byref(st))
+        else:
+            rc = self.L.dsrt_render(self.ctx, int(spp_begin), int(spp_count), int(spp_stride),
+                                    C.c_void_p(rgb.ctypes.data), C.byref(st))
+        self.cancelled = rc == 4
+        if rc != 4:
+            self._ck(rc, "dsrt_render")
+        return (rgb, img, st) if rgba8 else (rgb, st)
+
+    def cancel(self):
+        """dsrt_cancel: stops the dsrt_render running in another thread after its current chunk of samples."""
+        self._ck(self.L.dsrt_cancel(self.ctx), "dsrt_cancel")
 
     def render_device(self, d_accum_ptr, spp_begin, spp_count, spp_stride=1, stream=0, collect=False):
         st = Stats() if collect else None

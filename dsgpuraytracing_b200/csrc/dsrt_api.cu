@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -38,6 +39,7 @@ struct DevState {
   Totals* d_totals = nullptr;
   float* d_accum_own = nullptr; size_t accum_pixels = 0;
   float* d_stage = nullptr; size_t stage_floats = 0;      // device 0 only: staging for peers without P2P access
+  uint32_t* d_rgba8 = nullptr; size_t rgba8_pixels = 0;   // device 0 only: tone-mapped frame of dsrt_render_tonemapped
   bool peer_ok = true;                                    // device 0 can read this device's memory directly
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   struct Span { size_t e0, e1; int kind; };
@@ -51,6 +53,7 @@ struct dsrt_ctx {
   std::vector<DevState> devs;
   std::string err;
   std::mutex err_mutex;                   // dsrt_render drives its devices from one host thread each
+  std::atomic<int> cancel{0};             // dsrt_cancel: checked by dsrt_render between chunks of samples
   // host copies of the inputs
   bool have_scene = false, have_bvh = false, have_cam = false, have_accel = false;
   int n_prims = 0;
@@ -64,7 +67,7 @@ struct dsrt_ctx {
   Camera cam{};
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
-  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 12, opt_refill = 18, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_max_ctas = 0, opt_carveout = -1, opt_prim_cost = 100, opt_mem_budget_mb = 0;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 8, opt_refill = 18, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_max_ctas = 0, opt_carveout = -1, opt_prim_cost = 100, opt_mem_budget_mb = 0;
   WideBVH wide;
   std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
   int env_w = 0, env_h = 0;
@@ -157,7 +160,7 @@ void free_device(DevState& D) {
   dev_free(D.queue[0]); dev_free(D.queue[1]); dev_free(D.sq.a); dev_free(D.sq.b); dev_free(D.sq.c);
   dev_free(D.pool.ray_o); dev_free(D.pool.ray_d); dev_free(D.pool.hit); dev_free(D.pool.thr); dev_free(D.pool.pixel); dev_free(D.pool.sample);
   dev_free(D.pool_queue[0]); dev_free(D.pool_queue[1]); dev_free(D.pool_sq.a); dev_free(D.pool_sq.b); dev_free(D.pool_sq.c); dev_free(D.d_pool_counters);
-  dev_free(D.d_counters); dev_free(D.d_totals); dev_free(D.d_accum_own); dev_free(D.d_stage);
+  dev_free(D.d_counters); dev_free(D.d_totals); dev_free(D.d_accum_own); dev_free(D.d_stage); dev_free(D.d_rgba8);
   for (cudaEvent_t e : D.ev_pool) cudaEventDestroy(e);
   if (D.ev_begin) cudaEventDestroy(D.ev_begin);
   if (D.ev_end) cudaEventDestroy(D.ev_end);
@@ -472,8 +475,39 @@ int dsrt_accel_info(const dsrt_ctx* ctx, int64_t* n_wide_nodes, int64_t* node_by
 }
 
 // ------------------------------------------------------------------------------------------------ rendering
+// Samples per wavefront batch and batches per deep-path pool for a frame of npp (padded) pixels on device D.
+// Wavefront + pool memory = paths x (80 B state and queues + 48 B per light sample) x (1 + pooled batches).  The reference
+// accepts any -l / frame size, so the batch and the pool group shrink until the working set fits in what the device has
+// free (plus what this context already holds); only a single-sample batch that still does not fit is an error.
+static int plan_batches(dsrt_ctx* ctx, DevState& D, int npp, int spp_count, int* batch_spp_out, int* pool_group_out) {
+  const int nls = ctx->n_light_samples;
+  int batch_spp = (int)ctx->opt_batch_spp;
+  if (batch_spp <= 0) batch_spp = std::max(1, (int)((16u << 20) / (unsigned)npp));   // ~16M paths per batch (measured: 4 / 8 / 16 M paths -> 6.38 / 6.59 / 6.71 Grays/s)
+  batch_spp = std::min(batch_spp, std::max(1, spp_count));
+  int pool_group = (int)ctx->opt_pool_batches;
+  size_t free_b = 0, total_b = 0;
+  CK(cudaMemGetInfo(&free_b, &total_b));
+  const double held = (double)D.cap_paths * 80.0 + (double)D.cap_shadow * 48.0 + (double)D.cap_pool * 80.0 + (double)D.cap_pool_shadow * 48.0;
+  double budget = 0.8 * ((double)free_b + held);
+  if (ctx->opt_mem_budget_mb > 0) budget = std::min(budget, (double)ctx->opt_mem_budget_mb * 1048576.0);
+  const double per_path = 80.0 + 48.0 * (double)std::max(nls, 1);
+  auto need = [&](int bspp, int grp) { return (double)npp * bspp * per_path * (1.0 + (ctx->max_depth > 0 ? grp : 0)); };
+  while (need(batch_spp, pool_group) > budget) {
+    if (pool_group > 2) pool_group = (pool_group + 1) / 2;
+    else if (batch_spp > 1) batch_spp = (batch_spp + 1) / 2;
+    else if (pool_group > 1) pool_group = 1;
+    else return fail(ctx, DSRT_ERR_LIMIT, "dsrt_render: one sample per pixel of this frame with " + std::to_string(nls) +
+                     " light samples needs " + std::to_string((long long)(need(1, 1) / 1048576.0)) + " MiB of wavefront state; the device has " +
+                     std::to_string((long long)(budget / 1048576.0)) + " MiB available");
+  }
+  *batch_spp_out = batch_spp; *pool_group_out = pool_group;
+  return DSRT_OK;
+}
+
 // Enqueues the whole wavefront for samples spp_begin + k*spp_stride (k < spp_count) on one device; no host sync.
-static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count, int spp_stride, float* d_accum, cudaStream_t st) {
+// first == false: a later chunk of the same frame (dsrt_render splits a frame so that dsrt_cancel can take effect): counters,
+// launch totals and the begin event carry over.
+static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count, int spp_stride, float* d_accum, cudaStream_t st, bool first = true) {
   if (!ctx->have_accel || !ctx->have_cam) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: call dsrt_build_accel and dsrt_set_camera first");
   if (spp_count < 0 || spp_stride < 1 || spp_begin < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: bad sample range");
   CK(cudaSetDevice(D.device));
@@ -482,31 +516,9 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   const int blocks_x = (W + 7) / 8, blocks_y = (H + 3) / 4;
   const int npp = blocks_x * blocks_y * 32;
   const int aligned = (W % 8 == 0 && H % 4 == 0) ? 1 : 0;
-  int batch_spp = (int)ctx->opt_batch_spp;
-  if (batch_spp <= 0) batch_spp = std::max(1, (int)((16u << 20) / (unsigned)npp));   // ~16M paths per batch (measured: 4 / 8 / 16 M paths -> 6.38 / 6.59 / 6.71 Grays/s)
-  batch_spp = std::min(batch_spp, std::max(1, spp_count));
   const int nls = ctx->n_light_samples;
-  // Wavefront + pool memory = paths x (80 B state and queues + 48 B per light sample) x (1 + pooled batches).  The reference
-  // accepts any -l / frame size, so the batch and the pool group shrink until the working set fits in what the device has
-  // free (plus what this context already holds); only a single-sample batch that still does not fit is an error.
-  int pool_group = (int)ctx->opt_pool_batches;
-  {
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
-    const double held = (double)D.cap_paths * 80.0 + (double)D.cap_shadow * 48.0 + (double)D.cap_pool * 80.0 + (double)D.cap_pool_shadow * 48.0;
-    double budget = 0.8 * ((double)free_b + held);
-    if (ctx->opt_mem_budget_mb > 0) budget = std::min(budget, (double)ctx->opt_mem_budget_mb * 1048576.0);
-    const double per_path = 80.0 + 48.0 * (double)std::max(nls, 1);
-    auto need = [&](int bspp, int grp) { return (double)npp * bspp * per_path * (1.0 + (ctx->max_depth > 0 ? grp : 0)); };
-    while (need(batch_spp, pool_group) > budget) {
-      if (pool_group > 2) pool_group = (pool_group + 1) / 2;
-      else if (batch_spp > 1) batch_spp = (batch_spp + 1) / 2;
-      else if (pool_group > 1) pool_group = 1;
-      else return fail(ctx, DSRT_ERR_LIMIT, "dsrt_render: one sample per pixel of this frame with " + std::to_string(nls) +
-                       " light samples needs " + std::to_string((long long)(need(1, 1) / 1048576.0)) + " MiB of wavefront state; the device has " +
-                       std::to_string((long long)(budget / 1048576.0)) + " MiB available");
-    }
-  }
+  int batch_spp = 1, pool_group = 1;
+  { int rcp = plan_batches(ctx, D, npp, spp_count, &batch_spp, &pool_group); if (rcp) return rcp; }
   const size_t P = (size_t)npp * batch_spp;
   int rc = ensure_wavefront(ctx, D, P, P * (size_t)std::max(nls, 1));
   if (rc) return rc;
@@ -516,8 +528,11 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
     D.n_counter_blocks = std::max(n_batches, 1);
   }
   CK(cudaMemsetAsync(D.d_counters, 0, sizeof(Counters) * (size_t)std::max(n_batches, 1), st));
-  CK(cudaMemsetAsync(D.d_totals, 0, sizeof(Totals), st));
-  D.ev_used = 0; D.spans.clear(); D.launches = 0; D.batches = (uint32_t)n_batches;
+  if (first) {
+    CK(cudaMemsetAsync(D.d_totals, 0, sizeof(Totals), st));
+    D.ev_used = 0; D.spans.clear(); D.launches = 0; D.batches = 0;
+  }
+  D.batches += (uint32_t)n_batches;
 
   SceneDev sc; sc.bsdf = (const Bsdf*)D.d_bsdf; sc.lights = (const Light*)D.d_lights; sc.shade = (const float4*)D.d_shade;
   sc.n_lights = ctx->n_lights; sc.n_light_samples = nls;
@@ -546,7 +561,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
     }
     CK(cudaMemsetAsync(D.d_pool_counters, 0, sizeof(PoolCounters) * (size_t)n_groups, st));
   }
-  CK(cudaEventRecord(D.ev_begin, st));     // after every (re)allocation: gpu_seconds covers the kernels of the frame only
+  if (first) CK(cudaEventRecord(D.ev_begin, st));     // after every (re)allocation: gpu_seconds covers the kernels of the frame only
   auto trace = [&](bool any, const float4* ro, const float4* rd, const uint32_t* q, const uint32_t* n_ptr, uint32_t* work, float4* hits, const float4* contrib) {
     span_begin(any ? 1 : 0);
     if (any) {
@@ -659,11 +674,19 @@ int dsrt_sync(dsrt_ctx* ctx) {
   return DSRT_OK;
 }
 
-int dsrt_render(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp_stride, float* rgb_out, dsrt_stats* stats) {
-  if (!ctx || !rgb_out) return DSRT_ERR_INVALID;
+// dsrt_render / dsrt_render_tonemapped.  The frame is enqueued in chunks of a few pool groups (about 0.2 s of GPU work at
+// 1080p) with at most two chunks in flight, so that dsrt_cancel -- PathTracer::stop (src/pathtracer.cpp:148-171) -- takes
+// effect within a chunk; a frame that fits in one chunk (every test-sized frame) is enqueued exactly as before.
+static int render_host(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp_stride, float* rgb_out, uint32_t* rgba8_out, dsrt_stats* stats) {
+  if (!ctx || (!rgb_out && !rgba8_out)) return DSRT_ERR_INVALID;
   if (!ctx->have_cam) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: call dsrt_set_camera first");
+  if (!ctx->have_accel) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: call dsrt_build_accel first");
+  if (spp_count < 0 || spp_stride < 1 || spp_begin < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: bad sample range");
+  ctx->cancel.store(0);
   const size_t npix = (size_t)ctx->cam.width * ctx->cam.height;
   const int G = (int)ctx->devs.size();
+  const int npp = ((ctx->cam.width + 7) / 8) * ((ctx->cam.height + 3) / 4) * 32;
+  std::vector<int> done((size_t)G, 0);
   // GPU r renders samples k with k mod G == r of the requested list (load is balanced whatever the image content)
   // one host thread per device: a frame is a few thousand launches, and enqueueing them device after device from one
   // thread would start the last GPU tens of milliseconds late
@@ -673,7 +696,23 @@ int dsrt_render(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp
     if (npix > D.accum_pixels) { int rc = dev_alloc(ctx, &D.d_accum_own, npix * 3); if (rc) return rc; D.accum_pixels = npix; }
     CK(cudaMemsetAsync(D.d_accum_own, 0, npix * 3 * sizeof(float), D.stream));
     const int cnt = spp_count > r ? (spp_count - r + G - 1) / G : 0;
-    return render_impl(ctx, D, spp_begin + r * spp_stride, cnt, spp_stride * G, D.d_accum_own, D.stream);
+    int bspp = 1, grp = 1;
+    { int rc = plan_batches(ctx, D, npp, cnt, &bspp, &grp); if (rc) return rc; }
+    const int per_chunk = std::max(1, bspp * grp * 2);
+    Scratch fences; cudaEvent_t fence[2];
+    CK(fences.event(&fence[0])); CK(fences.event(&fence[1]));
+    int i = 0;
+    do {                                   // at least one call, so that an empty sample list still resets the counters
+      const int c = std::min(per_chunk, cnt - done[r]);
+      int rc = render_impl(ctx, D, spp_begin + (r + done[r] * G) * spp_stride, c, spp_stride * G, D.d_accum_own, D.stream, i == 0);
+      if (rc) return rc;
+      done[r] += c;
+      if (done[r] >= cnt) break;
+      CK(cudaEventRecord(fence[i & 1], D.stream));
+      if (i >= 1) CK(cudaEventSynchronize(fence[(i - 1) & 1]));
+      i++;
+    } while (!ctx->cancel.load());
+    return DSRT_OK;
   };
   if (G == 1) { int rc = enqueue(0); if (rc) return rc; }
   else {
@@ -683,6 +722,10 @@ int dsrt_render(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp
     for (std::thread& t : workers) t.join();
     for (int r = 0; r < G; r++) if (rcs[r]) return rcs[r];
   }
+  int total_done = 0; for (int r = 0; r < G; r++) total_done += done[r];
+  const bool cancelled = total_done < spp_count;
+  // a cancelled frame is normalised by the samples that were rendered (an unbiased, noisier image), a complete one by ns_aa
+  const float inv_spp = cancelled ? 1.0f / (float)std::max(total_done, 1) : 1.0f / (float)ctx->ns_aa;
   DevState& D0 = ctx->devs[0];
   CK(cudaSetDevice(D0.device));
   PeerPtrs pp; pp.n = G; pp.p[0] = D0.d_accum_own;
@@ -698,11 +741,30 @@ int dsrt_render(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp
       pp.p[r] = dst;
     }
   }
-  k_resolve_peers<<<(unsigned)((npix + 255) / 256), 256, 0, D0.stream>>>(pp, D0.d_accum_own, nullptr, (int)npix, 1.0f / (float)ctx->ns_aa);
+  if (rgba8_out && npix > D0.rgba8_pixels) { int rc = dev_alloc(ctx, &D0.d_rgba8, npix); if (rc) return rc; D0.rgba8_pixels = npix; }
+  k_resolve_peers<<<(unsigned)((npix + 255) / 256), 256, 0, D0.stream>>>(pp, D0.d_accum_own, rgba8_out ? D0.d_rgba8 : nullptr, (int)npix, inv_spp);
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(rgb_out, D0.d_accum_own, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, D0.stream));
+  if (rgb_out) CK(cudaMemcpyAsync(rgb_out, D0.d_accum_own, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, D0.stream));
+  if (rgba8_out) CK(cudaMemcpyAsync(rgba8_out, D0.d_rgba8, npix * sizeof(uint32_t), cudaMemcpyDeviceToHost, D0.stream));
   CK(cudaStreamSynchronize(D0.stream));
-  if (stats) return dsrt_collect_stats(ctx, stats);
+  if (stats) { int rc = dsrt_collect_stats(ctx, stats); if (rc) return rc; }
+  if (cancelled) { fail(ctx, DSRT_CANCELLED, "dsrt_render: cancelled after " + std::to_string(total_done) + " of " + std::to_string(spp_count) + " samples per pixel"); return DSRT_CANCELLED; }
+  return DSRT_OK;
+}
+
+int dsrt_render(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp_stride, float* rgb_out, dsrt_stats* stats) {
+  if (!rgb_out) return DSRT_ERR_INVALID;
+  return render_host(ctx, spp_begin, spp_count, spp_stride, rgb_out, nullptr, stats);
+}
+
+int dsrt_render_tonemapped(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp_stride, float* rgb_out, uint32_t* rgba8_out, dsrt_stats* stats) {
+  if (!rgba8_out) return DSRT_ERR_INVALID;
+  return render_host(ctx, spp_begin, spp_count, spp_stride, rgb_out, rgba8_out, stats);
+}
+
+int dsrt_cancel(dsrt_ctx* ctx) {
+  if (!ctx) return DSRT_ERR_INVALID;
+  ctx->cancel.store(1);
   return DSRT_OK;
 }
 

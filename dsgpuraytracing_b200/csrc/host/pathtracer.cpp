@@ -76,9 +76,11 @@ void PathTracer::build_accel() {
   accel_uploaded = false;
 }
 
+// pathtracer.cpp:148-171.  Callable from another thread while start_raytracing() is blocked in the render: the core stops
+// after the chunk of samples in flight (dsrt_cancel) and start_raytracing() returns with the frame rendered so far.
 void PathTracer::stop() {
-  if (state == RENDERING || state == DONE) state = READY;
-  if (state == VISUALIZE) state = READY;
+  if (state == RENDERING && ctx) { dsrt_cancel(ctx); return; }      // start_raytracing() moves the state to READY when it returns
+  if (state == DONE || state == VISUALIZE) state = READY;
 }
 
 void PathTracer::clear() {
@@ -130,15 +132,21 @@ void PathTracer::start_raytracing() {
   if (dsrt_set_camera(ctx, camera->pos, camera->c2w, (int)sampleBuffer.w, (int)sampleBuffer.h, camera->screenDist)) { fail("dsrt_set_camera"); state = READY; return; }
   fprintf(stdout, "[PathTracer] Rendering... "); fflush(stdout);
   auto t0 = std::chrono::steady_clock::now();
-  std::vector<float> rgb(sampleBuffer.w * sampleBuffer.h * 3);
-  if (dsrt_render(ctx, 0, (int)ns_aa, 1, rgb.data(), &last_stats)) { fail("dsrt_render"); state = READY; return; }
+  // sampleBuffer and the tone-mapped frameBuffer both come straight from the fused reduce + resolve kernel
+  const int rc = dsrt_render_tonemapped(ctx, 0, (int)ns_aa, 1, sampleBuffer.data.data(), frameBuffer.data.data(), &last_stats);
   render_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (rc == DSRT_CANCELLED) {            // stop(): keep what was rendered, go back to READY like the reference
+    fprintf(stdout, "stopped (%.4f sec, %llu camera samples)\n", render_seconds, (unsigned long long)last_stats.camera_samples);
+    state = READY; return;
+  }
+  if (rc) { fail("dsrt_render"); state = READY; return; }
   fprintf(stdout, "GPU ray tracing done! (%.4f sec)\n", render_seconds);
-  updateBufferFromGPU(rgb.data());
   state = DONE;
 }
 
-// HDRImageBuffer::update_pixel + toColor + ImageBuffer::update_pixel (image.h:113-117, 174-189, 49-58)
+// HDRImageBuffer::update_pixel + toColor + ImageBuffer::update_pixel (image.h:113-117, 174-189, 49-58) on the host: kept for
+// callers that hand in their own linear frame (cuda_src/setup.cu:829-843); start_raytracing() itself takes the tone-mapped
+// frame from the device (dsrt_render_tonemapped).
 void PathTracer::updateBufferFromGPU(const float* gpuBuffer) {
   const size_t n = sampleBuffer.w * sampleBuffer.h;
   std::memcpy(sampleBuffer.data.data(), gpuBuffer, n * 3 * sizeof(float));

@@ -40,7 +40,7 @@ constexpr int kTraceThreads = 128;        // 4 warps per CTA
 #define DSRT_ONEHOT_PAIRS 1               // pair table entries = (slot base | owner, one-hot primitive bit): the bit scan runs in the test, 32 lanes wide
 #endif
 #ifndef DSRT_NODE_STEPS
-#define DSRT_NODE_STEPS 1                 // node steps a lane may take between two warp-wide primitive-test decisions
+#define DSRT_NODE_STEPS 2                 // node steps a lane may take between two warp-wide primitive-test decisions (1 / 2 / 3: 6839 / 6893 / 6741 Mrays/s)
 #endif
 constexpr int kRayBlock = DSRT_TRI_FAST ? 20 : 17;   // floats per lane published for the cooperative primitive test
 #ifndef DSRT_PAIR_CAP

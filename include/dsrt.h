@@ -28,6 +28,7 @@ extern "C" {
 #define DSRT_ERR_INVALID 1   /* bad argument / call order */
 #define DSRT_ERR_CUDA 2      /* CUDA runtime failure (no device, out of memory, launch failure, ...) */
 #define DSRT_ERR_LIMIT 3     /* scene exceeds an internal limit */
+#define DSRT_CANCELLED 4     /* dsrt_render stopped early by dsrt_cancel: the frame holds the samples rendered so far */
 
 typedef struct dsrt_ctx dsrt_ctx;
 
@@ -109,7 +110,7 @@ int dsrt_set_envmap(dsrt_ctx* ctx, int32_t width, int32_t height, const float* r
 int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t max_ray_depth, uint32_t seed);
 /* named knobs: "count_traversal" (0/1), "batch_spp" (camera samples per pixel per wavefront batch),
  * "stage_timing" (0/1: per-stage CUDA events), "postpone_min_lanes" (primitive tests wait until this many lanes
- * of a warp have some pending; 0 = test at once; default 12), "pool_batches" (how many consecutive batches share one
+ * of a warp have some pending; 0 = test at once; default 8), "pool_batches" (how many consecutive batches share one
  * deep-path pool: paths that survive depth 0 are gathered and advanced together; default 8, 1 = per batch),
  * "coop_min_pairs" (any-hit kernel: when a warp has at least this many pending (ray, primitive) pairs they are
  * dealt out one per lane; default 6, a huge value disables the cooperative test), "postpone_wait_mode" (0: primitives are
@@ -147,6 +148,15 @@ int dsrt_accel_info(const dsrt_ctx* ctx, int64_t* n_wide_nodes, int64_t* node_by
  * (image.h:113-117).  Replaces startRayTracingPT + updateHostSampleBuffer, setup.cu:147-179, 813-827. */
 int dsrt_render(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp_stride, float* rgb_out,
                 dsrt_stats* stats);
+/* Same frame, plus the tone-mapped RGBA8 image (HDRImageBuffer::toColor, image.h:174-189: 0xAABBGGRR, row 0 = bottom) from the
+ * fused reduce + resolve kernel; rgb_out may be NULL.  Replaces updateHostSampleBuffer + PathTracer::updateBufferFromGPU,
+ * setup.cu:813-843. */
+int dsrt_render_tonemapped(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int32_t spp_stride, float* rgb_out,
+                           uint32_t* rgba8_out, dsrt_stats* stats);
+/* PathTracer::stop (src/pathtracer.cpp:148-171): callable from another thread while dsrt_render runs.  The render stops after
+ * the chunk of samples in flight (about 0.2 s of GPU work at 1080p), returns DSRT_CANCELLED, and its frame is the mean of the
+ * samples rendered so far (dsrt_stats.camera_samples / pixels).  The flag is cleared at the start of every dsrt_render. */
+int dsrt_cancel(dsrt_ctx* ctx);
 /* Same, but ADDS un-normalised radiance sums into a DEVICE buffer (width*height*3 floats) on the given
  * cudaStream_t (NULL = the context's stream) without synchronising: the multi-GPU path reduces these
  * partial sums with one NCCL reduce and then calls dsrt_resolve_device. */

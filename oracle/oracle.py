@@ -215,6 +215,12 @@ def philox(seed, pixel, sample, depth, block):
     return out
 
 
+def philox_raw(ctr, k0, k1):
+    c = np.asarray(ctr, np.uint32).copy(); out = np.zeros(4, np.uint32)
+    lib().orc_philox_raw(c.ctypes.data_as(C.c_void_p), C.c_uint32(k0), C.c_uint32(k1), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def to_color(rgb):
     rgb = _c(rgb, np.float32); n = rgb.size // 3
     out = np.zeros(n, np.uint32)

@@ -433,6 +433,12 @@ void orc_philox(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t depth, 
   philox4x32_10(c, seed, 0x5EEDu);
   memcpy(out4, c, 16);
 }
+/* raw generator for the Random123 known-answer vectors (tests/test_oracle_vs_reference.py) */
+void orc_philox_raw(const uint32_t* ctr4, uint32_t k0, uint32_t k1, uint32_t* out4) {
+  uint32_t c[4] = {ctr4[0], ctr4[1], ctr4[2], ctr4[3]};
+  philox4x32_10(c, k0, k1);
+  memcpy(out4, c, 16);
+}
 static inline double u24(uint32_t x) { return (double)(x >> 8) * (1.0 / 16777216.0); }
 static void rng_block(const orng* g, int depth, int block, double u[4]) {
   uint32_t c[4]; orc_philox(g->seed, g->pixel, g->sample, (uint32_t)depth, (uint32_t)block, c);

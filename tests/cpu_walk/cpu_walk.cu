@@ -87,6 +87,12 @@ void cw_trace(Walk* w, int any, int64_t n, const float* o, const float* d, const
 }
 
 // brute force over all slots with the production primitive tests (no BVH): separates culling from intersection bugs
+// the PRODUCT's Philox4x32-10 (rng.cuh, host build) on a raw counter / key: Random123 known-answer vectors
+void cw_philox_raw(const uint32_t* ctr4, uint32_t k0, uint32_t k1, uint32_t* out4) {
+  const uint4 r = philox4x32_10(make_uint4(ctr4[0], ctr4[1], ctr4[2], ctr4[3]), k0, k1);
+  out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}
+
 void cw_trace_brute(Walk* w, int64_t n, const float* o, const float* d, int32_t* prim_id, float* t) {
   const Accel A = accel_of(w, false);
   for (int64_t i = 0; i < n; i++) {

@@ -193,7 +193,7 @@ def test_arbitrary_rays_closest_any_and_fetch_counters(name, core, golden):
     assert abs(int(st.nodes_visited) - int(wc[3])) <= 2e-3 * wc[3]
     assert abs(int(st.prims_tested) - int(wc[4])) <= 2e-3 * wc[4]
     # postponed primitive tests (the default) change the visiting order, never the result
-    core.set_option("postpone_min_lanes", 12)
+    core.set_option("postpone_min_lanes", 8)
     core.set_option("coop_min_pairs", 6)
     rgb2, st2 = core.render()
     core.set_option("count_traversal", 0)

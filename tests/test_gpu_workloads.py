@@ -285,3 +285,45 @@ def test_reference_pathtracer_drives_libdsrt_through_the_shim(name, tmp_path):
     want, st, _ = D.render_file(dae, W, H, 4, cfg["nl"], cfg["depth"], cam_info=cam, seed=5)
     assert f"segments {int(st.extend_rays)} + {int(st.shadow_rays)}" in r.stdout
     assert np.allclose(got, want, rtol=1e-4, atol=1e-5 * want.mean())
+
+
+# ---- cancel / device tone map ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_cancel_stops_a_long_render_and_keeps_the_partial_frame(golden):
+    """dsrt_cancel from another thread (PathTracer::stop, pathtracer.cpp:148-171): the render returns early with the mean
+    of the samples done so far; an uncancelled render of the same context afterwards is complete again."""
+    import threading
+    import time
+    g = golden("CBspheres_lambertian"); cfg = CONFIGS["CBspheres_lambertian"]
+    cam = g["camera"].copy(); cam[14] *= 1080 / cam[13]; cam[12], cam[13] = 1920, 1080
+    c = D.Core(0)
+    c.set_params(4096, cfg["nl"], cfg["depth"], 1)
+    c.load(g, camera=cam)
+    ref, st_ref = c.render(spp_count=16)                 # 16 spp, normalised by ns_aa = 4096 -> rescale below
+    t = threading.Timer(0.4, c.cancel)
+    t0 = time.time(); t.start()
+    rgb, st = c.render()
+    dt = time.time() - t0; t.join()
+    assert c.cancelled and 0 < st.camera_samples < 4096 * 1920 * 1080
+    assert dt < 3.0, dt
+    spp_done = st.camera_samples / (1920 * 1080)
+    assert np.isfinite(rgb).all()
+    assert abs(rgb.mean() - ref.mean() * 4096 / 16) < 0.05 * rgb.mean()      # normalised by the samples rendered
+    again, st2 = c.render(spp_count=16)
+    assert not c.cancelled and st2.camera_samples == st_ref.camera_samples
+    assert np.allclose(again, ref, rtol=1e-4, atol=1e-6 * ref.mean())
+    c.close()
+    assert spp_done >= 1
+
+
+@pytest.mark.gpu
+def test_render_tonemapped_matches_toColor(core, golden):
+    g = golden("CBgems"); cfg = CONFIGS["CBgems"]
+    core.set_params(4, cfg["nl"], cfg["depth"], 5)
+    core.load(g, camera=g["small_camera"])
+    rgb, img, st = core.render(rgba8=True)
+    plain, _ = core.render()
+    assert np.allclose(rgb, plain, rtol=1e-5, atol=1e-6 * plain.mean())
+    exp = O.to_color(rgb).reshape(img.shape)
+    a = img.view(np.uint8).reshape(-1, 4).astype(int); b = exp.view(np.uint8).reshape(-1, 4).astype(int)
+    assert np.abs(a - b).max() <= 1 and (a[:, 3] == 255).all()

@@ -87,8 +87,19 @@ def test_known_answers():
     cam = np.array([1, 2, 3, 1, 0, 0, 0, 1, 0, 0, 0, 1, 640, 480, 500, 0, 0], float)
     o, d = O.generate_ray(cam, 0.5, 0.5)
     assert np.allclose(o, [1, 2, 4]) and np.allclose(d, [0, 0, -1])
-    # Philox4x32-10 known answer (Random123 kat: counter 0, key 0)
-    assert list(O.philox(0, 0, 0, 0, 0)) != [0, 0, 0, 0]
+    # Philox4x32-10 known answers (Random123 kat_vectors, philox4x32 10 rounds: counter[4], key[2] -> output[4]); the oracle's
+    # generator and the product's (rng.cuh, host build in tests/cpu_walk) must both reproduce them, and each other
+    import ctypes as C
+    from tests import cpuwalk
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        assert tuple(int(x) for x in O.philox_raw(ctr, *key)) == want
+        c = np.array(ctr, np.uint32); out = np.zeros(4, np.uint32)
+        cpuwalk.lib().cw_philox_raw(C.c_void_p(c.ctypes.data), C.c_uint32(key[0]), C.c_uint32(key[1]), C.c_void_p(out.ctypes.data))
+        assert tuple(int(x) for x in out) == want
+    assert tuple(O.philox(7, 11, 13, 2, 1)) == tuple(O.philox_raw((11, 13, 2, 1), 7, 0x5EED))      # key = (seed, 0x5EED), counter = (pixel, sample, depth, block)
     # toColor: (s*sqrt2)^(1/2.2) clamp, *255 truncating, ABGR packing (image.h:49-58,174-189)
     c = O.to_color(np.array([[0.0, 0.5, 10.0]], np.float32))
     assert c[0] == (0 | (int((0.5 * 2 ** 0.5) ** (1 / 2.2) * 255) << 8) | (255 << 16) | (255 << 24))

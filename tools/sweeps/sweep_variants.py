@@ -23,7 +23,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     V, F = S.torus_knot(); V = V.astype(np.float32).astype(np.float64)
     sc = S.cb_mesh_scene(V, F); cam = S.cam_dragon(1920, 1080)
     core = D.Core(0); core.set_params(spp, 4, 8, 0); core.load(sc, camera=cam); core.set_option("stage_timing", 1)
-    defaults = {"max_ctas_per_sm": 0, "postpone_min_lanes": 12, "refill_busy_lanes": 18, "coop_min_pairs": 6, "postpone_wait_mode": 0, "pool_batches": 8, "batch_spp": 0, "smem_carveout_pct": -1}
+    defaults = {"max_ctas_per_sm": 0, "postpone_min_lanes": 8, "refill_busy_lanes": 18, "coop_min_pairs": 6, "postpone_wait_mode": 0, "pool_batches": 8, "batch_spp": 0, "smem_carveout_pct": -1}
     for o in OPTS:
         try:
             for k, v in {**defaults, **o}.items():

@@ -199,10 +199,12 @@ class Core:
         self._ck(self.L.dsrt_accel_info(self.ctx, C.byref(a), C.byref(b), C.byref(c), C.byref(d)), "dsrt_accel_info")
         return {"wide_nodes": a.value, "node_bytes": b.value, "prim_bytes": c.value, "max_depth": d.value}
 
-    def load(self, arr, camera=None, bvh=None):
-        """set_scene + (host SAH build | given BVH) + build_accel (+ camera)."""
+    def load(self, arr, camera=None, bvh=None, device_build=False):
+        """set_scene + (host SAH build | given BVH | option "device_build": LBVH + collapse on the GPU) + build_accel (+ camera)."""
         self.set_scene(arr)
-        self.set_bvh(bvh if bvh is not None else build_bvh2(arr))
+        self.set_option("device_build", 1 if device_build else 0)
+        if not device_build:
+            self.set_bvh(bvh if bvh is not None else build_bvh2(arr))
         self.build_accel()
         if camera is not None:
             self.set_camera(camera)

@@ -16,6 +16,9 @@
 #include "../../include/dsrt.h"
 #include "kernels.cuh"
 #include "wide_bvh.h"
+#include "device_build.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <chrono>
 
 // ================================================================================================ host side
 using namespace dsrt;
@@ -67,7 +70,7 @@ struct dsrt_ctx {
   Camera cam{};
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
-  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 8, opt_refill = 18, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_max_ctas = 0, opt_carveout = -1, opt_prim_cost = 100, opt_mem_budget_mb = 0;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 8, opt_refill = 18, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_max_ctas = 0, opt_carveout = -1, opt_prim_cost = 100, opt_mem_budget_mb = 0, opt_device_build = 0;
   WideBVH wide;
   std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
   int env_w = 0, env_h = 0;
@@ -371,24 +374,122 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
   else if (n == "coop_min_pairs") ctx->opt_coop_min = value;
   else if (n == "max_ctas_per_sm") ctx->opt_max_ctas = value;
   else if (n == "collapse_prim_cost_pct") { ctx->opt_prim_cost = std::max<int64_t>(1, value); ctx->have_accel = false; }   // takes effect at the next dsrt_build_accel
+  else if (n == "device_build") { ctx->opt_device_build = value; ctx->have_accel = false; }   // takes effect at the next dsrt_build_accel
   else if (n == "wavefront_budget_mb") ctx->opt_mem_budget_mb = value;   // 0: 80 % of the free device memory; > 0: additional cap (tests)
   else if (n == "smem_carveout_pct") ctx->opt_carveout = value;        // -1: driver default          // 0: whatever fits
   else return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_option: unknown option " + n);
   return DSRT_OK;
 }
 
+
+// Option "device_build": the wide BVH, the leaf-contiguous primitive order and the primitive / shading records are built on the
+// first device (device_build.cuh) from the caller's scene arrays and read back into the same host containers the host SAH path
+// fills, so everything downstream (uploads to every GPU, parity records, statistics) is shared.
+static int build_wide_bvh_device(dsrt_ctx* ctx, DevState& D) {
+  const int n = ctx->n_prims;
+  const bool timing = std::getenv("DSRT_BUILD_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
+  CK(cudaSetDevice(D.device));
+  cudaStream_t st = D.stream;
+  Scratch tmp;
+  int32_t *d_type = nullptr, *d_bsdf = nullptr; double *d_pos = nullptr, *d_nrm = nullptr, *d_sph = nullptr;
+  CK(tmp.alloc(&d_type, (size_t)n * 4)); CK(tmp.alloc(&d_bsdf, (size_t)n * 4));
+  CK(tmp.alloc(&d_pos, (size_t)n * 72)); CK(tmp.alloc(&d_nrm, (size_t)n * 72)); CK(tmp.alloc(&d_sph, (size_t)n * 32));
+  CK(cudaMemcpyAsync(d_type, ctx->prim_type.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_bsdf, ctx->prim_bsdf.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_pos, ctx->tri_pos.data(), (size_t)n * 72, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_nrm, ctx->tri_nrm.data(), (size_t)n * 72, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_sph, ctx->sphere.data(), (size_t)n * 32, cudaMemcpyHostToDevice, st));
+  DbScene sc; sc.prim_type = d_type; sc.prim_bsdf = d_bsdf; sc.tri_pos = d_pos; sc.tri_nrm = d_nrm; sc.sphere = d_sph; sc.n = n;
+  float *d_pbox = nullptr, *d_ibox = nullptr; uint32_t* d_scene = nullptr;
+  uint64_t *d_keys = nullptr, *d_keys2 = nullptr; uint32_t *d_vals = nullptr, *d_sorted = nullptr;
+  int *d_left = nullptr, *d_right = nullptr, *d_first = nullptr, *d_last = nullptr, *d_pint = nullptr, *d_pleaf = nullptr, *d_visit = nullptr;
+  const size_t ni = (size_t)std::max(n - 1, 1);
+  CK(tmp.alloc(&d_pbox, (size_t)n * 24)); CK(tmp.alloc(&d_ibox, ni * 24)); CK(tmp.alloc(&d_scene, 32));
+  CK(tmp.alloc(&d_keys, (size_t)n * 8)); CK(tmp.alloc(&d_keys2, (size_t)n * 8)); CK(tmp.alloc(&d_vals, (size_t)n * 4)); CK(tmp.alloc(&d_sorted, (size_t)n * 4));
+  CK(tmp.alloc(&d_left, ni * 4)); CK(tmp.alloc(&d_right, ni * 4)); CK(tmp.alloc(&d_first, ni * 4)); CK(tmp.alloc(&d_last, ni * 4));
+  CK(tmp.alloc(&d_pint, ni * 4)); CK(tmp.alloc(&d_pleaf, (size_t)n * 4)); CK(tmp.alloc(&d_visit, ni * 4));
+  const uint32_t scene_init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+  CK(cudaMemcpyAsync(d_scene, scene_init, sizeof(scene_init), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(d_visit, 0, ni * 4, st));
+  const int B = 256, grid_n = (n + B - 1) / B;
+  k_db_boxes<<<grid_n, B, 0, st>>>(sc, d_pbox, d_scene);
+  k_db_morton<<<grid_n, B, 0, st>>>(n, d_pbox, d_scene, d_keys, d_vals);
+  size_t cub_bytes = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, d_keys, d_keys2, d_vals, d_sorted, n, 0, 63, st));
+  void* d_cub = nullptr; CK(tmp.alloc(&d_cub, cub_bytes + 16));
+  CK(cub::DeviceRadixSort::SortPairs(d_cub, cub_bytes, d_keys, d_keys2, d_vals, d_sorted, n, 0, 63, st));
+  if (n > 1) {
+    k_db_tree<<<(n - 1 + B - 1) / B, B, 0, st>>>(n, d_keys2, d_left, d_right, d_first, d_last, d_pint, d_pleaf);
+    k_db_refit<<<grid_n, B, 0, st>>>(n, d_left, d_right, d_pint, d_pleaf, d_pbox, d_sorted, d_ibox, d_visit);
+  }
+  CK(cudaGetLastError());
+  // collapse, one level of wide nodes per launch
+  const unsigned node_cap = (unsigned)n + 8u;      // every wide node below the root holds >= 2 primitives and has >= 2 children
+  WideNode* d_nodes = nullptr; int32_t* d_slot = nullptr; int2 *d_items[2] = {nullptr, nullptr}; unsigned int* d_cnt = nullptr;
+  CK(tmp.alloc(&d_nodes, (size_t)node_cap * sizeof(WideNode))); CK(tmp.alloc(&d_slot, (size_t)n * 4));
+  CK(tmp.alloc(&d_items[0], (size_t)node_cap * 8)); CK(tmp.alloc(&d_items[1], (size_t)node_cap * 8)); CK(tmp.alloc(&d_cnt, 16));
+  const unsigned int cnt_init[4] = {1u, 0u, 0u, 0u};               // the root is wide node 0
+  CK(cudaMemcpyAsync(d_cnt, cnt_init, sizeof(cnt_init), cudaMemcpyHostToDevice, st));
+  const int2 root_item = make_int2(n > 1 ? 0 : -1, 0);              // a single primitive: sorted leaf 0
+  CK(cudaMemcpyAsync(d_items[0], &root_item, sizeof(root_item), cudaMemcpyHostToDevice, st));
+  DbTree T; T.left = d_left; T.right = d_right; T.first = d_first; T.last = d_last; T.ibox = d_ibox; T.pbox = d_pbox; T.sorted = d_sorted;
+  CK(cudaStreamSynchronize(st));
+  const double t1 = now();
+  unsigned n_items = 1; int levels = 0, cur = 0;
+  while (n_items > 0) {
+    levels++;
+    if (levels > kStackEntries) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel(device_build): wide BVH deeper than the traversal stack");
+    k_db_collapse<<<(n_items + 127) / 128, 128, 0, st>>>(T, d_items[cur], (int)n_items, d_items[cur ^ 1], d_cnt, d_nodes, d_slot, node_cap);
+    unsigned int h[4];
+    CK(cudaMemcpyAsync(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h[3]) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel(device_build): wide node pool exhausted");
+    n_items = h[2];
+    const unsigned int zero = 0;
+    CK(cudaMemcpyAsync(d_cnt + 2, &zero, 4, cudaMemcpyHostToDevice, st));
+    cur ^= 1;
+  }
+  unsigned int h[4];
+  CK(cudaMemcpy(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
+  const size_t n_wide = h[0], n_slots = h[1];
+  if (n_slots != (size_t)n) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel(device_build): primitive slots do not add up");
+  const double t2 = now();
+  PrimRecord* d_recs = nullptr; ShadeRecord* d_shd = nullptr;
+  CK(tmp.alloc(&d_recs, n_slots * sizeof(PrimRecord))); CK(tmp.alloc(&d_shd, n_slots * sizeof(ShadeRecord)));
+  k_db_flatten<<<(unsigned)((n_slots + B - 1) / B), B, 0, st>>>(sc, (int)n_slots, d_slot, d_recs, d_shd);
+  CK(cudaGetLastError());
+  ctx->wide.nodes.resize(n_wide); ctx->wide.slot_prim.resize(n_slots); ctx->wide.max_depth = levels;
+  ctx->recs.resize(n_slots); ctx->shd.resize(n_slots);
+  CK(cudaMemcpyAsync(ctx->wide.nodes.data(), d_nodes, n_wide * sizeof(WideNode), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->wide.slot_prim.data(), d_slot, n_slots * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->recs.data(), d_recs, n_slots * sizeof(PrimRecord), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(ctx->shd.data(), d_shd, n_slots * sizeof(ShadeRecord), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (timing) fprintf(stderr, "device_build: %d prims, upload + boxes + morton + sort + tree + refit %.3f s, collapse (%d levels, %zu wide nodes) %.3f s, records + read-back %.3f s\n",
+                      n, t1 - t0, levels, n_wide, t2 - t1, now() - t2);
+  return DSRT_OK;
+}
+
 int dsrt_build_accel(dsrt_ctx* ctx) {
   if (!ctx) return DSRT_ERR_INVALID;
-  if (!ctx->have_scene || !ctx->have_bvh) return fail(ctx, DSRT_ERR_INVALID, "dsrt_build_accel: scene and BVH must be set first");
+  const bool on_device = ctx->opt_device_build != 0 && ctx->n_prims > 0;
+  if (!ctx->have_scene || (!ctx->have_bvh && !on_device)) return fail(ctx, DSRT_ERR_INVALID, "dsrt_build_accel: scene and BVH must be set first");
   dsrt_scene s{}; s.n_prims = ctx->n_prims; s.prim_type = ctx->prim_type.data(); s.prim_bsdf = ctx->prim_bsdf.data();
   s.tri_pos = ctx->tri_pos.data(); s.tri_nrm = ctx->tri_nrm.data(); s.sphere = ctx->sphere.data();
   std::vector<Box3> pbox; primitive_boxes(&s, pbox);
+  if (on_device) {
+    int rcd = build_wide_bvh_device(ctx, ctx->devs[0]);
+    if (rcd) return rcd;
+  } else {
   dsrt_bvh2 b{}; b.n_nodes = (int)ctx->node_start.size(); b.node_bbox = ctx->node_bbox.data(); b.node_start = ctx->node_start.data();
   b.node_range = ctx->node_range.data(); b.node_left = ctx->node_left.data(); b.node_right = ctx->node_right.data();
   b.prim_order = ctx->prim_order.data();
   std::string err;
   int rc = build_wide_bvh(b, pbox, ctx->n_prims, ctx->wide, err, (double)ctx->opt_prim_cost / 100.0);
   if (rc) return fail(ctx, rc, err);
+  }
   if (ctx->wide.max_depth > kStackEntries) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel: wide BVH deeper than the traversal stack");
   if (ctx->wide.slot_prim.size() >= ((size_t)1 << kOwnerShift)) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel: more than 2^27 primitives");
   Box3 all; all.reset(); for (const Box3& p : pbox) all.grow(p);
@@ -396,7 +497,7 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
   ctx->scene_diag = std::sqrt(dg) + 1.0;
   bounding_sphere(all, ctx->n_prims, ctx->bsphere);
 
-  flatten_records(s, ctx->wide, ctx->recs, ctx->shd);
+  if (!on_device) flatten_records(s, ctx->wide, ctx->recs, ctx->shd);
   ctx->r64.clear(); ctx->r64.shrink_to_fit();     // fp64 records: built and uploaded by the first dsrt_primary_hits(mode 1)
   ctx->n_light_samples = flatten_lights((int)ctx->light_type.size(), ctx->light_type.data(), ctx->light_param.data(), ctx->ns_area_light, ctx->env_w > 0, ctx->lights);
   ctx->n_lights = (int)ctx->lights.size();
@@ -422,37 +523,44 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
   return dsrt_upload_accel(ctx);
 }
 
-// H2D copy of the flattened scene (wide nodes, primitive / shading / fp64 records, BSDF and light tables) to every
-// GPU.  dsrt_build_accel calls it; callers may call it again to re-send the same scene (bench.py's e2e step).
+// Copy of the flattened scene (wide nodes, primitive / shading records, BSDF and light tables, environment tables) to every
+// GPU: ONE host-to-device copy, to the first device, then device-to-device copies from there to the others over NVLink
+// (the scene is replicated, fed from GPU 0).  dsrt_build_accel calls it; callers may call it again to re-send
+// the same scene (bench.py's e2e step).
 int dsrt_upload_accel(dsrt_ctx* ctx) {
   if (!ctx) return DSRT_ERR_INVALID;
   if (!ctx->have_accel) return fail(ctx, DSRT_ERR_INVALID, "dsrt_upload_accel: call dsrt_build_accel first");
   const size_t n = ctx->wide.slot_prim.size();
-  auto upload = [&](DevState& D) -> int {      // the scene is replicated on every GPU
-    CK(cudaSetDevice(D.device));
-    CK(cudaMemcpyAsync(D.d_nodes, ctx->wide.nodes.data(), ctx->wide.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, D.stream));
-    if (n) {
-      CK(cudaMemcpyAsync(D.d_prims, ctx->recs.data(), n * sizeof(PrimRecord), cudaMemcpyHostToDevice, D.stream));
-      CK(cudaMemcpyAsync(D.d_shade, ctx->shd.data(), n * sizeof(ShadeRecord), cudaMemcpyHostToDevice, D.stream));
-    }
-    if (!ctx->bsdfs.empty()) CK(cudaMemcpyAsync(D.d_bsdf, ctx->bsdfs.data(), ctx->bsdfs.size() * sizeof(Bsdf), cudaMemcpyHostToDevice, D.stream));
-    if (!ctx->lights.empty()) CK(cudaMemcpyAsync(D.d_lights, ctx->lights.data(), ctx->lights.size() * sizeof(Light), cudaMemcpyHostToDevice, D.stream));
+  const size_t np = (size_t)ctx->env_w * ctx->env_h;
+  auto parts_of = [&](DevState& D, std::vector<std::pair<void*, std::pair<const void*, size_t>>>& out) {
+    out.clear();
+    auto add = [&](void* d, const void* s, size_t b) { if (b) out.push_back({d, {s, b}}); };
+    add(D.d_nodes, ctx->wide.nodes.data(), ctx->wide.nodes.size() * sizeof(WideNode));
+    add(D.d_prims, ctx->recs.data(), n * sizeof(PrimRecord));
+    add(D.d_shade, ctx->shd.data(), n * sizeof(ShadeRecord));
+    add(D.d_bsdf, ctx->bsdfs.data(), ctx->bsdfs.size() * sizeof(Bsdf));
+    add(D.d_lights, ctx->lights.data(), ctx->lights.size() * sizeof(Light));
     if (ctx->env_w > 0) {
-      const size_t np = (size_t)ctx->env_w * ctx->env_h;
-      CK(cudaMemcpyAsync(D.d_env_rgb, ctx->env_rgb.data(), np * 3 * sizeof(float), cudaMemcpyHostToDevice, D.stream));
-      CK(cudaMemcpyAsync(D.d_env_tp, ctx->env_tp.data(), np * sizeof(float), cudaMemcpyHostToDevice, D.stream));
-      CK(cudaMemcpyAsync(D.d_env_t, ctx->env_t.data(), (size_t)ctx->env_h * sizeof(float), cudaMemcpyHostToDevice, D.stream));
-      CK(cudaMemcpyAsync(D.d_env_pgt, ctx->env_pgt.data(), np * sizeof(float), cudaMemcpyHostToDevice, D.stream));
+      add(D.d_env_rgb, ctx->env_rgb.data(), np * 3 * sizeof(float));
+      add(D.d_env_tp, ctx->env_tp.data(), np * sizeof(float));
+      add(D.d_env_t, ctx->env_t.data(), (size_t)ctx->env_h * sizeof(float));
+      add(D.d_env_pgt, ctx->env_pgt.data(), np * sizeof(float));
     }
-    CK(cudaStreamSynchronize(D.stream));
-    return DSRT_OK;
   };
-  if (ctx->devs.size() == 1) return upload(ctx->devs[0]);
-  std::vector<int> rcs(ctx->devs.size(), DSRT_OK);     // pageable-memory copies block the calling thread: one thread per GPU
-  std::vector<std::thread> workers;
-  for (size_t r = 0; r < ctx->devs.size(); r++) workers.emplace_back([&, r] { rcs[r] = upload(ctx->devs[r]); });
-  for (std::thread& t : workers) t.join();
-  for (int rc : rcs) if (rc) return rc;
+  std::vector<std::pair<void*, std::pair<const void*, size_t>>> p0, pr;
+  DevState& D0 = ctx->devs[0];
+  CK(cudaSetDevice(D0.device));
+  parts_of(D0, p0);
+  for (auto& p : p0) CK(cudaMemcpyAsync(p.first, p.second.first, p.second.second, cudaMemcpyHostToDevice, D0.stream));
+  CK(cudaStreamSynchronize(D0.stream));
+  for (size_t r = 1; r < ctx->devs.size(); r++) {       // peers: device 0's copy is the source, all peers in flight together
+    DevState& D = ctx->devs[r];
+    CK(cudaSetDevice(D.device));
+    parts_of(D, pr);
+    for (size_t k = 0; k < pr.size(); k++)
+      CK(cudaMemcpyPeerAsync(pr[k].first, D.device, p0[k].first, D0.device, pr[k].second.second, D.stream));
+  }
+  for (size_t r = 1; r < ctx->devs.size(); r++) { CK(cudaSetDevice(ctx->devs[r].device)); CK(cudaStreamSynchronize(ctx->devs[r].stream)); }
   return DSRT_OK;
 }
 

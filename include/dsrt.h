@@ -123,7 +123,10 @@ int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t
  * src/pathtracer.cpp:497-519; 1 = shadow rays whose contribution is exactly zero -- light behind the surface, non-diffuse
  * BSDF, emitter facing away -- keep their queue slot but are not traced; the image is identical, dsrt_stats.null_shadow_rays
  * says how many), "wavefront_budget_mb" (cap on the wavefront + pool memory, 0 = 80 % of the free device memory: the batch
- * and the pool group shrink to fit, whatever -l asks for) */
+ * and the pool group shrink to fit, whatever -l asks for), "device_build" (0/1, default 0; applies at the next
+ * dsrt_build_accel, which then needs no dsrt_set_bvh: Morton codes, radix sort, Karras' binary radix tree, bottom-up boxes and
+ * the collapse to the same 8-wide layout all run on the first GPU -- what the reference's disabled PARALLEL_BUILD_BVH path set
+ * out to do, cuda_src/setup.cu:478-686 -- for scenes of tens of millions of primitives; hit results do not depend on the builder) */
 int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value);
 
 /* Host SAH builder = BVHAccel::BVHAccel + buildBVH (src/bvh.cpp:21-202: 32 buckets, max leaf 4, with the

@@ -9,7 +9,7 @@ import dsgpuraytracing_b200 as D
 from oracle import oracle as O
 from tests.cpuwalk import Walk
 from tests.scenes import CONFIGS, ID_RES, RMSE_RES, RMSE_SPP, SMALL_RES
-from tests.util import images_match
+from tests.util import images_match, plog
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -37,8 +37,10 @@ def test_primary_hit_ids_bit_exact(name, core, golden):
     assert np.array_equal(ts[ok], g["hit_t"][ok])            # t is bit-exact too (fp64 leaf tests, reference op order)
     # production float kernel (watertight test): silhouette pixels may flip; report and bound
     ids0, ts0 = core.primary_hits(mode=0)
-    frac = (ids0 != g["hit_id"]).mean()
-    assert frac < 2e-3, frac
+    flips = int((ids0 != g["hit_id"]).sum())
+    plog(gate="ids", scene=name, res=list(ID_RES), parity_kernel_mismatches=0, ties=int(g["hit_tie"].sum()),
+         production_float_kernel_mismatches=flips, pixels=int(ids0.size))
+    assert flips <= 2, flips          # measured: 0 on every fixture scene (float watertight test vs the reference's fp64 Moller-Trumbore)
     same = (ids0 == g["hit_id"]) & (g["hit_id"] >= 0)
     assert np.max(np.abs(ts0[same] - g["hit_t"][same]) / g["hit_t"][same]) < 1e-3
 
@@ -73,7 +75,7 @@ def test_image_gate_1024spp(name, core, golden):
     # moves a plain RMSE by >1 %; such pixels are counted (at most 5 in 10 000 allowed) and excluded from the RMSE.
     ok, info = images_match(rgb, ref, pixel_tol=0.05, max_bad_fraction=5e-4, rmse_tol=0.01)
     assert ok, info
-    plain = np.sqrt(((rgb - ref) ** 2).mean(axis=(0, 1))) / ref.mean(axis=(0, 1))
+    plain = np.sqrt(((rgb - ref) ** 2).mean(axis=(0, 1))) / np.maximum(ref.mean(axis=(0, 1)), 1e-12)
     print(f"{name}: plain rel RMSE {plain.max():.2e}, flipped pixels {info['n_bad']}, RMSE of the rest {info['rel_rmse_of_matching_pixels']:.2e}")
     assert abs(int(st.extend_rays) - int(ph["philox_cnt"][0])) <= 2e-4 * ph["philox_cnt"][0]
     assert abs(int(st.shadow_rays) - int(ph["philox_cnt"][1])) <= 2e-4 * ph["philox_cnt"][1]
@@ -84,6 +86,13 @@ def test_image_gate_1024spp(name, core, golden):
     k = 20
     floor = np.sqrt(((block_mean(a, k) - block_mean(b, k)) ** 2).mean())
     got = np.sqrt(((block_mean(rgb.astype(np.float64), k) - block_mean(a, k)) ** 2).mean())
+    am = np.maximum(a.mean(axis=(0, 1)), 1e-12)
+    plog(gate="rmse_1024spp", scene=name, res=list(RMSE_RES), plain_rel_rmse_vs_philox_oracle=[float(x) for x in plain],
+         flipped_pixels=info["n_bad"], masked_rel_rmse=info["rel_rmse_of_matching_pixels"],
+         per_pixel_rel_rmse_vs_reference_rand=[float(x) for x in np.sqrt(((rgb - a) ** 2).mean(axis=(0, 1))) / am],
+         reference_vs_reference_per_pixel_rel_rmse=[float(x) for x in np.sqrt(((a - b) ** 2).mean(axis=(0, 1))) / am],
+         block20_rmse_vs_reference=float(got), block20_rmse_reference_vs_reference=float(floor),
+         extend=[int(st.extend_rays), int(ph["philox_cnt"][0])], shadow=[int(st.shadow_rays), int(ph["philox_cnt"][1])])
     assert got < 1.6 * floor + 1e-4, (got, floor)
 
 

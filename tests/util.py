@@ -17,3 +17,13 @@ def images_match(rgb, ref, pixel_tol=2e-3, max_bad_fraction=3e-3, rmse_tol=5e-4)
     rmse = float(np.sqrt(((rgb - ref)[good] ** 2).mean()) / mean) if good.any() else 0.0
     ok = frac <= max_bad_fraction and rmse <= rmse_tol
     return ok, {"bad_pixel_fraction": frac, "rel_rmse_of_matching_pixels": rmse, "n_bad": int(bad.sum())}
+
+
+def plog(**kw):
+    """Append one JSON line of measured parity figures to $DSRT_PARITY_LOG (profiles/r2_parity.md is built from it)."""
+    import json
+    import os
+    p = os.environ.get("DSRT_PARITY_LOG")
+    if p:
+        with open(p, "a") as f:
+            f.write(json.dumps(kw) + "\n")

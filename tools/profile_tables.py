@@ -31,7 +31,7 @@ json.dump({"traffic_bytes_per_launch": int(rd + wr),
            "launch": "k_trace<true> (connect) at depth 0 of one 4-spp wavefront batch at 1080p (8.3 M camera paths): 33.2 M shadow rays, %.3f ms under ncu" % g(conn, "gpu__time_duration.sum"),
            "dram_read_bytes": int(rd), "dram_write_bytes": int(wr),
            "algorithmic_bytes_in_launch": int(n_rays * bench["roofline"]["bytes_per_segment"]),
-           "source": "profiles/r1_ktrace_depth0_raw.csv (ncu --set full --clock-control none --import-source on -k regex:k_trace -s 18 -c 2 python profiles/profile_run.py 4; final build of round 1)",
+           "source": "" + os.path.relpath(sys.argv[1], ROOT) + " (ncu --set full --clock-control none --import-source on -k regex:k_trace -s 18 -c 2 python profiles/profile_run.py 4)",
            "note": "DRAM traffic = streaming the 48-byte shadow-queue records once (33.2 M x 48 B = 1.59 GB) + framebuffer atomics; node / primitive fetches are served by L1 and L2"},
           open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"), "w"), indent=1)
 K = [("duration (ms)", "gpu__time_duration.sum", "%.3f"), ("warp instructions (M)", "smsp__inst_executed.sum", None),

@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--depth", type=int, default=-1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0, help="host processes for the CPU arm (0 = all cores)")
+    ap.add_argument("--split", default="samples", choices=["samples", "tiles"],
+                    help="N > 1: each GPU takes a disjoint slice of the samples of every pixel (default) or a horizontal band of the image")
+    ap.add_argument("--device-build", action="store_true", help="option device_build: LBVH + collapse on the GPU instead of the host SAH builder")
     ap.add_argument("--skip-null-shadow", action="store_true", help="option skip_null_shadow (default off: the reference traces them)")
     a = ap.parse_args()
     label, w, h, spp, nl, depth = WORKLOADS[a.workload]
@@ -73,7 +76,8 @@ def parse():
 def workload_config(a, n_gpus, triangles=None):
     return {"workload": a.label, "name": a.workload,
             "width": a.width, "height": a.height, "spp": a.spp, "light_samples": a.light_samples, "max_depth": a.depth,
-            "triangles": triangles, "parallelism": f"sample-split x{n_gpus} + 1 NCCL reduce" if n_gpus > 1 else "single GPU",
+            "triangles": triangles, "builder": "device LBVH + collapse (option device_build)" if a.device_build else "host SAH (reference topology) + DP collapse",
+            "parallelism": (f"{'tile' if a.split == 'tiles' else 'sample'}-split x{n_gpus} + 1 NCCL reduce") if n_gpus > 1 else "single GPU",
             "l2": "explicit 256 MiB L2 flush between steps; the per-batch wavefront state (GBs, larger than L2) streams through "
                   "L2; the wide BVH + primitive records are re-read within a step"}
 
@@ -227,11 +231,11 @@ def run_ours(a):
     sc, cam = w["sc"], w["camera"]
     n_tris = int(len(sc["prim_type"]))
     t_sah0 = time.perf_counter()
-    bvh = D.build_bvh2(sc)
+    bvh = None if a.device_build else D.build_bvh2(sc)
     sah_seconds = time.perf_counter() - t_sah0
     core = D.Core(local)
     core.set_params(a.spp, a.light_samples, a.depth, 0)
-    core.load(sc, camera=cam, bvh=bvh)
+    core.load(sc, camera=cam, bvh=bvh, device_build=a.device_build)
     if a.skip_null_shadow:
         core.set_option("skip_null_shadow", 1)
     info = core.accel_info()
@@ -249,12 +253,18 @@ def run_ours(a):
     torch.cuda.synchronize(dev)
     spp_local = a.spp // world
     ev = lambda: torch.cuda.Event(enable_timing=True)
+    # how this rank's share of the frame is expressed to dsrt_render_device: (first sample, count, stride)
+    share = (rank, spp_local, world)
+    if world > 1 and a.split == "tiles":          # tile partitioning: a band of rows, all samples; the same sum-reduce combines the bands
+        y0 = a.height * rank // world; y1 = a.height * (rank + 1) // world
+        core.set_window(0, y0, a.width, y1 - y0)
+        share = (0, a.spp, 1)
 
     def step(i, marks=None):
         flush.fill_(float(i))
         accum.zero_()
         if marks: marks[0].record(stream)
-        core.render_device(accum.data_ptr(), rank, spp_local, world, stream=stream.cuda_stream)
+        core.render_device(accum.data_ptr(), *share, stream=stream.cuda_stream)
         if marks: marks[1].record(stream)
         if world > 1:
             dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
@@ -317,7 +327,10 @@ def run_ours(a):
     # Scene PREPARATION on the host (SAH build, collapse to the wide BVH, record flattening) is one-off per scene, as
     # in the reference (PathTracer::build_accel runs at set_scene time), and is reported separately below.
     t_prep0 = time.perf_counter()
-    core.set_scene(sc); core.set_bvh(bvh); core.build_accel()
+    core.set_scene(sc)
+    if bvh is not None:
+        core.set_bvh(bvh)
+    core.build_accel()
     scene_prepare_s = time.perf_counter() - t_prep0
     h2d = core.accel_bytes() + 200
     d2h = npix * 12
@@ -327,7 +340,9 @@ def run_ours(a):
             core.render(out=host_rgb.numpy().reshape(a.height, a.width, 3))                   # dsrt_render: host frame out
         else:
             accum.zero_()
-            core.render_device(accum.data_ptr(), rank, spp_local, world, stream=stream.cuda_stream)
+            if a.split == "tiles":
+                core.set_window(0, a.height * rank // world, a.width, a.height * (rank + 1) // world - a.height * rank // world)
+            core.render_device(accum.data_ptr(), *share, stream=stream.cuda_stream)
             dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0:
                 core.resolve_device(accum.data_ptr(), rgb.data_ptr(), 0, stream=stream.cuda_stream)
@@ -357,7 +372,7 @@ def run_ours(a):
     # ---- roofline of the dominant kernel: algorithmic bytes / CUDA-event time of its launches (last timed step)
     core.set_option("count_traversal", 1)
     accum.zero_()
-    stc = core.render_device(accum.data_ptr(), rank, spp_local, world, stream=stream.cuda_stream, collect=True)
+    stc = core.render_device(accum.data_ptr(), *share, stream=stream.cuda_stream, collect=True)
     core.set_option("count_traversal", 0)
     kinds = {"extend (closest-hit traversal, k_trace<false>)": (st.extend_seconds, stc.extend_nodes, stc.extend_prims, st.extend_rays),
              "connect (any-hit traversal, k_trace<true>)": (st.connect_seconds, stc.connect_nodes, stc.connect_prims, st.shadow_rays - st.null_shadow_rays)}

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 EXPORTED_SYMBOLS = [
     "dsrt_create", "dsrt_create_multi", "dsrt_device_count", "dsrt_destroy", "dsrt_last_error", "dsrt_version", "dsrt_set_scene", "dsrt_set_bvh",
-    "dsrt_set_camera", "dsrt_set_params", "dsrt_set_envmap", "dsrt_set_option", "dsrt_build_bvh2", "dsrt_build_accel",
+    "dsrt_set_camera", "dsrt_set_window", "dsrt_set_params", "dsrt_set_envmap", "dsrt_set_option", "dsrt_build_bvh2", "dsrt_build_accel",
     "dsrt_accel_info", "dsrt_upload_accel", "dsrt_accel_bytes", "dsrt_render", "dsrt_render_tonemapped", "dsrt_cancel", "dsrt_render_device", "dsrt_resolve_device", "dsrt_sync",
     "dsrt_collect_stats", "dsrt_primary_hits", "dsrt_trace_closest", "dsrt_trace_any", "dsrt_tonemap", "dsrt_measure_read_bandwidth",
 ]
@@ -166,6 +166,10 @@ class Core:
         self.width, self.height = int(cam[12]), int(cam[13])
         self._ck(self.L.dsrt_set_camera(self.ctx, C.c_void_p(pos.ctypes.data), C.c_void_p(c2w.ctypes.data),
                                         self.width, self.height, C.c_double(float(cam[14]))), "dsrt_set_camera")
+
+    def set_window(self, x0=0, y0=0, width=0, height=0):
+        """Tile partitioning: render only the pixels [x0, x0+width) x [y0, y0+height); width=0 clears the window."""
+        self._ck(self.L.dsrt_set_window(self.ctx, int(x0), int(y0), int(width), int(height)), "dsrt_set_window")
 
     def set_params(self, ns_aa, ns_area_light, max_depth, seed=0):
         self.ns_aa = int(ns_aa)

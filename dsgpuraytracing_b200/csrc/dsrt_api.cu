@@ -76,6 +76,7 @@ struct dsrt_ctx {
   int env_w = 0, env_h = 0;
   std::vector<float> env_rgb, env_tp, env_t, env_pgt;
   double scene_diag = 1.0;
+  int win[4] = {0, 0, 0, 0};               // dsrt_set_window: x0, y0, width, height (width 0 = the whole frame)
   float bsphere[4] = {0.f, 0.f, 0.f, 0.f};   // centre + radius of a sphere around all primitives (Accel::bcx..brad)
   int n_lights = 0, n_light_samples = 0;
 };
@@ -121,9 +122,11 @@ Accel make_accel(const dsrt_ctx* ctx, const DevState& D, bool parity) {
 
 // shared-memory traversal stack: one node group per wide-BVH level per lane (whatever is not used stays L1 cache)
 int stack_entries(const dsrt_ctx* ctx) { return std::max(ctx->wide.max_depth, 1) + DSRT_STACK_SLACK; }
-// dynamic shared memory of k_trace: traversal stacks + (any-hit kernel) ray blocks, pair tables, hit flags
-size_t stack_bytes(const dsrt_ctx* ctx) {
-  return (size_t)stack_entries(ctx) * kTraceThreads * sizeof(uint2) + (size_t)kRayBlock * kTraceThreads * sizeof(float) +
+// dynamic shared memory of k_trace: traversal stacks + the lanes' ray blocks; the any-hit kernel adds pair tables and hit flags
+size_t stack_bytes(const dsrt_ctx* ctx, bool any = true) {
+  const size_t stack = (size_t)stack_entries(ctx) * kTraceThreads * sizeof(uint2);
+  if (!any) return stack + (size_t)kRayBlockClosest * kTraceThreads * sizeof(float);
+  return stack + (size_t)kRayBlock * kTraceThreads * sizeof(float) +
          (size_t)(kTraceThreads / 32) * kPairCap * kPairBytes + kTraceThreads + (kTraceThreads / 32) * sizeof(uint32_t);
 }
 
@@ -334,6 +337,20 @@ int dsrt_set_camera(dsrt_ctx* ctx, const double* pos, const double* c2w, int32_t
   c.W64 = width; c.H64 = height; c.dist64 = screen_dist;
   c.w_over_dist = (float)(width / screen_dist); c.h_over_dist = (float)(height / screen_dist);
   ctx->have_cam = true;
+  ctx->win[0] = ctx->win[1] = ctx->win[2] = ctx->win[3] = 0;       // a new frame size: back to the whole frame
+  return DSRT_OK;
+}
+
+// Tile partitioning (north_star: "disjoint slice of samples per pixel (or image tiles)"): the render calls that follow only
+// generate camera samples for the pixels of [x0, x0+width) x [y0, y0+height); buffers keep the frame's size and indexing, so
+// partial frames of disjoint windows add up exactly like partial frames of disjoint sample sets.  width == 0 clears the window.
+int dsrt_set_window(dsrt_ctx* ctx, int32_t x0, int32_t y0, int32_t width, int32_t height) {
+  if (!ctx) return DSRT_ERR_INVALID;
+  if (!ctx->have_cam) return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_window: call dsrt_set_camera first");
+  if (width == 0) { ctx->win[0] = ctx->win[1] = ctx->win[2] = ctx->win[3] = 0; return DSRT_OK; }
+  if (x0 < 0 || y0 < 0 || width < 0 || height <= 0 || x0 + width > ctx->cam.width || y0 + height > ctx->cam.height)
+    return fail(ctx, DSRT_ERR_INVALID, "dsrt_set_window: window outside the frame");
+  ctx->win[0] = x0; ctx->win[1] = y0; ctx->win[2] = width; ctx->win[3] = height;
   return DSRT_OK;
 }
 
@@ -620,7 +637,10 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   if (spp_count < 0 || spp_stride < 1 || spp_begin < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: bad sample range");
   CK(cudaSetDevice(D.device));
   { int rc0 = size_trace_grid(ctx, D); if (rc0) return rc0; }
-  const int W = ctx->cam.width, H = ctx->cam.height;
+  const bool windowed = ctx->win[2] > 0;
+  const int wx0 = windowed ? ctx->win[0] : 0, wy0 = windowed ? ctx->win[1] : 0;
+  const int W = windowed ? ctx->win[2] : ctx->cam.width, H = windowed ? ctx->win[3] : ctx->cam.height;     // extent rendered by this call
+  if (wx0 < 0 || wy0 < 0 || wx0 + W > ctx->cam.width || wy0 + H > ctx->cam.height) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: window outside the frame");
   const int blocks_x = (W + 7) / 8, blocks_y = (H + 3) / 4;
   const int npp = blocks_x * blocks_y * 32;
   const int aligned = (W % 8 == 0 && H % 4 == 0) ? 1 : 0;
@@ -648,11 +668,12 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   sc.env.w = ctx->env_w; sc.env.h = ctx->env_h;
   RenderParams rp; rp.cam = ctx->cam; rp.seed = ctx->seed; rp.max_depth = ctx->max_depth; rp.spp_begin = spp_begin; rp.spp_stride = spp_stride;
   rp.n_pix_padded = npp; rp.blocks_x = blocks_x; rp.skip_null_shadow = (int)ctx->opt_skip_null; rp.batch_first_sample = 0;
+  rp.win_x0 = wx0; rp.win_y0 = wy0; rp.win_x1 = wx0 + W; rp.win_y1 = wy0 + H;
   const Accel A = make_accel(ctx, D, false);
   const bool count = ctx->opt_count != 0, timing = ctx->opt_stage_timing != 0;
   const int tgrid = D.trace_blocks;
   const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, coop_min = (int)ctx->opt_coop_min;
-  const size_t sbytes = stack_bytes(ctx);
+  const size_t sbytes = stack_bytes(ctx), sbytes_closest = stack_bytes(ctx, false);
 
   auto span_begin = [&](int kind) { if (timing) { DevState::Span s; s.kind = kind; s.e0 = D.ev_used; cudaEventRecord(next_event(D), st); s.e1 = 0; D.spans.push_back(s); } };
   auto span_end = [&]() { if (timing) { D.spans.back().e1 = D.ev_used; cudaEventRecord(next_event(D), st); } };
@@ -676,8 +697,8 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
       if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, nullptr, contrib, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
       else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, nullptr, contrib, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
     } else {
-      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
-      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
+      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes_closest, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
+      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes_closest, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
     }
     span_end();
     D.launches++;
@@ -793,7 +814,7 @@ static int render_host(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int3
   ctx->cancel.store(0);
   const size_t npix = (size_t)ctx->cam.width * ctx->cam.height;
   const int G = (int)ctx->devs.size();
-  const int npp = ((ctx->cam.width + 7) / 8) * ((ctx->cam.height + 3) / 4) * 32;
+  const int npp = (((ctx->win[2] > 0 ? ctx->win[2] : ctx->cam.width) + 7) / 8) * (((ctx->win[2] > 0 ? ctx->win[3] : ctx->cam.height) + 3) / 4) * 32;
   std::vector<int> done((size_t)G, 0);
   // GPU r renders samples k with k mod G == r of the requested list (load is balanced whatever the image content)
   // one host thread per device: a frame is a few thousand launches, and enqueueing them device after device from one
@@ -926,11 +947,11 @@ int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) 
     if (rc) return rc;
     if (D.n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &D.d_counters, (size_t)1))) return rc; D.n_counter_blocks = 1; }
     CK(cudaMemsetAsync(D.d_counters, 0, sizeof(Counters), st));
-    RenderParams rp; std::memset(&rp, 0, sizeof(rp)); rp.cam = ctx->cam;
+    RenderParams rp; std::memset(&rp, 0, sizeof(rp)); rp.cam = ctx->cam; rp.win_x1 = ctx->cam.width; rp.win_y1 = ctx->cam.height;
     const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, coop_min = (int)ctx->opt_coop_min;
     k_generate_centres<<<(n + 255) / 256, 256, 0, st>>>(D.ps, rp, n);
     k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
-    k_trace<false, false><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(make_accel(ctx, D, false), D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0],
+    k_trace<false, false><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx, false), st>>>(make_accel(ctx, D, false), D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0],
                                                                             &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
     CK(cudaGetLastError());
     std::vector<float4> hits(n);
@@ -967,7 +988,7 @@ static int trace_batch(dsrt_ctx* ctx, bool any, int64_t n, const float* o, const
   const Accel A = make_accel(ctx, D, false);
   const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, coop_min = (int)ctx->opt_coop_min;
   if (any) k_trace<true, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
-  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
+  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx, false), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
   CK(cudaGetLastError());
   std::vector<float4> hits(n);
   CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));

@@ -37,12 +37,21 @@ constexpr int kTraceThreads = 128;        // 4 warps per CTA
 #define DSRT_PREFETCH_AHEAD 16384         // queue positions between a refill's loads and the L2 prefetches it issues (0 = off)
 #endif
 #ifndef DSRT_ONEHOT_PAIRS
-#define DSRT_ONEHOT_PAIRS 1               // pair table entries = (slot base | owner, one-hot primitive bit): the bit scan runs in the test, 32 lanes wide
+#define DSRT_ONEHOT_PAIRS 0               // 1: pair table entries = (slot base | owner, one-hot primitive bit), bit scan in the test: +0.2 % on the bench scene, but 3 KB more shared memory per CTA (-19 % on the 8 Mi soup)
 #endif
 #ifndef DSRT_NODE_STEPS
 #define DSRT_NODE_STEPS 2                 // node steps a lane may take between two warp-wide primitive-test decisions (1 / 2 / 3: 6839 / 6893 / 6741 Mrays/s)
 #endif
-constexpr int kRayBlock = DSRT_TRI_FAST ? 20 : 17;   // floats per lane published for the cooperative primitive test
+// Per-lane ray block in shared memory (value-major): what a lane needs to test ANOTHER lane's ray against a triangle.  Shared
+// memory is the scarce resource of this kernel -- every KB taken here is L1 taken from the node / primitive fetches (7 CTAs per
+// SM; on the 8 Mi-triangle soup 2.5 KB more per CTA cost 19 % of the frame rate) -- so the block holds nothing a sphere-only
+// path could fetch from global memory instead: the origin / direction of the owner's ray are re-read through its queue index.
+constexpr int kRbBasis = 0;                // 9 floats: watertight basis rows (the closest-hit kernel keeps only these)
+constexpr int kRbPo = 9;                   // 3 floats: -(origin . basis row), hit_triangle_any
+constexpr int kRbTmax = 12, kRbSrc = 13, kRbItem = 14;
+constexpr int kRbO = 15;                   // 3 floats: origin, only when DSRT_TRI_FAST == 0
+constexpr int kRayBlock = DSRT_TRI_FAST ? 15 : 18;   // floats per lane published for the cooperative primitive test
+constexpr int kRayBlockClosest = 9;
 #ifndef DSRT_PAIR_CAP
 #define DSRT_PAIR_CAP 192
 #endif
@@ -72,6 +81,7 @@ struct RenderParams {
   int spp_begin, spp_stride;
   int batch_first_sample;   // index (within this call) of the first sample of the batch
   int n_pix_padded, blocks_x;
+  int win_x0, win_y0, win_x1, win_y1;   // pixel window [x0,x1) x [y0,y1) this call renders (dsrt_set_window; default: the frame)
   int skip_null_shadow;
 };
 
@@ -99,8 +109,8 @@ __global__ void k_generate(PathState ps, RenderParams rp, int n_paths, uint32_t*
   const int s_local = i / rp.n_pix_padded, rank = i - s_local * rp.n_pix_padded;
   const int blk = rank >> 5, lane = rank & 31;
   const int bx = blk % rp.blocks_x, by = blk / rp.blocks_x;
-  const int x = bx * 8 + (lane & 7), y = by * 4 + (lane >> 3);
-  const bool valid = x < rp.cam.width && y < rp.cam.height;
+  const int x = rp.win_x0 + bx * 8 + (lane & 7), y = rp.win_y0 + by * 4 + (lane >> 3);
+  const bool valid = x < rp.win_x1 && y < rp.win_y1;
   if (valid) {
     const uint32_t pix = (uint32_t)(y * rp.cam.width + x);
     const uint32_t smp = (uint32_t)(rp.spp_begin + (rp.batch_first_sample + s_local) * rp.spp_stride);
@@ -179,10 +189,10 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
   const uint32_t s_stack = s_base + threadIdx.x * 8u;                                      // entry e at s_stack + e * kStackPitch
   const uint32_t s_blk0 = s_base + (uint32_t)stack_entries * kStackPitch;                   // ray blocks of the CTA
   const uint32_t s_blk_warp = s_blk0 + (threadIdx.x & ~31u) * 4u;                           // ... of this warp's lane 0
-  const uint32_t s_pair = s_blk0 + kRayBlock * kBlkPitch + (threadIdx.x >> 5) * (kPairCap * kPairBytes);
+  const uint32_t s_pair = s_blk0 + kRayBlock * kBlkPitch + (threadIdx.x >> 5) * (kPairCap * kPairBytes);       // any-hit kernel only from here on
   const uint32_t s_flag_warp = s_blk0 + kRayBlock * kBlkPitch + (kTraceThreads / 32) * (kPairCap * kPairBytes) + (threadIdx.x & ~31u);
   const uint32_t s_cnt = s_blk0 + kRayBlock * kBlkPitch + (kTraceThreads / 32) * (kPairCap * kPairBytes) + kTraceThreads + (threadIdx.x >> 5) * 4u;
-  if (lane == 0) sts32(s_cnt, 0u);
+  if (ANY && lane == 0) sts32(s_cnt, 0u);
   __syncwarp();
   const uint32_t n = *n_ptr;
   TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
@@ -245,20 +255,20 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           busy = true;
           const uint32_t rb = s_blk_warp + lane * 4u;
           if (ANY) {
-            stsf(rb + 0 * kBlkPitch, ray.ox); stsf(rb + 1 * kBlkPitch, ray.oy); stsf(rb + 2 * kBlkPitch, ray.oz);
-            stsf(rb + 3 * kBlkPitch, ray.dx); stsf(rb + 4 * kBlkPitch, ray.dy); stsf(rb + 5 * kBlkPitch, ray.dz);
-            stsf(rb + 15 * kBlkPitch, ray.tmax); sts32(rb + 16 * kBlkPitch, (uint32_t)ray.src_slot);
+            stsf(rb + kRbTmax * kBlkPitch, ray.tmax); sts32(rb + kRbSrc * kBlkPitch, (uint32_t)ray.src_slot); sts32(rb + kRbItem * kBlkPitch, item);
             if (DSRT_TRI_FAST) {
-              stsf(rb + 17 * kBlkPitch, -(ray.ox * wr.bxx + ray.oy * wr.bxy + ray.oz * wr.bxz));
-              stsf(rb + 18 * kBlkPitch, -(ray.ox * wr.byx + ray.oy * wr.byy + ray.oz * wr.byz));
-              stsf(rb + 19 * kBlkPitch, -(ray.ox * wr.bzx + ray.oy * wr.bzy + ray.oz * wr.bzz));
+              stsf(rb + (kRbPo + 0) * kBlkPitch, -(ray.ox * wr.bxx + ray.oy * wr.bxy + ray.oz * wr.bxz));
+              stsf(rb + (kRbPo + 1) * kBlkPitch, -(ray.ox * wr.byx + ray.oy * wr.byy + ray.oz * wr.byz));
+              stsf(rb + (kRbPo + 2) * kBlkPitch, -(ray.ox * wr.bzx + ray.oy * wr.bzy + ray.oz * wr.bzz));
+            } else {
+              stsf(rb + (kRbO + 0) * kBlkPitch, ray.ox); stsf(rb + (kRbO + 1) * kBlkPitch, ray.oy); stsf(rb + (kRbO + 2) * kBlkPitch, ray.oz);
             }
             sts8(s_flag_warp + lane, 0u);
           }
           {
-            stsf(rb + 6 * kBlkPitch, wr.bxx); stsf(rb + 7 * kBlkPitch, wr.bxy); stsf(rb + 8 * kBlkPitch, wr.bxz);
-            stsf(rb + 9 * kBlkPitch, wr.byx); stsf(rb + 10 * kBlkPitch, wr.byy); stsf(rb + 11 * kBlkPitch, wr.byz);
-            stsf(rb + 12 * kBlkPitch, wr.bzx); stsf(rb + 13 * kBlkPitch, wr.bzy); stsf(rb + 14 * kBlkPitch, wr.bzz);
+            stsf(rb + (kRbBasis + 0) * kBlkPitch, wr.bxx); stsf(rb + (kRbBasis + 1) * kBlkPitch, wr.bxy); stsf(rb + (kRbBasis + 2) * kBlkPitch, wr.bxz);
+            stsf(rb + (kRbBasis + 3) * kBlkPitch, wr.byx); stsf(rb + (kRbBasis + 4) * kBlkPitch, wr.byy); stsf(rb + (kRbBasis + 5) * kBlkPitch, wr.byz);
+            stsf(rb + (kRbBasis + 6) * kBlkPitch, wr.bzx); stsf(rb + (kRbBasis + 7) * kBlkPitch, wr.bzy); stsf(rb + (kRbBasis + 8) * kBlkPitch, wr.bzz);
           }
           }
         }
@@ -343,23 +353,25 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
                 const int slot = (int)(pw & ((1u << kOwnerShift) - 1u)); const uint32_t s = pw >> kOwnerShift;
                 const uint32_t rb = s_blk_warp + s * 4u;
                 TraceRay r2; WatertightRay w2;
-                if (!DSRT_TRI_FAST) { r2.ox = ldsf(rb + 0 * kBlkPitch); r2.oy = ldsf(rb + 1 * kBlkPitch); r2.oz = ldsf(rb + 2 * kBlkPitch); }
+                if (!DSRT_TRI_FAST) { r2.ox = ldsf(rb + (kRbO + 0) * kBlkPitch); r2.oy = ldsf(rb + (kRbO + 1) * kBlkPitch); r2.oz = ldsf(rb + (kRbO + 2) * kBlkPitch); }
                 r2.dx = r2.dy = r2.dz = 0.f;       // origin (fast triangle test) / direction are only needed by the sphere test (loaded there)
-                w2.bxx = ldsf(rb + 6 * kBlkPitch); w2.bxy = ldsf(rb + 7 * kBlkPitch); w2.bxz = ldsf(rb + 8 * kBlkPitch);
-                w2.byx = ldsf(rb + 9 * kBlkPitch); w2.byy = ldsf(rb + 10 * kBlkPitch); w2.byz = ldsf(rb + 11 * kBlkPitch);
-                w2.bzx = ldsf(rb + 12 * kBlkPitch); w2.bzy = ldsf(rb + 13 * kBlkPitch); w2.bzz = ldsf(rb + 14 * kBlkPitch);
-                const float tmax2 = ldsf(rb + 15 * kBlkPitch); const int src2 = (int)lds32(rb + 16 * kBlkPitch);
+                w2.bxx = ldsf(rb + (kRbBasis + 0) * kBlkPitch); w2.bxy = ldsf(rb + (kRbBasis + 1) * kBlkPitch); w2.bxz = ldsf(rb + (kRbBasis + 2) * kBlkPitch);
+                w2.byx = ldsf(rb + (kRbBasis + 3) * kBlkPitch); w2.byy = ldsf(rb + (kRbBasis + 4) * kBlkPitch); w2.byz = ldsf(rb + (kRbBasis + 5) * kBlkPitch);
+                w2.bzx = ldsf(rb + (kRbBasis + 6) * kBlkPitch); w2.bzy = ldsf(rb + (kRbBasis + 7) * kBlkPitch); w2.bzz = ldsf(rb + (kRbBasis + 8) * kBlkPitch);
+                const float tmax2 = ldsf(rb + kRbTmax * kBlkPitch); const int src2 = (int)lds32(rb + kRbSrc * kBlkPitch);
                 if (COUNT) cnt.prims++;
                 const float4* pp = A.prims + (size_t)slot * 3;
                 const float4 a = DSRT_PRIM_LD(pp), b = DSRT_PRIM_LD(pp + 1);
                 float t, u, v; bool h;
                 if (b.w != 0.0f) {
                   const float4 cc = DSRT_PRIM_LD(pp + 2);
-                  if (DSRT_TRI_FAST) h = (slot != src2) && hit_triangle_any(ldsf(rb + 17 * kBlkPitch), ldsf(rb + 18 * kBlkPitch), ldsf(rb + 19 * kBlkPitch), w2, a, b, cc, tmax2);
+                  if (DSRT_TRI_FAST) h = (slot != src2) && hit_triangle_any(ldsf(rb + (kRbPo + 0) * kBlkPitch), ldsf(rb + (kRbPo + 1) * kBlkPitch), ldsf(rb + (kRbPo + 2) * kBlkPitch), w2, a, b, cc, tmax2);
                   else h = (slot != src2) && hit_triangle(r2, w2, a, b, cc, tmax2, t, u, v);
                 } else {
-                  if (DSRT_TRI_FAST) { r2.ox = ldsf(rb + 0 * kBlkPitch); r2.oy = ldsf(rb + 1 * kBlkPitch); r2.oz = ldsf(rb + 2 * kBlkPitch); }
-                  r2.dx = ldsf(rb + 3 * kBlkPitch); r2.dy = ldsf(rb + 4 * kBlkPitch); r2.dz = ldsf(rb + 5 * kBlkPitch);
+                  // spheres are rare: the owner's origin / direction come back from its queue record (L1 / L2), not from shared memory
+                  const uint32_t item2 = lds32(rb + kRbItem * kBlkPitch);
+                  const float4 o2 = DSRT_RAY_LD(ray_o + item2), d2 = DSRT_RAY_LD(ray_d + item2);
+                  r2.ox = o2.x; r2.oy = o2.y; r2.oz = o2.z; r2.dx = d2.x; r2.dy = d2.y; r2.dz = d2.z;
                   h = hit_sphere(r2, a, b, leaves_sphere(src2, slot), true, tmax2, t);
                 }
                 if (h) sts8(s_flag_warp + s, 1u);
@@ -383,10 +395,10 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
               // the watertight basis lives in the lane's shared-memory ray block only (9 registers less in the loop)
               const uint32_t rb = s_blk_warp + lane * 4u;
               WatertightRay w2;
-              w2.bxx = ldsf(rb + 6 * kBlkPitch); w2.bxy = ldsf(rb + 7 * kBlkPitch); w2.bxz = ldsf(rb + 8 * kBlkPitch);
-              w2.byx = ldsf(rb + 9 * kBlkPitch); w2.byy = ldsf(rb + 10 * kBlkPitch); w2.byz = ldsf(rb + 11 * kBlkPitch);
-              w2.bzx = ldsf(rb + 12 * kBlkPitch); w2.bzy = ldsf(rb + 13 * kBlkPitch); w2.bzz = ldsf(rb + 14 * kBlkPitch);
-              if (ANY && DSRT_TRI_FAST) { h = (slot != ray.src_slot) && hit_triangle_any(ldsf(rb + 17 * kBlkPitch), ldsf(rb + 18 * kBlkPitch), ldsf(rb + 19 * kBlkPitch), w2, a, b, c, tbest); t = 0.f; }
+              w2.bxx = ldsf(rb + (kRbBasis + 0) * kBlkPitch); w2.bxy = ldsf(rb + (kRbBasis + 1) * kBlkPitch); w2.bxz = ldsf(rb + (kRbBasis + 2) * kBlkPitch);
+              w2.byx = ldsf(rb + (kRbBasis + 3) * kBlkPitch); w2.byy = ldsf(rb + (kRbBasis + 4) * kBlkPitch); w2.byz = ldsf(rb + (kRbBasis + 5) * kBlkPitch);
+              w2.bzx = ldsf(rb + (kRbBasis + 6) * kBlkPitch); w2.bzy = ldsf(rb + (kRbBasis + 7) * kBlkPitch); w2.bzz = ldsf(rb + (kRbBasis + 8) * kBlkPitch);
+              if (ANY && DSRT_TRI_FAST) { h = (slot != ray.src_slot) && hit_triangle_any(ldsf(rb + (kRbPo + 0) * kBlkPitch), ldsf(rb + (kRbPo + 1) * kBlkPitch), ldsf(rb + (kRbPo + 2) * kBlkPitch), w2, a, b, c, tbest); t = 0.f; }
               else h = (slot != ray.src_slot) && hit_triangle(ray, w2, a, b, c, tbest, t, u, v);
             } else {
               h = hit_sphere(ray, a, b, leaves_sphere(ray.src_slot, slot), ANY, tbest, t);

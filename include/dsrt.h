@@ -101,6 +101,11 @@ int dsrt_set_bvh(dsrt_ctx* ctx, const dsrt_bvh2* bvh);        /* loadBVH, setup.
  * replaces loadCamera, setup.cu:221-247 */
 int dsrt_set_camera(dsrt_ctx* ctx, const double* pos, const double* c2w, int32_t width, int32_t height,
                     double screen_dist);
+/* Tile partitioning: restricts the render calls that follow to the pixels [x0, x0+width) x [y0, y0+height) of the frame
+ * (buffers keep the frame's size; pixels outside stay untouched / zero).  Disjoint windows rendered on different GPUs add up
+ * to the frame exactly like disjoint sample sets do.  width == 0 clears it; dsrt_set_camera clears it too.  The reference's
+ * own tiling is its WorkQueue of image tiles, src/pathtracer.cpp:585-647. */
+int dsrt_set_window(dsrt_ctx* ctx, int32_t x0, int32_t y0, int32_t width, int32_t height);
 /* Lat-long environment map (row 0 = +y pole, width*height*3 floats): PathTracer's `envmap` constructor argument
  * (src/pathtracer.cpp:41-45) -> EnvironmentLight (src/static_scene/environment_light.cpp).  The light is appended after
  * the scene's lights; rays that leave the scene with includeLe see the map.  width == height == 0 removes it.

@@ -370,3 +370,63 @@ def test_device_built_bvh_on_the_measured_scenes(core):
         rgb, st = core.render()
         assert np.isfinite(rgb).all()
     core.set_option("device_build", 0)
+
+
+# ---- a failed call must not leave a half-updated context usable ------------------------------------------------------
+@pytest.mark.gpu
+def test_failed_scene_or_bvh_calls_invalidate_the_context(golden):
+    g = golden("CBspheres")
+    c = D.Core(0)
+    c.set_params(1, 1, 2, 0)
+    c.load(g, camera=g["small_camera"])
+    good, _ = c.render()
+    bad = dict(g); bad["bsdf_type"] = g["bsdf_type"].copy(); bad["bsdf_type"][-1] = 9
+    with pytest.raises(D.DsrtError, match="unknown BSDF type"):
+        c.set_scene(bad)
+    with pytest.raises(D.DsrtError, match="dsrt_build_accel"):          # nothing of the old scene is usable any more
+        c.render()
+    with pytest.raises(D.DsrtError, match="scene"):
+        c.set_bvh(D.build_bvh2(g))
+    # a BVH whose child points back at its parent (would loop forever) / whose children do not partition the parent's range
+    c.set_scene(g)
+    bvh = D.build_bvh2(g)
+    cyc = {k: v.copy() for k, v in bvh.items()}
+    inner = int(np.argmax(cyc["node_left"] >= 0)); cyc["node_left"][inner] = inner
+    c.set_bvh(cyc)
+    with pytest.raises(D.DsrtError, match="not numbered after its parent"):
+        c.build_accel()
+    part = {k: v.copy() for k, v in bvh.items()}
+    part["node_range"][int(part["node_left"][inner])] += 1
+    c.set_bvh(part)
+    with pytest.raises(D.DsrtError, match="partition"):
+        c.build_accel()
+    c.set_bvh(bvh); c.build_accel(); c.set_camera(g["small_camera"])
+    again, _ = c.render()
+    assert np.allclose(again, good, rtol=1e-5, atol=1e-7)
+    c.close()
+
+
+@pytest.mark.gpu
+def test_window_tiles_add_up_to_the_frame(core, golden):
+    """dsrt_set_window (tile partitioning, the alternative to the sample split): disjoint windows rendered separately are
+    zero outside their window and add up to the full frame; counters add up too."""
+    g = golden("CBgems"); cfg = CONFIGS["CBgems"]
+    W, H = SMALL_RES
+    core.set_params(4, cfg["nl"], cfg["depth"], 3)
+    core.load(g, camera=g["small_camera"])
+    full, st = core.render()
+    tiles = [(0, 0, 40, 30), (40, 0, W - 40, 30), (0, 30, W, 17), (0, 47, 13, H - 47), (13, 47, W - 13, H - 47)]    # ragged on purpose
+    total = np.zeros_like(full); ext = sh = cam = 0
+    for (x0, y0, w, h) in tiles:
+        core.set_window(x0, y0, w, h)
+        part, sp = core.render()
+        mask = np.zeros((H, W), bool); mask[y0:y0 + h, x0:x0 + w] = True
+        assert (part[~mask] == 0).all() and sp.camera_samples == w * h * 4
+        total += part; ext += sp.extend_rays; sh += sp.shadow_rays; cam += sp.camera_samples
+    core.set_window()
+    assert cam == st.camera_samples and ext == st.extend_rays and sh == st.shadow_rays
+    assert np.allclose(total, full, rtol=1e-5, atol=1e-7)
+    with pytest.raises(D.DsrtError, match="outside the frame"):
+        core.set_window(W - 4, 0, 8, 8)
+    again, _ = core.render()
+    assert np.allclose(again, full, rtol=1e-5, atol=1e-7)

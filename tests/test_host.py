@@ -316,3 +316,41 @@ def test_parallel_host_builders_do_not_depend_on_the_thread_count():
     assert i1 == i5 and np.array_equal(n1, n5) and np.array_equal(s1, s5)
     assert i1[0] > 1024 * 8          # large enough for the parallel emission path
     assert np.array_equal(np.sort(s1), np.arange(300000))
+
+
+def test_untrusted_file_fields_are_errors_not_crashes(tmp_path):
+    """a 64-bit chunk offset near 2^64 must not wrap the EXR reader's bounds check; negative / absurd `count`
+    attributes in a .dae must come back as an error string through the C boundary, never as an escaped C++ exception."""
+    import struct
+    from tests.exr_writer import write_exr
+    from dsgpuraytracing_b200 import scenes as S
+    a = np.random.default_rng(3).random((8, 6, 3)).astype(np.float32)
+    p = str(tmp_path / "ok.exr")
+    write_exr(p, {"R": a[..., 0], "G": a[..., 1], "B": a[..., 2]}, "none")
+    raw = bytearray(open(p, "rb").read())
+    assert np.array_equal(D.load_envmap(p), a)
+    # the line-offset table sits right after the header's terminating NUL: find the first chunk offset by value and poison it
+    first_chunk = None
+    for off in range(len(raw) - 8):
+        v = struct.unpack_from("<Q", raw, off)[0]
+        if v == off + 8 * 8:           # 8 scan lines, NONE compression: table of 8 offsets, the first chunk follows it
+            first_chunk = off; break
+    assert first_chunk is not None
+    for poison in (0xFFFFFFFFFFFFFFF0, 0xFFFFFFFFFFFFFFFF, len(raw) + 5, len(raw) - 3):
+        bad = bytearray(raw); struct.pack_into("<Q", bad, first_chunk, poison)
+        fp = str(tmp_path / "poison.exr"); open(fp, "wb").write(bad)
+        with pytest.raises(D.DsrtError, match="corrupt|truncated"):
+            D.load_envmap(fp)
+    # .dae counts
+    V, F = S.torus_knot(n_around=4, n_along=12); V = V.astype(np.float32).astype(np.float64)
+    dae = str(tmp_path / "k.dae"); S.write_cb_mesh_dae(dae, V, F)
+    text = open(dae).read()
+    assert len(D.load_dae(dae, 8, 8)[0]["prim_type"]) == 2 * 4 * 12 + 12
+    import re
+    for pat, rep in ((r'<polylist count="\d+">', '<polylist count="-1">', ), (r'<polylist count="\d+">', '<polylist count="2000000000">'),
+                     (r'(<float_array id="mesh-mesh-positions-array" count=)"\d+"', r'\1"-7"'), (r'(<float_array id="mesh-mesh-positions-array" count=)"\d+"', r'\1"1999999999"')):
+        broken, n = re.subn(pat, rep, text, count=1)
+        assert n == 1
+        fp = str(tmp_path / "broken.dae"); open(fp, "w").write(broken)
+        with pytest.raises(D.DsrtError, match="implausible|too short"):
+            D.load_dae(fp, 8, 8)

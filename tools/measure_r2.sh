@@ -24,5 +24,8 @@ rm -f $O/cfg_$T.jsonl
 for w in c3 c4 soup1 soup8 soup64; do
   python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline >> $O/cfg_$T.jsonl 2>> $O/cfg_$T.err; tail -1 $O/cfg_$T.jsonl | cut -c1-160
 done
+for w in soup1 soup8 soup64; do
+  python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline --device-build >> $O/cfg_$T.jsonl 2>> $O/cfg_$T.err; tail -1 $O/cfg_$T.jsonl | cut -c1-160
+done
 DSRT_BUILD_TIMING=1 python tools/device_build_bench.py 0 1 8 64 > $O/devbuild_$T.jsonl 2> $O/devbuild_$T.err; cat $O/devbuild_$T.jsonl | cut -c1-300
 cp dsgpuraytracing_b200/csrc/build.log $O/build_$T.log

@@ -22,15 +22,16 @@ def golden(name, W, H):
 
 
 N_GPUS = 1
+DEVICE_BUILD = False
 
 
 def run(tag, sc, cam, spp, nl, depth, reps=2):
-    t0 = time.time(); bvh = D.build_bvh2(sc); t_sah = time.time() - t0
+    t0 = time.time(); bvh = None if DEVICE_BUILD else D.build_bvh2(sc); t_sah = time.time() - t0
     # N_GPUS > 1: one context over N devices (dsrt_create_multi): sample-split render, partial framebuffers combined by
     # device 0 reading its peers over NVLink inside the resolve kernel
     core = D.Core(0) if N_GPUS == 1 else D.Core(devices=list(range(N_GPUS)))
     core.set_params(spp, nl, depth, 0)
-    t0 = time.time(); core.load(sc, camera=cam, bvh=bvh); t_accel = time.time() - t0
+    t0 = time.time(); core.load(sc, camera=cam, bvh=bvh, device_build=DEVICE_BUILD); t_accel = time.time() - t0
     core.set_option("stage_timing", 1)
     best = None; wall = None
     for _ in range(reps):
@@ -45,7 +46,7 @@ def run(tag, sc, cam, spp, nl, depth, reps=2):
     seg = best.segments
     nn = sc2.nodes_visited / sc2.segments; nt = sc2.prims_tested / sc2.segments
     bps = nn * 80 + nt * 48 + 48
-    out = {"case": tag, "n_gpus": N_GPUS, "prims": int(len(sc["prim_type"])), "wide_nodes": info["wide_nodes"], "wide_depth": info["max_depth"],
+    out = {"case": tag, "n_gpus": N_GPUS, "builder": "device" if DEVICE_BUILD else "host_sah", "prims": int(len(sc["prim_type"])), "wide_nodes": info["wide_nodes"], "wide_depth": info["max_depth"],
            "accel_MB": (info["node_bytes"] + info["prim_bytes"]) / 1e6, "sah_build_s": round(t_sah, 3), "flatten_upload_s": round(t_accel, 3),
            "width": int(cam[12]), "height": int(cam[13]), "spp": spp, "light_samples": nl, "max_depth": depth,
            "segments": int(seg), "segments_per_sample": seg / best.camera_samples, "s_per_frame": best.gpu_seconds, "wall_s_incl_reduce_and_readback": wall,
@@ -62,10 +63,12 @@ if __name__ == "__main__":
     ap.add_argument("--soup-min", type=int, default=1, help="smallest soup in Mi triangles")
     ap.add_argument("--quick", action="store_true", help="16 spp instead of the configured 256/512")
     ap.add_argument("--gpus", type=int, default=1, help="GPUs of this box driven by one context (dsrt_create_multi)")
+    ap.add_argument("--device-build", action="store_true", help="option device_build (LBVH + collapse on the first GPU) instead of the host SAH builder")
     ap.add_argument("--only", default="", help="comma list of case prefixes to run, e.g. C4,C5")
     a = ap.parse_args()
     q = a.quick
     N_GPUS = a.gpus
+    DEVICE_BUILD = a.device_build
     only = [x for x in a.only.split(",") if x]
     want = lambda c: not only or any(c == x for x in only)
     gtag = f"{N_GPUS} GPU" + ("s" if N_GPUS > 1 else "")

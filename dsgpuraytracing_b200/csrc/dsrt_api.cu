@@ -18,6 +18,7 @@
 #include "wide_bvh.h"
 #include "device_build.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <nvtx3/nvToolsExt.h>          // header-only: ranges show up in nsys / ncu timelines, no-ops otherwise
 #include <chrono>
 
 // ================================================================================================ host side
@@ -76,6 +77,7 @@ struct dsrt_ctx {
   int env_w = 0, env_h = 0;
   std::vector<float> env_rgb, env_tp, env_t, env_pgt;
   double scene_diag = 1.0;
+  bool recs_on_device = false;             // device_build: the primitive / shading records live on the first GPU only (no host copy)
   int win[4] = {0, 0, 0, 0};               // dsrt_set_window: x0, y0, width, height (width 0 = the whole frame)
   float bsphere[4] = {0.f, 0.f, 0.f, 0.f};   // centre + radius of a sphere around all primitives (Accel::bcx..brad)
   int n_lights = 0, n_light_samples = 0;
@@ -402,7 +404,7 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
 // Option "device_build": the wide BVH, the leaf-contiguous primitive order and the primitive / shading records are built on the
 // first device (device_build.cuh) from the caller's scene arrays and read back into the same host containers the host SAH path
 // fills, so everything downstream (uploads to every GPU, parity records, statistics) is shared.
-static int build_wide_bvh_device(dsrt_ctx* ctx, DevState& D) {
+static int build_wide_bvh_device(dsrt_ctx* ctx, DevState& D, float scene_box[6]) {
   const int n = ctx->n_prims;
   const bool timing = std::getenv("DSRT_BUILD_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -470,19 +472,22 @@ static int build_wide_bvh_device(dsrt_ctx* ctx, DevState& D) {
   }
   unsigned int h[4];
   CK(cudaMemcpy(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
+  { uint32_t so[6]; CK(cudaMemcpy(so, d_scene, sizeof(so), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 6; k++) { const uint32_t o = so[k]; const uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o; std::memcpy(&scene_box[k], &u, 4); } }
   const size_t n_wide = h[0], n_slots = h[1];
   if (n_slots != (size_t)n) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel(device_build): primitive slots do not add up");
   const double t2 = now();
-  PrimRecord* d_recs = nullptr; ShadeRecord* d_shd = nullptr;
-  CK(tmp.alloc(&d_recs, n_slots * sizeof(PrimRecord))); CK(tmp.alloc(&d_shd, n_slots * sizeof(ShadeRecord)));
-  k_db_flatten<<<(unsigned)((n_slots + B - 1) / B), B, 0, st>>>(sc, (int)n_slots, d_slot, d_recs, d_shd);
+  // The 48-byte primitive / shading records (the bulk of the structure) are written straight into this GPU's final arrays and
+  // never visit the host: the other GPUs get them GPU -> GPU (dsrt_upload_accel).  The nodes and the slot -> primitive map are
+  // read back (statistics, id mapping, the parity kernel's fp64 records).
+  dev_free(D.d_prims); dev_free(D.d_shade); D.d_prims = D.d_shade = nullptr;
+  CK(cudaMalloc(&D.d_prims, n_slots * sizeof(PrimRecord))); CK(cudaMalloc(&D.d_shade, n_slots * sizeof(ShadeRecord)));
+  k_db_flatten<<<(unsigned)((n_slots + B - 1) / B), B, 0, st>>>(sc, (int)n_slots, d_slot, (PrimRecord*)D.d_prims, (ShadeRecord*)D.d_shade);
   CK(cudaGetLastError());
   ctx->wide.nodes.resize(n_wide); ctx->wide.slot_prim.resize(n_slots); ctx->wide.max_depth = levels;
-  ctx->recs.resize(n_slots); ctx->shd.resize(n_slots);
+  ctx->recs.clear(); ctx->recs.shrink_to_fit(); ctx->shd.clear(); ctx->shd.shrink_to_fit(); ctx->recs_on_device = true;
   CK(cudaMemcpyAsync(ctx->wide.nodes.data(), d_nodes, n_wide * sizeof(WideNode), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(ctx->wide.slot_prim.data(), d_slot, n_slots * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(ctx->recs.data(), d_recs, n_slots * sizeof(PrimRecord), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(ctx->shd.data(), d_shd, n_slots * sizeof(ShadeRecord), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   if (timing) fprintf(stderr, "device_build: %d prims, upload + boxes + morton + sort + tree + refit %.3f s, collapse (%d levels, %zu wide nodes) %.3f s, records + read-back %.3f s\n",
                       n, t1 - t0, levels, n_wide, t2 - t1, now() - t2);
@@ -491,15 +496,24 @@ static int build_wide_bvh_device(dsrt_ctx* ctx, DevState& D) {
 
 int dsrt_build_accel(dsrt_ctx* ctx) {
   if (!ctx) return DSRT_ERR_INVALID;
+  struct Range { Range(const char* n) { nvtxRangePushA(n); } ~Range() { nvtxRangePop(); } } nvtx_range("dsrt_build_accel");
   const bool on_device = ctx->opt_device_build != 0 && ctx->n_prims > 0;
   if (!ctx->have_scene || (!ctx->have_bvh && !on_device)) return fail(ctx, DSRT_ERR_INVALID, "dsrt_build_accel: scene and BVH must be set first");
   dsrt_scene s{}; s.n_prims = ctx->n_prims; s.prim_type = ctx->prim_type.data(); s.prim_bsdf = ctx->prim_bsdf.data();
   s.tri_pos = ctx->tri_pos.data(); s.tri_nrm = ctx->tri_nrm.data(); s.sphere = ctx->sphere.data();
-  std::vector<Box3> pbox; primitive_boxes(&s, pbox);
-  if (on_device) {
-    int rcd = build_wide_bvh_device(ctx, ctx->devs[0]);
+  const bool timing = std::getenv("DSRT_BUILD_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tb0 = now();
+  std::vector<Box3> pbox;
+  Box3 all; all.reset();
+  if (on_device) {          // the device builder makes its own primitive boxes and hands back the scene box
+    float sb[6];
+    int rcd = build_wide_bvh_device(ctx, ctx->devs[0], sb);
     if (rcd) return rcd;
+    for (int k = 0; k < 3; k++) { all.lo[k] = sb[k]; all.hi[k] = sb[3 + k]; }
   } else {
+  primitive_boxes(&s, pbox);
+  for (const Box3& p : pbox) all.grow(p);
   dsrt_bvh2 b{}; b.n_nodes = (int)ctx->node_start.size(); b.node_bbox = ctx->node_bbox.data(); b.node_start = ctx->node_start.data();
   b.node_range = ctx->node_range.data(); b.node_left = ctx->node_left.data(); b.node_right = ctx->node_right.data();
   b.prim_order = ctx->prim_order.data();
@@ -509,23 +523,27 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
   }
   if (ctx->wide.max_depth > kStackEntries) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel: wide BVH deeper than the traversal stack");
   if (ctx->wide.slot_prim.size() >= ((size_t)1 << kOwnerShift)) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel: more than 2^27 primitives");
-  Box3 all; all.reset(); for (const Box3& p : pbox) all.grow(p);
+  const double tb1 = now();
   double dg = 0; for (int k = 0; k < 3; k++) { double e = ctx->n_prims ? all.hi[k] - all.lo[k] : 0; double m = ctx->n_prims ? std::fmax(std::fabs(all.lo[k]), std::fabs(all.hi[k])) : 0; dg += (e + m) * (e + m); }
   ctx->scene_diag = std::sqrt(dg) + 1.0;
   bounding_sphere(all, ctx->n_prims, ctx->bsphere);
 
-  if (!on_device) flatten_records(s, ctx->wide, ctx->recs, ctx->shd);
+  if (!on_device) { flatten_records(s, ctx->wide, ctx->recs, ctx->shd); ctx->recs_on_device = false; }
   ctx->r64.clear(); ctx->r64.shrink_to_fit();     // fp64 records: built and uploaded by the first dsrt_primary_hits(mode 1)
   ctx->n_light_samples = flatten_lights((int)ctx->light_type.size(), ctx->light_type.data(), ctx->light_param.data(), ctx->ns_area_light, ctx->env_w > 0, ctx->lights);
   ctx->n_lights = (int)ctx->lights.size();
   for (DevState& D : ctx->devs) {      // new sizes: (re)allocate the device copies
     CK(cudaSetDevice(D.device));
-    dev_free(D.d_nodes); dev_free(D.d_prims); dev_free(D.d_shade); dev_free(D.d_prims64); dev_free(D.d_bsdf); dev_free(D.d_lights);
-    D.d_nodes = D.d_prims = D.d_shade = D.d_prims64 = D.d_bsdf = D.d_lights = nullptr;
+    const bool keep_records = ctx->recs_on_device && &D == &ctx->devs[0];      // written in place by the device builder
+    dev_free(D.d_nodes); dev_free(D.d_prims64); dev_free(D.d_bsdf); dev_free(D.d_lights);
+    if (!keep_records) { dev_free(D.d_prims); dev_free(D.d_shade); D.d_prims = D.d_shade = nullptr; }
+    D.d_nodes = D.d_prims64 = D.d_bsdf = D.d_lights = nullptr;
     const size_t n = ctx->wide.slot_prim.size();
     CK(cudaMalloc(&D.d_nodes, std::max<size_t>(ctx->wide.nodes.size() * sizeof(WideNode), 16)));
-    CK(cudaMalloc(&D.d_prims, std::max<size_t>(n * sizeof(PrimRecord), 16)));
-    CK(cudaMalloc(&D.d_shade, std::max<size_t>(n * sizeof(ShadeRecord), 16)));
+    if (!keep_records) {
+      CK(cudaMalloc(&D.d_prims, std::max<size_t>(n * sizeof(PrimRecord), 16)));
+      CK(cudaMalloc(&D.d_shade, std::max<size_t>(n * sizeof(ShadeRecord), 16)));
+    }
     CK(cudaMalloc(&D.d_bsdf, std::max<size_t>(ctx->bsdfs.size() * sizeof(Bsdf), 16)));
     CK(cudaMalloc(&D.d_lights, std::max<size_t>(ctx->lights.size() * sizeof(Light), 16)));
     dev_free(D.d_env_rgb); dev_free(D.d_env_tp); dev_free(D.d_env_t); dev_free(D.d_env_pgt);
@@ -537,7 +555,11 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
     }
   }
   ctx->have_accel = true;
-  return dsrt_upload_accel(ctx);
+  const double tb2 = now();
+  const int rcu = dsrt_upload_accel(ctx);
+  if (timing) fprintf(stderr, "dsrt_build_accel: wide BVH %.3f s (%s), records + light tables + device allocation %.3f s, upload to %zu GPU(s) %.3f s\n",
+                      tb1 - tb0, on_device ? "device_build" : "host collapse", tb2 - tb1, ctx->devs.size(), now() - tb2);
+  return rcu;
 }
 
 // Copy of the flattened scene (wide nodes, primitive / shading records, BSDF and light tables, environment tables) to every
@@ -553,8 +575,8 @@ int dsrt_upload_accel(dsrt_ctx* ctx) {
     out.clear();
     auto add = [&](void* d, const void* s, size_t b) { if (b) out.push_back({d, {s, b}}); };
     add(D.d_nodes, ctx->wide.nodes.data(), ctx->wide.nodes.size() * sizeof(WideNode));
-    add(D.d_prims, ctx->recs.data(), n * sizeof(PrimRecord));
-    add(D.d_shade, ctx->shd.data(), n * sizeof(ShadeRecord));
+    add(D.d_prims, ctx->recs_on_device ? nullptr : ctx->recs.data(), n * sizeof(PrimRecord));      // no host source: resident on device 0
+    add(D.d_shade, ctx->recs_on_device ? nullptr : ctx->shd.data(), n * sizeof(ShadeRecord));
     add(D.d_bsdf, ctx->bsdfs.data(), ctx->bsdfs.size() * sizeof(Bsdf));
     add(D.d_lights, ctx->lights.data(), ctx->lights.size() * sizeof(Light));
     if (ctx->env_w > 0) {
@@ -568,7 +590,7 @@ int dsrt_upload_accel(dsrt_ctx* ctx) {
   DevState& D0 = ctx->devs[0];
   CK(cudaSetDevice(D0.device));
   parts_of(D0, p0);
-  for (auto& p : p0) CK(cudaMemcpyAsync(p.first, p.second.first, p.second.second, cudaMemcpyHostToDevice, D0.stream));
+  for (auto& p : p0) if (p.second.first) CK(cudaMemcpyAsync(p.first, p.second.first, p.second.second, cudaMemcpyHostToDevice, D0.stream));
   CK(cudaStreamSynchronize(D0.stream));
   for (size_t r = 1; r < ctx->devs.size(); r++) {       // peers: device 0's copy is the source, all peers in flight together
     DevState& D = ctx->devs[r];
@@ -584,7 +606,7 @@ int dsrt_upload_accel(dsrt_ctx* ctx) {
 int dsrt_accel_bytes(const dsrt_ctx* ctx, int64_t* h2d_bytes) {
   if (!ctx || !ctx->have_accel || !h2d_bytes) return DSRT_ERR_INVALID;
   const size_t n = ctx->wide.slot_prim.size();
-  *h2d_bytes = (int64_t)(ctx->wide.nodes.size() * sizeof(WideNode) + n * (sizeof(PrimRecord) + sizeof(ShadeRecord)) +
+  *h2d_bytes = (int64_t)(ctx->wide.nodes.size() * sizeof(WideNode) + (ctx->recs_on_device ? 0 : n * (sizeof(PrimRecord) + sizeof(ShadeRecord))) +
                          ctx->bsdfs.size() * sizeof(Bsdf) + ctx->lights.size() * sizeof(Light) +
                          (size_t)ctx->env_w * ctx->env_h * 5 * sizeof(float) + (size_t)ctx->env_h * sizeof(float));
   return DSRT_OK;
@@ -636,6 +658,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   if (!ctx->have_accel || !ctx->have_cam) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: call dsrt_build_accel and dsrt_set_camera first");
   if (spp_count < 0 || spp_stride < 1 || spp_begin < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: bad sample range");
   CK(cudaSetDevice(D.device));
+  struct Range { Range(const char* n) { nvtxRangePushA(n); } ~Range() { nvtxRangePop(); } } nvtx_range("dsrt render_impl (enqueue wavefront)");
   { int rc0 = size_trace_grid(ctx, D); if (rc0) return rc0; }
   const bool windowed = ctx->win[2] > 0;
   const int wx0 = windowed ? ctx->win[0] : 0, wy0 = windowed ? ctx->win[1] : 0;

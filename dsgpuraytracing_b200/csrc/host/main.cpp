@@ -6,6 +6,7 @@
 //      or a binary .pfm (PF, little endian) lat-long map
 // additions: -g <number of GPUs>  -o <output.png>  -S <seed>  -r <raw float dump of the linear buffer>
 //            -T tolerate non-manifold meshes (direct indexed-triangle import; the reference exit(1)s on them)
+//            -j print one JSON line per run (counters, seconds per stage, Mrays/s) on stdout after the human-readable lines
 // As in the reference, -h is the frame HEIGHT and the default frame is 1000x1000 (main.cpp:79-80).
 #include <unistd.h>
 
@@ -27,17 +28,17 @@ static void usage(const char* bin) {
   printf("  -g <INT>  number of GPUs (default 1)\n  -o <FILE> output PNG (default \"Screen Shot GPU <time>.png\")\n");
   printf("  -e <FILE> lat-long environment map (.exr or .pfm)\n");
   printf("  -T        import meshes the half-edge builder rejects (non-manifold ...) as plain indexed triangles\n");
-  printf("  -S <INT>  Philox seed (default 0)\n  -r <FILE> also dump the linear float RGB buffer\n");
+  printf("  -S <INT>  Philox seed (default 0)\n  -r <FILE> also dump the linear float RGB buffer\n  -j        one JSON line of run statistics\n");
 }
 
 int main(int argc, char** argv) {
   size_t ns_aa = 1, ns_area_light = 4, max_ray_depth = 1, num_threads = 1;   // application.h:45-58
   int screenW = 1000, screenH = 1000, n_gpus = 1;
   unsigned seed = 0;
-  bool useCPU = false;
+  bool useCPU = false, json = false;
   std::string camFileName, outName, rawName, envName;
   int opt;
-  while ((opt = getopt(argc, argv, "s:l:t:m:f:w:h:g:o:S:r:e:vcT")) != -1) {
+  while ((opt = getopt(argc, argv, "s:l:t:m:f:w:h:g:o:S:r:e:vcTj")) != -1) {
     switch (opt) {
       case 's': ns_aa = (size_t)atoi(optarg); break;
       case 'l': ns_area_light = (size_t)atoi(optarg); break;
@@ -53,6 +54,7 @@ int main(int argc, char** argv) {
       case 'e': envName = optarg; break;
       case 'c': useCPU = true; break;
       case 'T': set_direct_triangle_fallback(true); break;
+      case 'j': json = true; break;
       case 'v': fprintf(stderr, "the interactive viewer is not part of this port\n"); return 1;
       default: usage(argv[0]); return 1;
     }
@@ -78,6 +80,13 @@ int main(int argc, char** argv) {
   printf("[PathTracer] %llu camera samples, %llu extend + %llu shadow segments, %.4f s on the GPU, %.1f Mrays/s\n",
          (unsigned long long)st.camera_samples, (unsigned long long)st.extend_rays, (unsigned long long)st.shadow_rays, st.gpu_seconds,
          (double)(st.extend_rays + st.shadow_rays) / st.gpu_seconds / 1e6);
+  if (json)
+    printf("{\"scene\": \"%s\", \"width\": %d, \"height\": %d, \"spp\": %zu, \"light_samples\": %zu, \"max_depth\": %zu, \"gpus\": %d, \"seed\": %u, "
+           "\"camera_samples\": %llu, \"extend_rays\": %llu, \"shadow_rays\": %llu, \"gpu_seconds\": %.6f, \"render_call_seconds\": %.6f, "
+           "\"bvh_build_seconds\": %.6f, \"kernel_launches\": %u, \"batches\": %u, \"mrays_per_s\": %.2f}\n",
+           sceneFilePath.c_str(), screenW, screenH, ns_aa, ns_area_light, max_ray_depth, n_gpus, seed, (unsigned long long)st.camera_samples,
+           (unsigned long long)st.extend_rays, (unsigned long long)st.shadow_rays, st.gpu_seconds, pathtracer.render_seconds, pathtracer.bvh_build_seconds,
+           st.kernel_launches, st.batches, (double)(st.extend_rays + st.shadow_rays) / st.gpu_seconds / 1e6);
   if (!rawName.empty()) {
     FILE* f = fopen(rawName.c_str(), "wb");
     if (f) { fwrite(pathtracer.sampleBuffer.data.data(), sizeof(float), pathtracer.sampleBuffer.data.size(), f); fclose(f); }

@@ -253,10 +253,13 @@ def test_cli_binary(tmp_path):
     import subprocess
     exe = os.path.join(os.path.dirname(D.lib_path()), "pathtracer")
     raw = tmp_path / "f.raw"; png = tmp_path / "f.png"
-    r = subprocess.run([exe, "-s", "4", "-l", "4", "-m", "5", "-w", "96", "-h", "72", "-S", "5", "-o", str(png), "-r", str(raw),
+    r = subprocess.run([exe, "-s", "4", "-l", "4", "-m", "5", "-w", "96", "-h", "72", "-S", "5", "-j", "-o", str(png), "-r", str(raw),
                         O.ref_scene_path("CBspheres_lambertian.dae")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GPU ray tracing done" in r.stdout
+    import json
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])          # -j: one JSON line of run statistics
+    assert line["camera_samples"] == 96 * 72 * 4 and line["extend_rays"] >= line["camera_samples"] and line["mrays_per_s"] > 0
     rgb = np.fromfile(raw, np.float32).reshape(72, 96, 3)
     ref = np.load(os.path.join(GOLDEN, "CBspheres_lambertian.npz"))
     sc = O.Scene({k: ref[k] for k in ref.files}).with_camera(ref["small_camera"])

@@ -77,6 +77,7 @@ def test_image_gate_1024spp(name, core, golden):
     assert ok, info
     plain = np.sqrt(((rgb - ref) ** 2).mean(axis=(0, 1))) / np.maximum(ref.mean(axis=(0, 1)), 1e-12)
     print(f"{name}: plain rel RMSE {plain.max():.2e}, flipped pixels {info['n_bad']}, RMSE of the rest {info['rel_rmse_of_matching_pixels']:.2e}")
+    assert plain.max() < 0.01, plain          # north_star gate 2, literally: no pixel excluded (measured 4e-6 ... 1.5e-3, profiles/r2_parity.md)
     assert abs(int(st.extend_rays) - int(ph["philox_cnt"][0])) <= 2e-4 * ph["philox_cnt"][0]
     assert abs(int(st.shadow_rays) - int(ph["philox_cnt"][1])) <= 2e-4 * ph["philox_cnt"][1]
     # statistical agreement with the compiled reference (different random source)

@@ -180,6 +180,7 @@ def test_standin_image_gate_1024spp(name, core):
          block20_rmse_vs_reference=got, block20_rmse_reference_vs_reference=floor, mean_dev=mean_dev, mean_dev_reference_vs_reference=mean_floor,
          extend=[int(st.extend_rays), int(fx["philox_cnt"][0])], shadow=[int(st.shadow_rays), int(fx["philox_cnt"][1])])
     assert ok, info
+    assert plain.max() < 0.01, plain          # north_star gate 2, literally: plain per-channel RMSE, no pixel excluded
     assert abs(int(st.extend_rays) - int(fx["philox_cnt"][0])) <= 2e-4 * fx["philox_cnt"][0]
     assert abs(int(st.shadow_rays) - int(fx["philox_cnt"][1])) <= 2e-4 * fx["philox_cnt"][1]
     assert mean_dev < 0.01 + 3 * mean_floor

@@ -5,13 +5,24 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
+#include <memory>
 #include <thread>
 #include <vector>
 
 #include "../../include/dsrt.h"
 
 namespace dsrt {
+
+// vector of trivially copyable elements whose resize() leaves new elements uninitialised (no single-threaded zero fill of
+// gigabyte arrays that are about to be overwritten), filled by a parallel copy
+template <class T> struct DefaultInitAllocator : std::allocator<T> {
+  template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+  template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+  template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using PodVec = std::vector<T, DefaultInitAllocator<T>>;
 
 struct Box3 {
   double lo[3], hi[3];
@@ -68,5 +79,10 @@ template <class F> void parallel_for(size_t n, size_t grain, F f) {
 
 // Triangle::get_bbox (triangle.cpp:11-23) / Sphere::get_bbox (sphere.h:30-32)
 void primitive_boxes(const dsrt_scene* sc, std::vector<Box3>& out);
+
+template <class T> void assign_parallel(PodVec<T>& v, const T* src, size_t n) {
+  v.resize(n);
+  parallel_for(n, (size_t)1 << 22, [&](size_t a, size_t b) { std::memcpy(v.data() + a, src + a, (b - a) * sizeof(T)); });
+}
 
 }  // namespace dsrt

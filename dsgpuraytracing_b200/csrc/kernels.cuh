@@ -224,8 +224,11 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
         hit_out[item] = make_float4(hit.t, hit.u, hit.v, __int_as_float(hit.slot));
       }
     }
-    // ---- refill idle lanes
+    // ---- refill idle lanes.  With "skip_null_shadow" a lane may draw a ray that needs no tracing (tmax = -1): the warp then
+    // fetches again for those lanes (at most three more times), so that dropping rays does not leave lanes idle until the next refill
+    for (int round = 0; round < (ANY ? 4 : 1); round++) {
     const unsigned idle = __ballot_sync(kFull, !busy);
+    bool drew_null = false;
     if (idle && !exhausted) {
       uint32_t base = 0;
       const int leader = __ffs(idle) - 1;
@@ -245,6 +248,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           }
           if (ANY && o.w < 0.f) {          // "skip_null_shadow": a shadow ray whose contribution is zero was queued with tmax = -1
             if (hit_out) hit_out[item] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            drew_null = true;
           } else {
           ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.tmax = o.w;
           ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.src_slot = __float_as_int(d.w);
@@ -274,6 +278,8 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
         }
       }
       if (base + (uint32_t)__popc(idle) >= n) exhausted = true;
+    }
+    if (!ANY || !__any_sync(kFull, drew_null)) break;
     }
     if (!__any_sync(kFull, busy)) break;
 

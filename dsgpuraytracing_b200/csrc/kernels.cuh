@@ -33,6 +33,9 @@ constexpr int kTraceThreads = 128;        // 4 warps per CTA
 #ifndef DSRT_TRACE_MIN_CTAS
 #define DSRT_TRACE_MIN_CTAS 7             // resident CTAs per SM the traversal kernels are compiled for (register cap 72; measured best of 6, 7, 8)
 #endif
+#ifndef DSRT_NODE_STEPS_CLOSEST
+#define DSRT_NODE_STEPS_CLOSEST 2         // the same for the closest-hit kernel
+#endif
 #ifndef DSRT_PREFETCH_AHEAD
 #define DSRT_PREFETCH_AHEAD 16384         // queue positions between a refill's loads and the L2 prefetches it issues (0 = off)
 #endif
@@ -202,6 +205,8 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
   uint32_t item = 0;
   TraceRay ray; NodeFrame fr;
   float tbest = 0.f; TraceHit hit;
+  constexpr bool kSat = ANY ? (DSRT_SAT_SLAB != 0) : (DSRT_SAT_CLOSEST != 0);      // saturating node test (traverse.cuh)
+  float t_unit = 1.f;                              // closest hit: the distance the frame is currently scaled to
   uint32_t spa = s_stack;                          // address of the first free stack entry (== s_stack: empty)
   uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
   hit.slot = -1; hit.t = 0.f; hit.u = 0.f; hit.v = 0.f;
@@ -252,7 +257,9 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           } else {
           ray.ox = o.x; ray.oy = o.y; ray.oz = o.z; ray.tmax = o.w;
           ray.dx = d.x; ray.dy = d.y; ray.dz = d.z; ray.src_slot = __float_as_int(d.w);
-          fr = make_frame(ray, (ANY && DSRT_SAT_SLAB) ? any_hit_scale(A, ray) : 1.0f);
+          const float scale0 = kSat ? any_hit_scale(A, ray) : 1.0f;
+          fr = make_frame(ray, scale0);
+          if (!ANY && kSat) t_unit = hd_rcp(scale0);
           const WatertightRay wr = make_watertight(ray);
           tbest = ray.tmax; hit.slot = -1; hit.t = ray.tmax; hit.u = 0.f; hit.v = 0.f;
           spa = s_stack; ngroup = make_uint2(0u, 0x80000000u); tgroup = make_uint2(0u, 0u);
@@ -290,7 +297,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
       // most one group per tree level).  A lane that still holds an untested primitive group waits for the warp's next test
       // (parking such groups on the stack was measured: 2-3 % slower than this simpler loop).
 #pragma unroll
-      for (int step = 0; step < DSRT_NODE_STEPS; step++)
+      for (int step = 0; step < (ANY ? DSRT_NODE_STEPS : DSRT_NODE_STEPS_CLOSEST); step++)
       if (busy && tgroup.y == 0u) {
         if (ngroup.y <= 0x00ffffffu && spa != s_stack) { spa -= kStackPitch; ngroup = lds64(spa); }
         if (ngroup.y > 0x00ffffffu) {
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           const uint4* np = A.nodes + (size_t)(ngroup.x + rel) * 5;
           const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
           if (COUNT) cnt.nodes++;
-          const uint32_t m = test_children<false, ANY && DSRT_SAT_SLAB>(ray, fr, n0, n1, n2, n3, n4, tbest, 0.f, A.one_bits);
+          const uint32_t m = test_children<false, kSat>(ray, fr, n0, n1, n2, n3, n4, tbest, 0.f, A.one_bits);
           ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
           tgroup = make_uint2(n1.y, drop_source(m & 0x00ffffffu, n1.y, ray.src_slot));
           did_node = true;
@@ -412,6 +419,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
             if (h) {
               tbest = t; hit.slot = slot; hit.t = t; hit.u = u; hit.v = v;
               if (ANY) { done = true; break; }
+              if (kSat) { rescale_frame(fr, t_unit, t); t_unit = t; }
             }
           }
         }

@@ -328,20 +328,32 @@ struct Accel {
 #ifndef DSRT_SAT_SLAB
 #define DSRT_SAT_SLAB 1                    // saturating node test for any-hit rays (see test_children)
 #endif
-// 1 / (effective tmax) of an any-hit ray: tmax itself, or the far side of the scene's bounding sphere when tmax is infinite
-// (directional / hemisphere / environment lights).  A ray with tmax <= 0 gets a huge scale: every box then clamps to a miss.
+#ifndef DSRT_SAT_CLOSEST
+#define DSRT_SAT_CLOSEST 1                 // ... and for closest-hit rays: the frame is rescaled by t_old / t_new whenever a closer hit is found
+#endif
+// 1 / (effective tmax) of a ray: tmax itself when it is finite (area / point light shadow rays), else the far side of the
+// scene's bounding sphere (camera and bounce rays, directional / hemisphere / environment lights).  A ray with tmax <= 0 gets a
+// huge scale: every box then clamps to a miss.
 DSRT_HD float any_hit_scale(const Accel& A, const TraceRay& r) {
+  if (r.tmax < 1.0e30f) return hd_rcp(fmaxf(r.tmax, 1.0e-30f));
   const float cx = A.bcx - r.ox, cy = A.bcy - r.oy, cz = A.bcz - r.oz;
   // in units of |d| (directions handed to dsrt_trace_any need not be normalised)
   const float reach = (sqrtf(cx * cx + cy * cy + cz * cz) + A.brad) * hd_rsqrt(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz) * 1.0001f;
-  return hd_rcp(fmaxf(fminf(r.tmax, reach), 1.0e-30f));
+  return hd_rcp(fmaxf(reach, 1.0e-30f));
+}
+// closest hit: the node test works in units of the current best distance; a closer hit at t rescales the frame
+DSRT_HD void rescale_frame(NodeFrame& fr, float t_scaled_to, float t_new) {
+  const float k = t_scaled_to * hd_rcp(t_new);
+  fr.idx *= k; fr.idy *= k; fr.idz *= k;
 }
 
 template <bool ANY, bool PARITY, bool COUNT>
 DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, uint2* stack, int stride,
                                           TraceHit& hit, double* t64_out, TraceCounters* cnt) {
-  constexpr bool SAT = ANY && !PARITY && DSRT_SAT_SLAB;
-  const NodeFrame fr = make_frame(ray, SAT ? any_hit_scale(A, ray) : 1.0f);
+  constexpr bool SAT = !PARITY && (ANY ? DSRT_SAT_SLAB : DSRT_SAT_CLOSEST);
+  const float scale0 = SAT ? any_hit_scale(A, ray) : 1.0f;
+  NodeFrame fr = make_frame(ray, scale0);
+  float t_unit = SAT ? hd_rcp(scale0) : 1.0f;          // the distance that maps to 1 in the saturating node test
   const WatertightRay wr = make_watertight(ray);
   constexpr bool FAST = ANY && !PARITY && DSRT_TRI_FAST;
   const float pox = FAST ? -(ray.ox * wr.bxx + ray.oy * wr.bxy + ray.oz * wr.bxz) : 0.f;
@@ -395,6 +407,7 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
         if (h) {
           if (ANY) { hit.slot = slot; hit.t = t; return; }
           tbest = t; hit.slot = slot; hit.t = t; hit.u = u; hit.v = v;
+          if (SAT) { rescale_frame(fr, t_unit, t); t_unit = t; }
         }
       }
     }

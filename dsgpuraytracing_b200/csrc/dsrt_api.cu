@@ -71,7 +71,7 @@ struct dsrt_ctx {
   Camera cam{};
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
-  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 8, opt_refill = 18, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_max_ctas = 0, opt_carveout = -1, opt_prim_cost = 100, opt_mem_budget_mb = 0, opt_device_build = 0;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 8, opt_refill = 18, opt_refill_hi = 26, opt_refill_patience = 6, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_max_ctas = 0, opt_carveout = -1, opt_prim_cost = 100, opt_mem_budget_mb = 0, opt_device_build = 0;
   WideBVH wide;
   std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
   int env_w = 0, env_h = 0;
@@ -388,6 +388,8 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
   else if (n == "skip_null_shadow") ctx->opt_skip_null = value;
   else if (n == "postpone_min_lanes") ctx->opt_tri_min = value;
   else if (n == "refill_busy_lanes") ctx->opt_refill = value;
+  else if (n == "refill_hi_lanes") ctx->opt_refill_hi = value;
+  else if (n == "refill_patience") ctx->opt_refill_patience = std::max<int64_t>(1, value);
   else if (n == "postpone_wait_mode") ctx->opt_wait_mode = value;
   else if (n == "pool_batches") ctx->opt_pool_batches = std::max<int64_t>(1, value);
   else if (n == "coop_min_pairs") ctx->opt_coop_min = value;
@@ -695,7 +697,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   const Accel A = make_accel(ctx, D, false);
   const bool count = ctx->opt_count != 0, timing = ctx->opt_stage_timing != 0;
   const int tgrid = D.trace_blocks;
-  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, coop_min = (int)ctx->opt_coop_min;
+  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, coop_min = (int)ctx->opt_coop_min, refill_hi = (int)ctx->opt_refill_hi, refill_patience = (int)ctx->opt_refill_patience;
   const size_t sbytes = stack_bytes(ctx), sbytes_closest = stack_bytes(ctx, false);
 
   auto span_begin = [&](int kind) { if (timing) { DevState::Span s; s.kind = kind; s.e0 = D.ev_used; cudaEventRecord(next_event(D), st); s.e1 = 0; D.spans.push_back(s); } };
@@ -717,11 +719,11 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   auto trace = [&](bool any, const float4* ro, const float4* rd, const uint32_t* q, const uint32_t* n_ptr, uint32_t* work, float4* hits, const float4* contrib) {
     span_begin(any ? 1 : 0);
     if (any) {
-      if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, nullptr, contrib, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
-      else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, nullptr, contrib, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
+      if (count) k_trace<true, true><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, nullptr, contrib, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min, refill_hi, refill_patience);
+      else k_trace<true, false><<<tgrid, kTraceThreads, sbytes, st>>>(A, ro, rd, q, n_ptr, work, nullptr, contrib, d_accum, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min, refill_hi, refill_patience);
     } else {
-      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes_closest, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
-      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes_closest, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
+      if (count) k_trace<false, true><<<tgrid, kTraceThreads, sbytes_closest, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min, refill_hi, refill_patience);
+      else k_trace<false, false><<<tgrid, kTraceThreads, sbytes_closest, st>>>(A, ro, rd, q, n_ptr, work, hits, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min, refill_hi, refill_patience);
     }
     span_end();
     D.launches++;
@@ -971,11 +973,11 @@ int dsrt_primary_hits(dsrt_ctx* ctx, int32_t mode, int32_t* prim_id, double* t) 
     if (D.n_counter_blocks < 1) { if ((rc = dev_alloc(ctx, &D.d_counters, (size_t)1))) return rc; D.n_counter_blocks = 1; }
     CK(cudaMemsetAsync(D.d_counters, 0, sizeof(Counters), st));
     RenderParams rp; std::memset(&rp, 0, sizeof(rp)); rp.cam = ctx->cam; rp.win_x1 = ctx->cam.width; rp.win_y1 = ctx->cam.height;
-    const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, coop_min = (int)ctx->opt_coop_min;
+    const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, coop_min = (int)ctx->opt_coop_min, refill_hi = (int)ctx->opt_refill_hi, refill_patience = (int)ctx->opt_refill_patience;
     k_generate_centres<<<(n + 255) / 256, 256, 0, st>>>(D.ps, rp, n);
     k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
     k_trace<false, false><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx, false), st>>>(make_accel(ctx, D, false), D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0],
-                                                                            &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
+                                                                            &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min, refill_hi, refill_patience);
     CK(cudaGetLastError());
     std::vector<float4> hits(n);
     CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));
@@ -1009,9 +1011,9 @@ static int trace_batch(dsrt_ctx* ctx, bool any, int64_t n, const float* o, const
   CK(cudaMemcpyAsync(D.ps.ray_d, hd.data(), n * sizeof(float4), cudaMemcpyHostToDevice, st));
   k_set_u32<<<1, 1, 0, st>>>(&D.d_counters->q_count[0], (uint32_t)n);
   const Accel A = make_accel(ctx, D, false);
-  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, coop_min = (int)ctx->opt_coop_min;
-  if (any) k_trace<true, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
-  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx, false), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min);
+  const int tri_min = (int)ctx->opt_tri_min, refill_busy = (int)ctx->opt_refill, wait_mode = (int)ctx->opt_wait_mode, coop_min = (int)ctx->opt_coop_min, refill_hi = (int)ctx->opt_refill_hi, refill_patience = (int)ctx->opt_refill_patience;
+  if (any) k_trace<true, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min, refill_hi, refill_patience);
+  else k_trace<false, true><<<D.trace_blocks, kTraceThreads, stack_bytes(ctx, false), st>>>(A, D.ps.ray_o, D.ps.ray_d, nullptr, &D.d_counters->q_count[0], &D.d_counters->work_extend[0], D.ps.hit, nullptr, nullptr, D.d_totals, tri_min, refill_busy, wait_mode, stack_entries(ctx), coop_min, refill_hi, refill_patience);
   CK(cudaGetLastError());
   std::vector<float4> hits(n);
   CK(cudaMemcpyAsync(hits.data(), D.ps.hit, n * sizeof(float4), cudaMemcpyDeviceToHost, st));

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
                                                          const uint32_t* __restrict__ queue, const uint32_t* __restrict__ n_ptr,
                                                          uint32_t* work, float4* hit_out, const float4* __restrict__ contrib,
                                                          float* accum, Totals* totals, int tri_min, int refill_busy, int wait_mode,
-                                                         int stack_entries, int coop_min) {
+                                                         int stack_entries, int coop_min, int refill_hi, int refill_patience) {
   extern __shared__ uint2 smem_stack[];
   const int lane = threadIdx.x & 31;
   // shared memory: [stacks: entry-major, 8 B per lane -> conflict free][any-hit kernel only: per-lane ray blocks (kRayBlock
@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
     if (!__any_sync(kFull, busy)) break;
 
     // ---- traverse until the warp is due for a refill
+    int iters = 0;
     while (true) {
       bool done = false, did_node = false;
       // (1) node step: open the highest-priority pending internal child, or take the next node group off the stack (at
@@ -430,7 +431,11 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
         if (done) { busy = false; fin = true; tgroup.y = 0u; ngroup.y = 0u; spa = s_stack; }
       }
       const int nbusy = __popc(__ballot_sync(kFull, busy));
-      if (nbusy == 0 || (!exhausted && nbusy <= refill_busy)) break;
+      // refill when few lanes are busy -- or, if the rays of this warp turn out to be long (many iterations since the last
+      // refill: tens of node visits per ray in the soups), already when a quarter of the lanes idle: the refill's fixed cost is
+      // then small against the iterations the idle lanes would sit out
+      iters++;
+      if (nbusy == 0 || (!exhausted && (nbusy <= refill_busy || (nbusy <= refill_hi && iters >= refill_patience)))) break;
     }
   }
   if (COUNT) {

@@ -121,6 +121,9 @@ int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t
  * dealt out one per lane; default 6, a huge value disables the cooperative test), "postpone_wait_mode" (0: primitives are
  * tested as soon as one lane has nothing else to do; 1: only when no lane opened a node; K >= 2: when K lanes wait),
  * "refill_busy_lanes" (a warp fetches new rays for its idle lanes when at most this many are busy; default 18),
+ * "refill_hi_lanes" / "refill_patience" (... or already when at most refill_hi_lanes (26) are busy, once the warp has run
+ * refill_patience (6) traversal iterations since its last refill: long rays -- tens of node visits in the triangle soups --
+ * make an early refill worth its fixed cost, short rays never get there),
  * "max_ctas_per_sm" (caps the persistent grid; 0 = what fits), "smem_carveout_pct" (shared-memory carve-out of the
  * traversal kernels, -1 = driver default, which measured best), "collapse_prim_cost_pct" (SAH cost of a primitive test
  * relative to a wide-node visit in the collapse, percent; default 100; applies at the next dsrt_build_accel),

@@ -27,7 +27,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         V, F = S.torus_knot(); V = V.astype(np.float32).astype(np.float64)
         sc = S.cb_mesh_scene(V, F); cam = S.cam_dragon(1920, 1080); nl = 4
     core = D.Core(0); core.set_params(spp, nl, 8, 0); core.load(sc, camera=cam, device_build=bool(int(os.environ.get("SWEEP_DEVICE_BUILD", "0")))); core.set_option("stage_timing", 1)
-    defaults = {"max_ctas_per_sm": 0, "postpone_min_lanes": 8, "refill_busy_lanes": 18, "coop_min_pairs": 6, "postpone_wait_mode": 0, "pool_batches": 8, "batch_spp": 0, "smem_carveout_pct": -1}
+    defaults = {"max_ctas_per_sm": 0, "postpone_min_lanes": 8, "refill_busy_lanes": 18, "coop_min_pairs": 6, "postpone_wait_mode": 0, "pool_batches": 8, "batch_spp": 0, "smem_carveout_pct": -1, "refill_hi_lanes": 26, "refill_patience": 6}
     for o in OPTS:
         try:
             for k, v in {**defaults, **o}.items():

@@ -15,7 +15,7 @@ python bench.py --spp 16 --steps 1 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_$T.csv python bench.py --spp 16 --steps 1 --warmup 1 --no-cpu-baseline > $O/ncu_list_$T.log 2>&1
 python profiles/profile_run.py 4 > $O/pr_on_$T.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:k_trace -s 18 -c 2 -f -o $O/prof_on_$T python profiles/profile_run.py 4 > $O/pr_ncu_on_$T.log 2>&1
-OFF="refill_busy_lanes=0 postpone_min_lanes=0 coop_min_pairs=1000000"
+OFF="refill_busy_lanes=0 refill_hi_lanes=0 postpone_min_lanes=0 coop_min_pairs=1000000"
 python profiles/profile_run.py 4 $OFF > $O/pr_off_$T.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:k_trace -s 18 -c 2 -f -o $O/prof_off_$T python profiles/profile_run.py 4 $OFF > $O/pr_ncu_off_$T.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_shade|k_generate" -s 10 -c 2 -f -o $O/prof_shade_$T python profiles/profile_run.py 4 > $O/pr_ncu_shade_$T.log 2>&1

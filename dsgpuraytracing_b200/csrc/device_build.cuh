@@ -267,13 +267,12 @@ __global__ void k_db_collapse(DbTree T, const int2* __restrict__ items, int n_it
     }
     w.qlox[s] = q[0]; w.qloy[s] = q[1]; w.qloz[s] = q[2]; w.qhix[s] = q[3]; w.qhiy[s] = q[4]; w.qhiz[s] = q[5];
     if ((inner >> kid_at[s]) & 1) {
-      w.meta[s] = (uint8_t)((1 << 5) | (24 + s));
+      w.inner |= 8u << (4 * s);
       w.imask |= (uint8_t)(1 << s);
       next_items[next_base + rank] = make_int2(c.ref, (int)(child_base + rank));
       rank++;
     } else {
-      const uint8_t unary = c.count == 1 ? 1 : (c.count == 2 ? 3 : 7);
-      w.meta[s] = (uint8_t)((unary << 5) | prim_off);
+      w.valid |= ((1u << c.count) - 1u) << (4 * s);
       for (int j = 0; j < c.count; j++) slot_prim[prim_base + prim_off + j] = (int32_t)T.sorted[c.first + j];
       prim_off += c.count;
     }

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -19,7 +20,6 @@
 #include "device_build.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <nvtx3/nvToolsExt.h>          // header-only: ranges show up in nsys / ncu timelines, no-ops otherwise
-#include <chrono>
 
 // ================================================================================================ host side
 using namespace dsrt;
@@ -84,6 +84,13 @@ struct dsrt_ctx {
 };
 
 namespace {
+
+// DSRT_HOST_TRACE=1: host-side wall time between named points of a dsrt_render call, printed to stderr at its end (where an
+// end-to-end step spends time outside the GPU window that dsrt_stats.gpu_seconds reports)
+struct HostTrace { bool on = false; std::vector<std::pair<const char*, double>> pts; };
+thread_local HostTrace g_host_trace;
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define TP(name) do { if (g_host_trace.on) g_host_trace.pts.emplace_back(name, now_s()); } while (0)
 
 int fail(dsrt_ctx* c, int code, const std::string& msg) {
   if (c) { std::lock_guard<std::mutex> g(c->err_mutex); c->err = msg; }
@@ -634,8 +641,19 @@ static int plan_batches(dsrt_ctx* ctx, DevState& D, int npp, int spp_count, int*
   if (batch_spp <= 0) batch_spp = std::max(1, (int)((16u << 20) / (unsigned)npp));   // ~16M paths per batch (measured: 4 / 8 / 16 M paths -> 6.38 / 6.59 / 6.71 Grays/s)
   batch_spp = std::min(batch_spp, std::max(1, spp_count));
   int pool_group = (int)ctx->opt_pool_batches;
+  // A frame like the previous one finds its buffers in place: nothing to size, and no cudaMemGetInfo (the query takes
+  // 10-70 ms every few calls once tens of GB are allocated -- measured as the only host-side stall of an end-to-end step)
+  if (ctx->opt_mem_budget_mb == 0) {
+    const size_t P = (size_t)npp * (size_t)batch_spp, ls = (size_t)std::max(nls, 1);
+    const size_t grp = (size_t)std::max(1, std::min((std::max(spp_count, 1) + batch_spp - 1) / batch_spp, pool_group));
+    if (P <= D.cap_paths && P * ls <= D.cap_shadow && (ctx->max_depth <= 0 || (P * grp <= D.cap_pool && P * grp * ls <= D.cap_pool_shadow))) {
+      *batch_spp_out = batch_spp; *pool_group_out = pool_group;
+      return DSRT_OK;
+    }
+  }
   size_t free_b = 0, total_b = 0;
   CK(cudaMemGetInfo(&free_b, &total_b));
+  TP("cudaMemGetInfo");
   const double held = (double)D.cap_paths * 80.0 + (double)D.cap_shadow * 48.0 + (double)D.cap_pool * 80.0 + (double)D.cap_pool_shadow * 48.0;
   double budget = 0.8 * ((double)free_b + held);
   if (ctx->opt_mem_budget_mb > 0) budget = std::min(budget, (double)ctx->opt_mem_budget_mb * 1048576.0);
@@ -662,6 +680,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   CK(cudaSetDevice(D.device));
   struct Range { Range(const char* n) { nvtxRangePushA(n); } ~Range() { nvtxRangePop(); } } nvtx_range("dsrt render_impl (enqueue wavefront)");
   { int rc0 = size_trace_grid(ctx, D); if (rc0) return rc0; }
+  TP("trace grid");
   const bool windowed = ctx->win[2] > 0;
   const int wx0 = windowed ? ctx->win[0] : 0, wy0 = windowed ? ctx->win[1] : 0;
   const int W = windowed ? ctx->win[2] : ctx->cam.width, H = windowed ? ctx->win[3] : ctx->cam.height;     // extent rendered by this call
@@ -675,6 +694,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   const size_t P = (size_t)npp * batch_spp;
   int rc = ensure_wavefront(ctx, D, P, P * (size_t)std::max(nls, 1));
   if (rc) return rc;
+  TP("plan + wavefront buffers");
   const int n_batches = (spp_count + batch_spp - 1) / batch_spp;
   if (n_batches > D.n_counter_blocks) {
     if ((rc = dev_alloc(ctx, &D.d_counters, (size_t)std::max(n_batches, 1)))) return rc;
@@ -715,6 +735,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
     }
     CK(cudaMemsetAsync(D.d_pool_counters, 0, sizeof(PoolCounters) * (size_t)n_groups, st));
   }
+  TP("pool buffers + memsets");
   if (first) CK(cudaEventRecord(D.ev_begin, st));     // after every (re)allocation: gpu_seconds covers the kernels of the frame only
   auto trace = [&](bool any, const float4* ro, const float4* rd, const uint32_t* q, const uint32_t* n_ptr, uint32_t* work, float4* hits, const float4* contrib) {
     span_begin(any ? 1 : 0);
@@ -770,6 +791,7 @@ static int render_impl(dsrt_ctx* ctx, DevState& D, int spp_begin, int spp_count,
   }
   CK(cudaEventRecord(D.ev_end, st));
   CK(cudaGetLastError());
+  TP("launches enqueued");
   return DSRT_OK;
 }
 
@@ -837,6 +859,9 @@ static int render_host(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int3
   if (!ctx->have_accel) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: call dsrt_build_accel first");
   if (spp_count < 0 || spp_stride < 1 || spp_begin < 0) return fail(ctx, DSRT_ERR_INVALID, "dsrt_render: bad sample range");
   ctx->cancel.store(0);
+  static const bool host_trace = std::getenv("DSRT_HOST_TRACE") != nullptr;
+  g_host_trace.on = host_trace; g_host_trace.pts.clear();
+  TP("enter");
   const size_t npix = (size_t)ctx->cam.width * ctx->cam.height;
   const int G = (int)ctx->devs.size();
   const int npp = (((ctx->win[2] > 0 ? ctx->win[2] : ctx->cam.width) + 7) / 8) * (((ctx->win[2] > 0 ? ctx->win[3] : ctx->cam.height) + 3) / 4) * 32;
@@ -852,12 +877,17 @@ static int render_host(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int3
     const int cnt = spp_count > r ? (spp_count - r + G - 1) / G : 0;
     int bspp = 1, grp = 1;
     { int rc = plan_batches(ctx, D, npp, cnt, &bspp, &grp); if (rc) return rc; }
+    TP("accum memset + plan");
     const int per_chunk = std::max(1, bspp * grp * 2);
     Scratch fences; cudaEvent_t fence[2];
     CK(fences.event(&fence[0])); CK(fences.event(&fence[1]));
     int i = 0;
+    // experiment (DSRT_STAGGER=1, several streams on one GPU): odd streams start with half a batch, so that their
+    // bandwidth-bound stages (generate / shade) fall into the other stream's issue-bound traversal stages
+    static const bool stagger = std::getenv("DSRT_STAGGER") != nullptr;
     do {                                   // at least one call, so that an empty sample list still resets the counters
-      const int c = std::min(per_chunk, cnt - done[r]);
+      int c = std::min(per_chunk, cnt - done[r]);
+      if (stagger && i == 0 && (r & 1) && bspp >= 2) c = std::min(c, bspp / 2);
       int rc = render_impl(ctx, D, spp_begin + (r + done[r] * G) * spp_stride, c, spp_stride * G, D.d_accum_own, D.stream, i == 0);
       if (rc) return rc;
       done[r] += c;
@@ -898,10 +928,25 @@ static int render_host(dsrt_ctx* ctx, int32_t spp_begin, int32_t spp_count, int3
   if (rgba8_out && npix > D0.rgba8_pixels) { int rc = dev_alloc(ctx, &D0.d_rgba8, npix); if (rc) return rc; D0.rgba8_pixels = npix; }
   k_resolve_peers<<<(unsigned)((npix + 255) / 256), 256, 0, D0.stream>>>(pp, D0.d_accum_own, rgba8_out ? D0.d_rgba8 : nullptr, (int)npix, inv_spp);
   CK(cudaGetLastError());
+  TP("resolve enqueued");
+  if (host_trace) { CK(cudaEventSynchronize(D0.ev_end)); TP("kernels finished"); }
   if (rgb_out) CK(cudaMemcpyAsync(rgb_out, D0.d_accum_own, npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, D0.stream));
   if (rgba8_out) CK(cudaMemcpyAsync(rgba8_out, D0.d_rgba8, npix * sizeof(uint32_t), cudaMemcpyDeviceToHost, D0.stream));
   CK(cudaStreamSynchronize(D0.stream));
+  TP("resolve + D2H + sync");
   if (stats) { int rc = dsrt_collect_stats(ctx, stats); if (rc) return rc; }
+  if (host_trace) {
+    TP("stats");
+    std::string line = "[dsrt host trace]";
+    char buf[96];
+    for (size_t i = 1; i < g_host_trace.pts.size(); i++) {
+      std::snprintf(buf, sizeof(buf), "  %s %.4f", g_host_trace.pts[i].first, g_host_trace.pts[i].second - g_host_trace.pts[i - 1].second);
+      line += buf;
+    }
+    std::snprintf(buf, sizeof(buf), "  | total %.4f s", g_host_trace.pts.back().second - g_host_trace.pts.front().second);
+    std::fprintf(stderr, "%s%s\n", line.c_str(), buf);
+    g_host_trace.on = false;
+  }
   if (cancelled) { fail(ctx, DSRT_CANCELLED, "dsrt_render: cancelled after " + std::to_string(total_done) + " of " + std::to_string(spp_count) + " samples per pixel"); return DSRT_CANCELLED; }
   return DSRT_OK;
 }

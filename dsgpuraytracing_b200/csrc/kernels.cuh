@@ -39,9 +39,6 @@ constexpr int kTraceThreads = 128;        // 4 warps per CTA
 #ifndef DSRT_PREFETCH_AHEAD
 #define DSRT_PREFETCH_AHEAD 16384         // queue positions between a refill's loads and the L2 prefetches it issues (0 = off)
 #endif
-#ifndef DSRT_ONEHOT_PAIRS
-#define DSRT_ONEHOT_PAIRS 0               // 1: pair table entries = (slot base | owner, one-hot primitive bit), bit scan in the test: +0.2 % on the bench scene, but 3 KB more shared memory per CTA (-19 % on the 8 Mi soup)
-#endif
 #ifndef DSRT_NODE_STEPS
 #define DSRT_NODE_STEPS 2                 // node steps a lane may take between two warp-wide primitive-test decisions (1 / 2 / 3: 6839 / 6893 / 6741 Mrays/s)
 #endif
@@ -61,7 +58,7 @@ constexpr int kRayBlockClosest = 9;
 #ifndef DSRT_STACK_SLACK
 #define DSRT_STACK_SLACK 1
 #endif
-constexpr uint32_t kPairBytes = DSRT_ONEHOT_PAIRS ? 8u : 4u;
+constexpr uint32_t kPairBytes = 4u;
 constexpr int kPairCap = DSRT_PAIR_CAP;             // (ray, primitive) pairs one warp can deal out per round set
 constexpr int kMaxDepthSlots = 64;        // queue-size slots per batch (depth 0..63)
 constexpr unsigned kFull = 0xffffffffu;
@@ -206,6 +203,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
   TraceRay ray; NodeFrame fr;
   float tbest = 0.f; TraceHit hit;
   constexpr bool kSat = ANY ? (DSRT_SAT_SLAB != 0) : (DSRT_SAT_CLOSEST != 0);      // saturating node test (traverse.cuh)
+  constexpr bool kOrdered = !ANY || (DSRT_ANY_ORDERED != 0);                       // children opened front to back
   float t_unit = 1.f;                              // closest hit: the distance the frame is currently scaled to
   uint32_t spa = s_stack;                          // address of the first free stack entry (== s_stack: empty)
   uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
@@ -300,19 +298,16 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
 #pragma unroll
       for (int step = 0; step < (ANY ? DSRT_NODE_STEPS : DSRT_NODE_STEPS_CLOSEST); step++)
       if (busy && tgroup.y == 0u) {
-        if (ngroup.y <= 0x00ffffffu && spa != s_stack) { spa -= kStackPitch; ngroup = lds64(spa); }
-        if (ngroup.y > 0x00ffffffu) {
-          const uint32_t bit = 31u - (uint32_t)__clz(ngroup.y);
-          ngroup.y &= ~(1u << bit);
-          if (ngroup.y > 0x00ffffffu) { sts64(spa, ngroup); spa += kStackPitch; }
-          const uint32_t slot = (bit - 24u) ^ fr.octinv;
-          const uint32_t rel = __popc(ngroup.y & 0xffu & ((1u << slot) - 1u));
-          const uint4* np = A.nodes + (size_t)(ngroup.x + rel) * 5;
+        if (!(ngroup.y & kHitBits) && spa != s_stack) { spa -= kStackPitch; ngroup = lds64(spa); }
+        if (ngroup.y & kHitBits) {
+          bool more;
+          const uint32_t node = next_child<kOrdered>(ngroup, fr, more);
+          if (more) { sts64(spa, ngroup); spa += kStackPitch; }
+          const uint4* np = A.nodes + (size_t)node * 5;
           const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
           if (COUNT) cnt.nodes++;
-          const uint32_t m = test_children<false, kSat>(ray, fr, n0, n1, n2, n3, n4, tbest, 0.f, A.one_bits);
-          ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
-          tgroup = make_uint2(n1.y, drop_source(m & 0x00ffffffu, n1.y, ray.src_slot));
+          const uint32_t m = test_children<false, kSat>(ray, fr, n0, n2, n3, n4, tbest, 0.f, A.one_bits);
+          split_hits<kOrdered>(m, n1, fr, ray.src_slot, node, ngroup, tgroup);
           did_node = true;
         }
       }
@@ -342,28 +337,24 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           const int incl = (int)excl + c;
           if (P >= coop_min && P <= kPairCap) {
             coop = true;
-            uint32_t m = pending ? tgroup.y : 0u;
-            const uint32_t tag = tgroup.x | ((uint32_t)lane << kOwnerShift);
-#if DSRT_ONEHOT_PAIRS
-            // the owner only peels one-hot bits off its mask (two dependent ALU operations per primitive); turning a bit into
-            // a slot number (a bit scan on the slow XU pipe) is left to the testing lane, where it runs 32 lanes wide
-            uint32_t pa = s_pair + (uint32_t)(incl - c) * 8u;
-            while (m) { const uint32_t rest = m & (m - 1u); sts64(pa, make_uint2(tag, m ^ rest)); m = rest; pa += 8u; }
-#else
-            uint32_t pa = s_pair + (uint32_t)(incl - c) * 4u;
-            while (m) { const uint32_t k = 31u - (uint32_t)__clz(m); m &= ~(1u << k); sts32(pa, tag + k); pa += 4u; }
-#endif
-            if (pending) tgroup.y = 0u;
+            // tgroup = (node, primitive bits in the node's nibble format): the owner re-reads the node's (prim_base, valid)
+            // word (L1: the node was fetched a few steps ago) and turns each bit into its record index
+            if (pending) {
+              const uint2 pv = __ldg(reinterpret_cast<const uint2*>(A.nodes + (size_t)tgroup.x * 5 + 1));
+              const uint32_t tag = pv.x | ((uint32_t)lane << kOwnerShift);
+              uint32_t m = tgroup.y;
+              uint32_t pa = s_pair + (uint32_t)(incl - c) * 4u;
+              while (m) {
+                const uint32_t k = 31u - (uint32_t)__clz(m); m &= ~(1u << k);
+                sts32(pa, tag + (uint32_t)__popc(pv.y & ((1u << k) - 1u))); pa += 4u;
+              }
+              tgroup.y = 0u;
+            }
             __syncwarp();
             for (int base = 0; base < P; base += 32) {
               const int j = base + lane;
               if (j < P) {
-#if DSRT_ONEHOT_PAIRS
-                const uint2 pw2 = lds64(s_pair + (uint32_t)j * 8u);
-                const uint32_t pw = pw2.x + (31u - (uint32_t)__clz(pw2.y));
-#else
                 const uint32_t pw = lds32(s_pair + (uint32_t)j * 4u);
-#endif
                 const int slot = (int)(pw & ((1u << kOwnerShift) - 1u)); const uint32_t s = pw >> kOwnerShift;
                 const uint32_t rb = s_blk_warp + s * 4u;
                 TraceRay r2; WatertightRay w2;
@@ -396,10 +387,12 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           }
         }
         if (!coop) {
+          uint2 pv = make_uint2(0u, 0u);
+          if (pending) pv = __ldg(reinterpret_cast<const uint2*>(A.nodes + (size_t)tgroup.x * 5 + 1));
           while (pending && tgroup.y) {
             const uint32_t k = 31u - (uint32_t)__clz(tgroup.y);
             tgroup.y &= ~(1u << k);
-            const int slot = (int)(tgroup.x + k);
+            const int slot = prim_slot(pv.x, pv.y, k);
             if (COUNT) cnt.prims++;
             const float4* pp = A.prims + (size_t)slot * 3;
             const float4 a = DSRT_PRIM_LD(pp), b = DSRT_PRIM_LD(pp + 1);
@@ -427,7 +420,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
       }
       // (3) retire finished rays (their results are written at the next refill)
       if (busy) {
-        if (!done && ngroup.y <= 0x00ffffffu && spa == s_stack && tgroup.y == 0u) done = true;
+        if (!done && !(ngroup.y & kHitBits) && spa == s_stack && tgroup.y == 0u) done = true;
         if (done) { busy = false; fin = true; tgroup.y = 0u; ngroup.y = 0u; spa = s_stack; }
       }
       const int nbusy = __popc(__ballot_sync(kFull, busy));

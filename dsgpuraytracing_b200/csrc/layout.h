@@ -5,12 +5,17 @@
 // own box: lo = origin + qlo * 2^(e-127), hi = origin + qhi * 2^(e-127), rounded OUTWARDS so every
 // quantised box encloses the exact double-precision box of the reference's binary SAH tree.
 // Internal children are stored contiguously from child_base in slot order; the primitives of all
-// leaf children are stored contiguously from prim_base (leaf-contiguous primitive order).
-//   meta[i] == 0            empty slot
-//   meta[i] = 001 sssss     internal child, sssss = 24 + slot
-//   meta[i] = ccc ooooo     leaf child, ccc = unary primitive count (001, 011, 111), ooooo = offset from prim_base
-// so (meta >> 5) << (meta & 31) is the child's contribution to the 32-bit hit mask
-// (bits 31..24 internal children, bits 23..0 primitives).
+// leaf children are stored contiguously from prim_base (leaf-contiguous primitive order, ascending slot).
+//
+// The node test (traverse.cuh) answers with one NIBBLE per slot (slot s -> bits 4s..4s+3, all four set when the ray meets
+// the child's box), so that a hit costs one predicated OR with a constant.  Two 32-bit words of the node turn that into the
+// two things the traversal needs:
+//   valid  nibble s = the low c bits set when slot s is a leaf child with c primitives (c = 1..3), 0 otherwise;
+//          (hits & valid) is the mask of primitives to test, and primitive bit k is record
+//          prim_base + popc(valid & ((1 << k) - 1))
+//   inner  bit 4s+3 set when slot s is an internal child; (hits & inner) are the children to open, (inner >> 3) is the
+//          slot-ordered internal-child mask used to index them from child_base
+// imask (bit s = slot s is internal) is kept for host-side consumers.
 #pragma once
 #include <stdint.h>
 
@@ -21,9 +26,10 @@ constexpr float kInfF = __builtin_huge_valf();
 struct alignas(16) WideNode {
   float ox, oy, oz;
   uint8_t ex, ey, ez, imask;
+  uint32_t prim_base;            // (prim_base, valid) are re-read as one 64-bit word when a lane turns hit bits into records
+  uint32_t valid;
   uint32_t child_base;
-  uint32_t prim_base;
-  uint8_t meta[8];
+  uint32_t inner;
   uint8_t qlox[8], qloy[8];
   uint8_t qloz[8], qhix[8];
   uint8_t qhiy[8], qhiz[8];

@@ -34,12 +34,24 @@ struct TraceRay {
 // source codes of rays that leave a primitive
 DSRT_HD int source_code(int slot, bool is_triangle) { return is_triangle ? slot : -(slot + 2); }
 DSRT_HD bool leaves_sphere(int src, int slot) { return src < -1 && slot == -(src + 2); }
-// removes the source triangle from a leaf hit mask (bits 23..0 = primitives prim_base + bit): a ray always passes the box of the
-// triangle it starts on, so without this every secondary ray would fetch and test its own source once
-DSRT_HD uint32_t drop_source(uint32_t prim_mask, uint32_t prim_base, int src) {
+// Removes the source triangle from a node's primitive mask: a ray always passes the box of the triangle it starts on, so
+// without this every secondary ray would fetch and test its own source once.  prim_mask / valid are in the node's nibble
+// format (layout.h): record prim_base + r is the r-th set bit of `valid`.  The source lies in this node for about one node
+// visit per ray, so the bit is looked up in a (rare) branch instead of with straight-line code on every visit.
+DSRT_HD uint32_t drop_source(uint32_t prim_mask, uint32_t prim_base, uint32_t valid, int src) {
   const uint32_t rel = (uint32_t)src - prim_base;     // wraps to a huge value for src < prim_base (incl. -1 and sphere codes)
-  return rel < 24u ? prim_mask & ~(1u << rel) : prim_mask;
+  if (rel < (uint32_t)hd_popc(valid)) {
+    uint32_t v = valid;
+#pragma unroll 1
+    for (uint32_t i = 0; i < rel; i++) v &= v - 1u;
+    prim_mask &= ~(v & (0u - v));
+  }
+  return prim_mask;
 }
+// record index of primitive bit k of a node (layout.h)
+DSRT_HD int prim_slot(uint32_t prim_base, uint32_t valid, uint32_t k) { return (int)(prim_base + (uint32_t)hd_popc(valid & ((1u << k) - 1u))); }
+constexpr uint32_t kHitBits = 0x88888888u;        // node-group word: bit 4p+3 = pending internal child of priority p
+constexpr uint32_t kInnerBits = 0x11111111u;      //                  bit 4s   = slot s is an internal child
 struct TraceHit {
   float t, u, v;  // u,v = barycentric weights of p2,p3 (the reference's u,v, triangle.cpp:69-70)
   int slot;       // -1 = miss
@@ -211,7 +223,7 @@ DSRT_HD bool hit_sphere64(const Ray64& r, const double* __restrict__ p, double t
 struct NodeFrame {   // per-ray constants
   float idx, idy, idz;   // reciprocal direction (clamped away from 0)
   uint32_t octinv;       // 7 - octant
-  uint32_t octinv4;      // octinv replicated into the four bytes
+  uint32_t bytesel;      // PRMT selector that moves byte b of a word to byte b ^ (octinv >> 1) (order_children)
   bool nx, ny, nz;       // direction component is negative: the near plane of a slab is its HIGH plane
 };
 
@@ -227,7 +239,7 @@ DSRT_HD NodeFrame make_frame(const TraceRay& r, float t_scale = 1.0f) {
   f.nx = dx < 0.0f; f.ny = dy < 0.0f; f.nz = dz < 0.0f;
   const uint32_t oct = (f.nx ? 1u : 0u) | (f.ny ? 2u : 0u) | (f.nz ? 4u : 0u);
   f.octinv = 7u - oct;
-  f.octinv4 = f.octinv * 0x01010101u;
+  f.bytesel = 0x3210u ^ ((f.octinv >> 1) * 0x1111u);
   return f;
 }
 
@@ -243,11 +255,11 @@ DSRT_HD float byte_unit(uint32_t w, int i, uint32_t one) {
 #endif
 }
 
-// Tests the 8 quantised child boxes of one node; returns the 32-bit hit mask (31..24 internal children in
-// visiting priority, 23..0 primitives).  Near / far planes are picked per axis from the ray's sign (no per-child
-// min/max).  Float rounding of the dequantised planes (<= 2^-9 quantum) is covered by the 1/64-quantum margin the
-// host puts on every quantised plane (wide_bvh.cpp), so no widening is needed here; empty slots need no test
-// because their meta byte contributes no bits.  pad > 0 only in parity mode (extra conservative slabs).
+// Tests the 8 quantised child boxes of one node; returns one nibble per SLOT (bits 4s..4s+3 all set when the ray meets the
+// box of slot s; the caller ANDs with the node's `valid` / `inner` words, layout.h -- empty slots drop out there).  Near / far
+// planes are picked per axis from the ray's sign (no per-child min/max).  Float rounding of the dequantised planes (<= 2^-9
+// quantum) is covered by the 1/64-quantum margin the host puts on every quantised plane (wide_bvh.cpp), so no widening is
+// needed here.  pad > 0 only in parity mode (extra conservative slabs).
 //
 // SAT (any-hit rays, DSRT_SAT_SLAB): the frame is pre-scaled by 1 / tmax (make_frame's t_scale), so the ray's valid range is
 // [0, 1] and every plane distance is evaluated with ONE saturating FMA: the clamp to [0, 1] replaces max(near, 0) and
@@ -256,8 +268,8 @@ DSRT_HD float byte_unit(uint32_t w, int i, uint32_t one) {
 // (near clamps to 1) then fails as it must.  Strictness cannot lose a real hit: every quantised box contains its exact box
 // with >= 1/64 quantum to spare on each side, so a ray that touches the contents has near < far by >= 1/32 quantum of t.
 template <bool PARITY, bool SAT = false>
-DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uint4 n0, const uint4 n1,
-                                                  const uint4 n2, const uint4 n3, const uint4 n4, float tmax, float pad, uint32_t one) {
+DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uint4 n0, const uint4 n2, const uint4 n3,
+                                                  const uint4 n4, float tmax, float pad, uint32_t one) {
   const float ox = hd_u2f(n0.x), oy = hd_u2f(n0.y), oz = hd_u2f(n0.z);
   // 2^15 * 2^(e-127) * idir: the exponent byte is biased up by 15 instead of multiplying
   const float sx = hd_u2f(((n0.w & 0xffu) + 15u) << 23) * fr.idx;
@@ -276,18 +288,12 @@ DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uin
   uint32_t mask = 0;
 #pragma unroll
   for (int half = 0; half < 2; half++) {
-    const uint32_t meta4 = half ? n1.w : n1.z;
     const uint32_t qlx = half ? n2.y : n2.x, qly = half ? n2.w : n2.z;
     const uint32_t qlz = half ? n3.y : n3.x, qhx = half ? n3.w : n3.z;
     const uint32_t qhy = half ? n4.y : n4.x, qhz = half ? n4.w : n4.z;
     const uint32_t nearx = fr.nx ? qhx : qlx, farx = fr.nx ? qlx : qhx;
     const uint32_t neary = fr.ny ? qhy : qly, fary = fr.ny ? qly : qhy;
     const uint32_t nearz = fr.nz ? qhz : qlz, farz = fr.nz ? qlz : qhz;
-    // per-child bit index (internal children: visiting priority (24 + slot) ^ octinv) and unary count, 4 at a time
-    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-    const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
-    const uint32_t bit_index4 = (meta4 ^ (fr.octinv4 & inner_mask4)) & 0x1f1f1f1fu;
-    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       bool hit;
@@ -304,10 +310,26 @@ DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uin
         const float tf = fminf(fminf(bx, by), fminf(bz, tmax));
         hit = tn <= tf;
       }
-      if (hit) mask |= ((child_bits4 >> (8 * i)) & 0xffu) << ((bit_index4 >> (8 * i)) & 0xffu);
+      if (hit) mask |= 0xfu << (16 * half + 4 * i);
     }
   }
   return mask;
+}
+
+// Internal-child hits (bit 4s+3 of slot s) -> visiting priority: slot s gets priority p = s ^ octinv (the host places
+// children in octant-ordered slots, wide_bvh.cpp), i.e. bit 4p+3.  XOR of the nibble index = swap of adjacent nibbles
+// (octinv bit 0; a bit-select of the word shifted up and down) + a byte permutation (octinv bits 1, 2; one PRMT).
+DSRT_HD uint32_t order_children(uint32_t hits, const NodeFrame& fr) {
+  const uint32_t sh = (fr.octinv & 1u) << 2;
+  const uint32_t up = hits << sh, down = hits >> sh;
+  const uint32_t x = (up & 0x80808080u) | (down & ~0x80808080u);      // sh == 0: x == hits
+#ifdef __CUDA_ARCH__
+  return __byte_perm(x, 0u, fr.bytesel);
+#else
+  uint32_t r = 0;
+  for (int b = 0; b < 4; b++) r |= ((x >> (8 * ((fr.bytesel >> (4 * b)) & 3u))) & 0xffu) << (8 * b);
+  return r;
+#endif
 }
 
 // ---- the traversal loop --------------------------------------------------------------------------------------
@@ -347,10 +369,35 @@ DSRT_HD void rescale_frame(NodeFrame& fr, float t_scaled_to, float t_new) {
   fr.idx *= k; fr.idy *= k; fr.idz *= k;
 }
 
+// DSRT_ANY_ORDERED: shadow rays open internal children front to back like closest-hit rays (1) or in slot order (0, saves
+// the reordering; an any-hit query is correct in any order)
+#ifndef DSRT_ANY_ORDERED
+#define DSRT_ANY_ORDERED 1
+#endif
+
+// One node step, shared by trace_ray and k_trace: pops the highest-priority pending child of `ngroup` (the caller has checked
+// ngroup.y & kHitBits), returns its node index; `more` tells whether the group still has pending children (push it back).
+template <bool ORDERED>
+DSRT_HD uint32_t next_child(uint2& ngroup, const NodeFrame& fr, bool& more) {
+  const uint32_t bit = 31u - (uint32_t)hd_clz(ngroup.y & kHitBits);
+  ngroup.y &= ~(1u << bit);
+  more = (ngroup.y & kHitBits) != 0u;
+  const uint32_t slot4 = ORDERED ? ((bit & 0x1cu) ^ (fr.octinv << 2)) : (bit & 0x1cu);       // 4 * slot
+  return ngroup.x + (uint32_t)hd_popc(ngroup.y & kInnerBits & ((1u << slot4) - 1u));
+}
+// node test results -> (children to open, primitives to test).  n1 = (prim_base, valid, child_base, inner), layout.h
+template <bool ORDERED>
+DSRT_HD void split_hits(uint32_t m, const uint4 n1, const NodeFrame& fr, int src_slot, uint32_t node, uint2& ngroup, uint2& tgroup) {
+  const uint32_t open = m & n1.w;
+  ngroup = make_uint2(n1.z, (ORDERED ? order_children(open, fr) : open) | (n1.w >> 3));
+  tgroup = make_uint2(node, drop_source(m & n1.y, n1.x, n1.y, src_slot));
+}
+
 template <bool ANY, bool PARITY, bool COUNT>
 DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, uint2* stack, int stride,
                                           TraceHit& hit, double* t64_out, TraceCounters* cnt) {
   constexpr bool SAT = !PARITY && (ANY ? DSRT_SAT_SLAB : DSRT_SAT_CLOSEST);
+  constexpr bool ORDERED = !ANY || DSRT_ANY_ORDERED;
   const float scale0 = SAT ? any_hit_scale(A, ray) : 1.0f;
   NodeFrame fr = make_frame(ray, scale0);
   float t_unit = SAT ? hd_rcp(scale0) : 1.0f;          // the distance that maps to 1 in the saturating node test
@@ -363,28 +410,27 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
   double tbest64 = PARITY ? (double)ray.tmax : 0.0;
   hit.slot = -1; hit.t = ray.tmax; hit.u = 0.f; hit.v = 0.f;
   int sp = 0;
-  uint2 ngroup = make_uint2(0u, 0x80000000u);
+  uint2 ngroup = make_uint2(0u, 0x80000000u);          // "child 0 of nothing": the root
   uint2 tgroup = make_uint2(0u, 0u);
+  uint32_t prim_base = 0, valid = 0;
   while (true) {
-    if (ngroup.y > 0x00ffffffu) {
-      const uint32_t bit = 31u - (uint32_t)hd_clz(ngroup.y);
-      ngroup.y &= ~(1u << bit);
-      if (ngroup.y > 0x00ffffffu) { stack[sp * stride] = ngroup; sp++; }
-      const uint32_t slot = (bit - 24u) ^ fr.octinv;
-      const uint32_t rel = hd_popc(ngroup.y & 0xffu & ((1u << slot) - 1u));
-      const uint4* np = A.nodes + (size_t)(ngroup.x + rel) * 5;
+    if (ngroup.y & kHitBits) {
+      bool more;
+      const uint32_t node = next_child<ORDERED>(ngroup, fr, more);
+      if (more) { stack[sp * stride] = ngroup; sp++; }
+      const uint4* np = A.nodes + (size_t)node * 5;
       const uint4 n0 = hd_ldg(np), n1 = hd_ldg(np + 1), n2 = hd_ldg(np + 2), n3 = hd_ldg(np + 3), n4 = hd_ldg(np + 4);
       if (COUNT) cnt->nodes++;
-      const uint32_t m = test_children<PARITY, SAT>(ray, fr, n0, n1, n2, n3, n4, tbest, A.pad, A.one_bits);
-      ngroup = make_uint2(n1.x, (m & 0xff000000u) | (n0.w >> 24));
-      tgroup = make_uint2(n1.y, drop_source(m & 0x00ffffffu, n1.y, ray.src_slot));
+      const uint32_t m = test_children<PARITY, SAT>(ray, fr, n0, n2, n3, n4, tbest, A.pad, A.one_bits);
+      split_hits<ORDERED>(m, n1, fr, ray.src_slot, node, ngroup, tgroup);
+      prim_base = n1.x; valid = n1.y;
     } else {
       tgroup = make_uint2(0u, 0u);
     }
     while (tgroup.y) {
       const uint32_t k = 31u - (uint32_t)hd_clz(tgroup.y);
       tgroup.y &= ~(1u << k);
-      const int slot = (int)(tgroup.x + k);
+      const int slot = prim_slot(prim_base, valid, k);
       if (COUNT) cnt->prims++;
       if (PARITY) {
         const double* p = A.prims64 + (size_t)slot * 12;
@@ -411,7 +457,7 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
         }
       }
     }
-    if (ngroup.y <= 0x00ffffffu) {
+    if (!(ngroup.y & kHitBits)) {
       if (sp == 0) break;
       sp--;
       ngroup = stack[sp * stride];

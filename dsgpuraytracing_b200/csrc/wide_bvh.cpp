@@ -219,12 +219,11 @@ struct Collapse {
       w.qlox[s] = q[0]; w.qloy[s] = q[1]; w.qloz[s] = q[2]; w.qhix[s] = q[3]; w.qhiy[s] = q[4]; w.qhiz[s] = q[5];
       if (leaf_at[s]) {
         if (cn.range < 1 || cn.range > 3 || prim_off + cn.range > 24) { err = "wide BVH: leaf packing overflow"; return -1; }
-        uint8_t unary = cn.range == 1 ? 1 : (cn.range == 2 ? 3 : 7);
-        w.meta[s] = (uint8_t)((unary << 5) | prim_off);
+        w.valid |= ((1u << cn.range) - 1u) << (4 * s);
         for (int q2 = 0; q2 < cn.range; q2++) slot_prim.push_back(b2.prim_order[cn.start + q2]);
         prim_off += cn.range;
       } else {
-        w.meta[s] = (uint8_t)((1 << 5) | (24 + s));
+        w.inner |= 8u << (4 * s);
         w.imask |= (uint8_t)(1 << s);
         kids_out[n_internal++] = c;
       }

@@ -21,7 +21,7 @@ python tools/profile_tables.py $P/r2_ktrace_depth0_raw.csv $P/r2_ktrace_depth0_n
 ncu -i $O/prof_on_$T.ncu-rep --page source --csv --print-source sass > /tmp/r2_src.csv 2>/dev/null
 rm -rf /tmp/xelf_r2 && mkdir /tmp/xelf_r2 && (cd /tmp/xelf_r2 && cuobjdump -xelf all $OLDPWD/dsgpuraytracing_b200/libdsrt.so > /dev/null && nvdisasm -g -c dsrt_api.sm_100a.cubin > /tmp/r2_dis.txt 2>/dev/null)
 # (cuobjdump prints every function; keep the two production instantiations, without the encoding column)
-cuobjdump -sass dsgpuraytracing_b200/libdsrt.so | sed -E 's/\s+\/\* 0x[0-9a-f]{16} \*\///' | awk '/Function :/ {keep = ($0 ~ /k_traceILb1ELb0/)} keep && (/Function :/ || /^\s+\/\*[0-9a-f]{4}\*\//)' > $P/r2_ktrace_any_sass.txt
-cuobjdump -sass dsgpuraytracing_b200/libdsrt.so | sed -E 's/\s+\/\* 0x[0-9a-f]{16} \*\///' | awk '/Function :/ {keep = ($0 ~ /k_traceILb0ELb0/)} keep && (/Function :/ || /^\s+\/\*[0-9a-f]{4}\*\//)' > $P/r2_ktrace_closest_sass.txt
+cuobjdump -sass dsgpuraytracing_b200/libdsrt.so | sed -E 's/\s+\/\* 0x[0-9a-f]{16} \*\///' | awk '/Function :/ {keep = ($0 ~ /k_traceILb1ELb0/)} keep && (/Function :/ || /^[ \t]+\/\*[0-9a-f][0-9a-f][0-9a-f][0-9a-f]\*\//)' > $P/r2_ktrace_any_sass.txt
+cuobjdump -sass dsgpuraytracing_b200/libdsrt.so | sed -E 's/\s+\/\* 0x[0-9a-f]{16} \*\///' | awk '/Function :/ {keep = ($0 ~ /k_traceILb0ELb0/)} keep && (/Function :/ || /^[ \t]+\/\*[0-9a-f][0-9a-f][0-9a-f][0-9a-f]\*\//)' > $P/r2_ktrace_closest_sass.txt
 python tools/sass_by_line.py /tmp/r2_src.csv /tmp/r2_dis.txt 'k_traceILb1ELb0' 2 60 > $P/r2_ktrace_connect_by_line.txt || true
 cat $P/r2_compaction_table.md; head -8 $P/r2_launch_shares.txt; head -12 $P/r2_ktrace_connect_by_line.txt

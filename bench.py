@@ -378,7 +378,7 @@ def run_ours(a):
              "connect (any-hit traversal, k_trace<true>)": (st.connect_seconds, stc.connect_nodes, stc.connect_prims, st.shadow_rays - st.null_shadow_rays)}
     dom = max(kinds, key=lambda k: kinds[k][0])
     sec, nn, nt, nr = kinds[dom]
-    algo_bytes = nn * 80 + nt * 48 + nr * 48
+    algo_bytes = nn * 80 + nt * 48 + nr * 48      # 80 B of information per node visit (the record is padded to 96 B for 256-bit loads: not counted)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

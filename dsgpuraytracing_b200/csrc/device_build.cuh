@@ -245,7 +245,10 @@ __global__ void k_db_collapse(DbTree T, const int2* __restrict__ items, int n_it
       if (ceil((nhi[k] - (double)org[k]) / scale[k] + 1.0 / 64) <= 255.0 || e >= 110) break;
       e++;
     }
-    (&w.ex)[k] = (uint8_t)(e + 127);
+    (&w.ex)[k] = (uint8_t)(e + 127 + 15);
+#if DSRT_NODE96
+    (&w.sx)[k] = __uint_as_float((uint32_t)(e + 127 + 15) << 23);
+#endif
   }
   w.ox = org[0]; w.oy = org[1]; w.oz = org[2];
   int n_internal = 0, n_leaf_prims = 0;

@@ -303,11 +303,10 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           bool more;
           const uint32_t node = next_child<kOrdered>(ngroup, fr, more);
           if (more) { sts64(spa, ngroup); spa += kStackPitch; }
-          const uint4* np = A.nodes + (size_t)node * 5;
-          const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+          const NodeRegs nd = load_node(A.nodes, node);
           if (COUNT) cnt.nodes++;
-          const uint32_t m = test_children<false, kSat>(ray, fr, n0, n2, n3, n4, tbest, 0.f, A.one_bits);
-          split_hits<kOrdered>(m, n1, fr, ray.src_slot, node, ngroup, tgroup);
+          const uint32_t m = test_children<false, kSat>(ray, fr, nd, tbest, 0.f, A.one_bits);
+          split_hits<kOrdered>(m, nd.n1, fr, ray.src_slot, node, ngroup, tgroup);
           did_node = true;
         }
       }
@@ -340,7 +339,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
             // tgroup = (node, primitive bits in the node's nibble format): the owner re-reads the node's (prim_base, valid)
             // word (L1: the node was fetched a few steps ago) and turns each bit into its record index
             if (pending) {
-              const uint2 pv = __ldg(reinterpret_cast<const uint2*>(A.nodes + (size_t)tgroup.x * 5 + 1));
+              const uint2 pv = load_node_prims(A.nodes, tgroup.x);
               const uint32_t tag = pv.x | ((uint32_t)lane << kOwnerShift);
               uint32_t m = tgroup.y;
               uint32_t pa = s_pair + (uint32_t)(incl - c) * 4u;
@@ -363,18 +362,18 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
                 w2.bxx = ldsf(rb + (kRbBasis + 0) * kBlkPitch); w2.bxy = ldsf(rb + (kRbBasis + 1) * kBlkPitch); w2.bxz = ldsf(rb + (kRbBasis + 2) * kBlkPitch);
                 w2.byx = ldsf(rb + (kRbBasis + 3) * kBlkPitch); w2.byy = ldsf(rb + (kRbBasis + 4) * kBlkPitch); w2.byz = ldsf(rb + (kRbBasis + 5) * kBlkPitch);
                 w2.bzx = ldsf(rb + (kRbBasis + 6) * kBlkPitch); w2.bzy = ldsf(rb + (kRbBasis + 7) * kBlkPitch); w2.bzz = ldsf(rb + (kRbBasis + 8) * kBlkPitch);
-                const float tmax2 = ldsf(rb + kRbTmax * kBlkPitch); const int src2 = (int)lds32(rb + kRbSrc * kBlkPitch);
+                const float tmax2 = ldsf(rb + kRbTmax * kBlkPitch);
                 if (COUNT) cnt.prims++;
                 const float4* pp = A.prims + (size_t)slot * 3;
                 const float4 a = DSRT_PRIM_LD(pp), b = DSRT_PRIM_LD(pp + 1);
                 float t, u, v; bool h;
                 if (b.w != 0.0f) {
                   const float4 cc = DSRT_PRIM_LD(pp + 2);
-                  if (DSRT_TRI_FAST) h = (slot != src2) && hit_triangle_any(ldsf(rb + (kRbPo + 0) * kBlkPitch), ldsf(rb + (kRbPo + 1) * kBlkPitch), ldsf(rb + (kRbPo + 2) * kBlkPitch), w2, a, b, cc, tmax2);
-                  else h = (slot != src2) && hit_triangle(r2, w2, a, b, cc, tmax2, t, u, v);
+                  if (DSRT_TRI_FAST) h = hit_triangle_any(ldsf(rb + (kRbPo + 0) * kBlkPitch), ldsf(rb + (kRbPo + 1) * kBlkPitch), ldsf(rb + (kRbPo + 2) * kBlkPitch), w2, a, b, cc, tmax2);
+                  else h = hit_triangle(r2, w2, a, b, cc, tmax2, t, u, v);
                 } else {
                   // spheres are rare: the owner's origin / direction come back from its queue record (L1 / L2), not from shared memory
-                  const uint32_t item2 = lds32(rb + kRbItem * kBlkPitch);
+                  const uint32_t item2 = lds32(rb + kRbItem * kBlkPitch); const int src2 = (int)lds32(rb + kRbSrc * kBlkPitch);
                   const float4 o2 = DSRT_RAY_LD(ray_o + item2), d2 = DSRT_RAY_LD(ray_d + item2);
                   r2.ox = o2.x; r2.oy = o2.y; r2.oz = o2.z; r2.dx = d2.x; r2.dy = d2.y; r2.dz = d2.z;
                   h = hit_sphere(r2, a, b, leaves_sphere(src2, slot), true, tmax2, t);
@@ -388,7 +387,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
         }
         if (!coop) {
           uint2 pv = make_uint2(0u, 0u);
-          if (pending) pv = __ldg(reinterpret_cast<const uint2*>(A.nodes + (size_t)tgroup.x * 5 + 1));
+          if (pending) pv = load_node_prims(A.nodes, tgroup.x);
           while (pending && tgroup.y) {
             const uint32_t k = 31u - (uint32_t)__clz(tgroup.y);
             tgroup.y &= ~(1u << k);
@@ -405,8 +404,8 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
               w2.bxx = ldsf(rb + (kRbBasis + 0) * kBlkPitch); w2.bxy = ldsf(rb + (kRbBasis + 1) * kBlkPitch); w2.bxz = ldsf(rb + (kRbBasis + 2) * kBlkPitch);
               w2.byx = ldsf(rb + (kRbBasis + 3) * kBlkPitch); w2.byy = ldsf(rb + (kRbBasis + 4) * kBlkPitch); w2.byz = ldsf(rb + (kRbBasis + 5) * kBlkPitch);
               w2.bzx = ldsf(rb + (kRbBasis + 6) * kBlkPitch); w2.bzy = ldsf(rb + (kRbBasis + 7) * kBlkPitch); w2.bzz = ldsf(rb + (kRbBasis + 8) * kBlkPitch);
-              if (ANY && DSRT_TRI_FAST) { h = (slot != ray.src_slot) && hit_triangle_any(ldsf(rb + (kRbPo + 0) * kBlkPitch), ldsf(rb + (kRbPo + 1) * kBlkPitch), ldsf(rb + (kRbPo + 2) * kBlkPitch), w2, a, b, c, tbest); t = 0.f; }
-              else h = (slot != ray.src_slot) && hit_triangle(ray, w2, a, b, c, tbest, t, u, v);
+              if (ANY && DSRT_TRI_FAST) { h = hit_triangle_any(ldsf(rb + (kRbPo + 0) * kBlkPitch), ldsf(rb + (kRbPo + 1) * kBlkPitch), ldsf(rb + (kRbPo + 2) * kBlkPitch), w2, a, b, c, tbest); t = 0.f; }
+              else h = hit_triangle(ray, w2, a, b, c, tbest, t, u, v);
             } else {
               h = hit_sphere(ray, a, b, leaves_sphere(ray.src_slot, slot), ANY, tbest, t);
             }

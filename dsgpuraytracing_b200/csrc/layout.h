@@ -1,8 +1,9 @@
 // layout.h -- HBM data layout shared by the host flattening code and the sm_100a kernels.
 //
-// Wide node: 8-wide BVH node, 80 bytes = five 128-bit loads (compressed wide-BVH layout after
+// Wide node: 8-wide BVH node, 80 bytes of information (compressed wide-BVH layout after
 // Ylitie, Karras, Laine 2017).  Child boxes are quantised to 8 bits per plane relative to the node's
-// own box: lo = origin + qlo * 2^(e-127), hi = origin + qhi * 2^(e-127), rounded OUTWARDS so every
+// own box: lo = origin + qlo * 2^(e-127), hi = origin + qhi * 2^(e-127) (the exponent bytes ex, ey, ez hold e + 15: the
+// node test multiplies by 2^15, traverse.cuh byte_unit), rounded OUTWARDS so every
 // quantised box encloses the exact double-precision box of the reference's binary SAH tree.
 // Internal children are stored contiguously from child_base in slot order; the primitives of all
 // leaf children are stored contiguously from prim_base (leaf-contiguous primitive order, ascending slot).
@@ -23,9 +24,20 @@ namespace dsrt {
 
 constexpr float kInfF = __builtin_huge_valf();
 
-struct alignas(16) WideNode {
+// DSRT_NODE96 (default): the node is padded to 96 bytes = three 256-bit loads (sm_100 LDG.256) on 32-byte boundaries.  An
+// 80-byte node already occupies three 32-byte sectors wherever it lies, so the padding costs no cache or DRAM traffic; it
+// takes two load instructions (and two passes through the LSU data pipe) off every node visit, and the spare words hold the
+// three plane scales 2^15 * 2^(e-127) as ready-made floats (no exponent decoding in the node test).
+#ifndef DSRT_NODE96
+#define DSRT_NODE96 1
+#endif
+struct alignas(DSRT_NODE96 ? 32 : 16) WideNode {
   float ox, oy, oz;
   uint8_t ex, ey, ez, imask;
+#if DSRT_NODE96
+  float sx, sy, sz;              // 2^15 * 2^(e-127) per axis: the floats the exponent bytes encode
+  uint32_t pad;
+#endif
   uint32_t prim_base;            // (prim_base, valid) are re-read as one 64-bit word when a lane turns hit bits into records
   uint32_t valid;
   uint32_t child_base;
@@ -34,7 +46,9 @@ struct alignas(16) WideNode {
   uint8_t qloz[8], qhix[8];
   uint8_t qhiy[8], qhiz[8];
 };
-static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
+static_assert(sizeof(WideNode) == (DSRT_NODE96 ? 96 : 80), "WideNode must be 80 (96) bytes");
+constexpr int kNodeQuads = (int)(sizeof(WideNode) / 16);       // 128-bit words per node
+constexpr int kNodeInfoBytes = 80;                             // bytes of information per node (what the roofline counts)
 
 // Primitive record in leaf-contiguous order, 48 bytes = three 128-bit loads.
 //   triangle: a = (p1.xyz, prim_id bits)  b = (p2.xyz, 1.0f)      c = (p3.xyz, bsdf bits)

@@ -40,7 +40,7 @@ DSRT_HD bool leaves_sphere(int src, int slot) { return src < -1 && slot == -(src
 // visit per ray, so the bit is looked up in a (rare) branch instead of with straight-line code on every visit.
 DSRT_HD uint32_t drop_source(uint32_t prim_mask, uint32_t prim_base, uint32_t valid, int src) {
   const uint32_t rel = (uint32_t)src - prim_base;     // wraps to a huge value for src < prim_base (incl. -1 and sphere codes)
-  if (rel < (uint32_t)hd_popc(valid)) {
+  if (rel < 24u && rel < (uint32_t)hd_popc(valid)) {      // (a node holds at most 24 primitives: the first test is the cheap one)
     uint32_t v = valid;
 #pragma unroll 1
     for (uint32_t i = 0; i < rel; i++) v &= v - 1u;
@@ -219,11 +219,53 @@ DSRT_HD bool hit_sphere64(const Ray64& r, const double* __restrict__ p, double t
   return true;
 }
 
+// ---- node fetch -----------------------------------------------------------------------------------------------
+struct NodeRegs {
+  uint4 n0;            // ox, oy, oz (float bits), exponent bytes | imask
+  uint4 n1;            // prim_base, valid, child_base, inner
+  uint4 n2, n3, n4;    // quantised planes: (qlox, qloy) (qloz, qhix) (qhiy, qhiz), 8 bytes each
+  float sx, sy, sz;    // plane scales 2^15 * 2^(e-127)
+};
+DSRT_HD NodeRegs load_node(const uint4* __restrict__ nodes, uint32_t node) {
+  NodeRegs n;
+  const uint4* np = nodes + (size_t)node * kNodeQuads;
+#if DSRT_NODE96
+#ifdef __CUDA_ARCH__
+  uint32_t sx, sy, sz, pad;
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(n.n0.x), "=r"(n.n0.y), "=r"(n.n0.z), "=r"(n.n0.w), "=r"(sx), "=r"(sy), "=r"(sz), "=r"(pad) : "l"(np));
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(n.n1.x), "=r"(n.n1.y), "=r"(n.n1.z), "=r"(n.n1.w), "=r"(n.n2.x), "=r"(n.n2.y), "=r"(n.n2.z), "=r"(n.n2.w) : "l"(np + 2));
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(n.n3.x), "=r"(n.n3.y), "=r"(n.n3.z), "=r"(n.n3.w), "=r"(n.n4.x), "=r"(n.n4.y), "=r"(n.n4.z), "=r"(n.n4.w) : "l"(np + 4));
+  n.sx = __uint_as_float(sx); n.sy = __uint_as_float(sy); n.sz = __uint_as_float(sz);
+#else
+  const uint4 s4 = np[1];
+  n.n0 = np[0]; n.n1 = np[2]; n.n2 = np[3]; n.n3 = np[4]; n.n4 = np[5];
+  n.sx = hd_u2f(s4.x); n.sy = hd_u2f(s4.y); n.sz = hd_u2f(s4.z);
+#endif
+#else
+  n.n0 = hd_ldg(np); n.n1 = hd_ldg(np + 1); n.n2 = hd_ldg(np + 2); n.n3 = hd_ldg(np + 3); n.n4 = hd_ldg(np + 4);
+  // the node stores its exponent bytes biased up by 15 (layout.h): a byte moved into the exponent field IS 2^15 * 2^(e-127)
+  n.sx = hd_u2f((n.n0.w << 23) & 0x7f800000u); n.sy = hd_u2f((n.n0.w << 15) & 0x7f800000u); n.sz = hd_u2f((n.n0.w << 7) & 0x7f800000u);
+#endif
+  return n;
+}
+// the (prim_base, valid) word pair of a node (layout.h)
+DSRT_HD uint2 load_node_prims(const uint4* __restrict__ nodes, uint32_t node) {
+  const uint2* p = reinterpret_cast<const uint2*>(nodes + (size_t)node * kNodeQuads + (DSRT_NODE96 ? 2 : 1));
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 // ---- node test -----------------------------------------------------------------------------------------------
 struct NodeFrame {   // per-ray constants
   float idx, idy, idz;   // reciprocal direction (clamped away from 0)
-  uint32_t octinv;       // 7 - octant
-  uint32_t bytesel;      // PRMT selector that moves byte b of a word to byte b ^ (octinv >> 1) (order_children)
+  uint32_t oct4;         // 4 * (7 - octant): the XOR that turns a slot's nibble position into its visiting priority's
+  uint32_t bytesel;      // PRMT selector that moves byte b of a word to byte b ^ (octant code >> 1) (order_children)
   bool nx, ny, nz;       // direction component is negative: the near plane of a slab is its HIGH plane
 };
 
@@ -238,8 +280,8 @@ DSRT_HD NodeFrame make_frame(const TraceRay& r, float t_scale = 1.0f) {
   f.idx = hd_rcp(dx) * t_scale; f.idy = hd_rcp(dy) * t_scale; f.idz = hd_rcp(dz) * t_scale;
   f.nx = dx < 0.0f; f.ny = dy < 0.0f; f.nz = dz < 0.0f;
   const uint32_t oct = (f.nx ? 1u : 0u) | (f.ny ? 2u : 0u) | (f.nz ? 4u : 0u);
-  f.octinv = 7u - oct;
-  f.bytesel = 0x3210u ^ ((f.octinv >> 1) * 0x1111u);
+  f.oct4 = (7u - oct) << 2;
+  f.bytesel = 0x3210u ^ ((f.oct4 >> 3) * 0x1111u);
   return f;
 }
 
@@ -268,13 +310,11 @@ DSRT_HD float byte_unit(uint32_t w, int i, uint32_t one) {
 // (near clamps to 1) then fails as it must.  Strictness cannot lose a real hit: every quantised box contains its exact box
 // with >= 1/64 quantum to spare on each side, so a ray that touches the contents has near < far by >= 1/32 quantum of t.
 template <bool PARITY, bool SAT = false>
-DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uint4 n0, const uint4 n2, const uint4 n3,
-                                                  const uint4 n4, float tmax, float pad, uint32_t one) {
+DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const NodeRegs& nd, float tmax, float pad, uint32_t one) {
+  const uint4 n0 = nd.n0, n2 = nd.n2, n3 = nd.n3, n4 = nd.n4;
   const float ox = hd_u2f(n0.x), oy = hd_u2f(n0.y), oz = hd_u2f(n0.z);
-  // 2^15 * 2^(e-127) * idir: the exponent byte is biased up by 15 instead of multiplying
-  const float sx = hd_u2f(((n0.w & 0xffu) + 15u) << 23) * fr.idx;
-  const float sy = hd_u2f((((n0.w >> 8) & 0xffu) + 15u) << 23) * fr.idy;
-  const float sz = hd_u2f((((n0.w >> 16) & 0xffu) + 15u) << 23) * fr.idz;
+  // 2^15 * 2^(e-127) * idir
+  const float sx = nd.sx * fr.idx, sy = nd.sy * fr.idy, sz = nd.sz * fr.idz;
   float bnx, bny, bnz, bfx, bfy, bfz, sfx = sx, sfy = sy, sfz = sz;
   if (PARITY) {
     const float k = 1.0001f;
@@ -320,11 +360,13 @@ DSRT_HD uint32_t test_children(const TraceRay& r, const NodeFrame& fr, const uin
 // children in octant-ordered slots, wide_bvh.cpp), i.e. bit 4p+3.  XOR of the nibble index = swap of adjacent nibbles
 // (octinv bit 0; a bit-select of the word shifted up and down) + a byte permutation (octinv bits 1, 2; one PRMT).
 DSRT_HD uint32_t order_children(uint32_t hits, const NodeFrame& fr) {
-  const uint32_t sh = (fr.octinv & 1u) << 2;
+  const uint32_t sh = fr.oct4 & 4u;
   const uint32_t up = hits << sh, down = hits >> sh;
   const uint32_t x = (up & 0x80808080u) | (down & ~0x80808080u);      // sh == 0: x == hits
 #ifdef __CUDA_ARCH__
-  return __byte_perm(x, 0u, fr.bytesel);
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(r) : "r"(x), "r"(fr.bytesel));      // (__byte_perm would mask the selector first)
+  return r;
 #else
   uint32_t r = 0;
   for (int b = 0; b < 4; b++) r |= ((x >> (8 * ((fr.bytesel >> (4 * b)) & 3u))) & 0xffu) << (8 * b);
@@ -382,7 +424,7 @@ DSRT_HD uint32_t next_child(uint2& ngroup, const NodeFrame& fr, bool& more) {
   const uint32_t bit = 31u - (uint32_t)hd_clz(ngroup.y & kHitBits);
   ngroup.y &= ~(1u << bit);
   more = (ngroup.y & kHitBits) != 0u;
-  const uint32_t slot4 = ORDERED ? ((bit & 0x1cu) ^ (fr.octinv << 2)) : (bit & 0x1cu);       // 4 * slot
+  const uint32_t slot4 = ORDERED ? ((bit & 0x1cu) ^ fr.oct4) : (bit & 0x1cu);       // 4 * slot
   return ngroup.x + (uint32_t)hd_popc(ngroup.y & kInnerBits & ((1u << slot4) - 1u));
 }
 // node test results -> (children to open, primitives to test).  n1 = (prim_base, valid, child_base, inner), layout.h
@@ -418,12 +460,11 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
       bool more;
       const uint32_t node = next_child<ORDERED>(ngroup, fr, more);
       if (more) { stack[sp * stride] = ngroup; sp++; }
-      const uint4* np = A.nodes + (size_t)node * 5;
-      const uint4 n0 = hd_ldg(np), n1 = hd_ldg(np + 1), n2 = hd_ldg(np + 2), n3 = hd_ldg(np + 3), n4 = hd_ldg(np + 4);
+      const NodeRegs nd = load_node(A.nodes, node);
       if (COUNT) cnt->nodes++;
-      const uint32_t m = test_children<PARITY, SAT>(ray, fr, n0, n2, n3, n4, tbest, A.pad, A.one_bits);
-      split_hits<ORDERED>(m, n1, fr, ray.src_slot, node, ngroup, tgroup);
-      prim_base = n1.x; valid = n1.y;
+      const uint32_t m = test_children<PARITY, SAT>(ray, fr, nd, tbest, A.pad, A.one_bits);
+      split_hits<ORDERED>(m, nd.n1, fr, ray.src_slot, node, ngroup, tgroup);
+      prim_base = nd.n1.x; valid = nd.n1.y;
     } else {
       tgroup = make_uint2(0u, 0u);
     }
@@ -445,8 +486,9 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
         float t, u = 0.f, v = 0.f; bool h;
         if (b.w != 0.0f) {
           const float4 c = hd_ldg(pp + 2);
-          if (FAST) { h = (slot != ray.src_slot) && hit_triangle_any(pox, poy, poz, wr, a, b, c, tbest); t = 0.f; }
-          else h = (slot != ray.src_slot) && hit_triangle(ray, wr, a, b, c, tbest, t, u, v);
+          // (the source triangle never gets here: drop_source took it out of the node's primitive mask)
+          if (FAST) { h = hit_triangle_any(pox, poy, poz, wr, a, b, c, tbest); t = 0.f; }
+          else h = hit_triangle(ray, wr, a, b, c, tbest, t, u, v);
         } else {
           h = hit_sphere(ray, a, b, leaves_sphere(ray.src_slot, slot), ANY, tbest, t);
         }

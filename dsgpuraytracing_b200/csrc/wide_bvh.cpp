@@ -199,9 +199,13 @@ struct Collapse {
         if (std::ceil((nb.hi[k] - (double)org[k]) / scale[k] + 1.0 / 64) <= 255.0 || e >= 110) break;
         e++;
       }
-      ebits[k] = (uint8_t)(e + 127);
+      ebits[k] = (uint8_t)(e + 127 + 15);     // stored with the node test's 2^15 folded in (layout.h)
     }
     w.ox = org[0]; w.oy = org[1]; w.oz = org[2]; w.ex = ebits[0]; w.ey = ebits[1]; w.ez = ebits[2];
+#if DSRT_NODE96
+    { const uint32_t bx = (uint32_t)ebits[0] << 23, by = (uint32_t)ebits[1] << 23, bz = (uint32_t)ebits[2] << 23;
+      std::memcpy(&w.sx, &bx, 4); std::memcpy(&w.sy, &by, 4); std::memcpy(&w.sz, &bz, 4); }
+#endif
     w.prim_base = (uint32_t)slot_prim.size();
     w.child_base = child_base;
     int n_internal = 0, prim_off = 0;
@@ -239,6 +243,9 @@ int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_pri
   if (b2.n_nodes <= 0 || n_prims <= 0) {
     // empty scene: a single node with no children
     WideNode w; std::memset(&w, 0, sizeof(w)); w.ex = w.ey = w.ez = 1;
+#if DSRT_NODE96
+    { const uint32_t b = 1u << 23; std::memcpy(&w.sx, &b, 4); std::memcpy(&w.sy, &b, 4); std::memcpy(&w.sz, &b, 4); }
+#endif
     out.nodes.push_back(w); out.max_depth = 1;
     return DSRT_OK;
   }

@@ -56,7 +56,8 @@ Walk* cw_create(const dsrt_scene* s, const dsrt_bvh2* b, int ns_area_light, int 
   return w;
 }
 void cw_destroy(Walk* w) { delete w; }
-void cw_nodes(Walk* w, void* out) { std::memcpy(out, w->wide.nodes.data(), w->wide.nodes.size() * sizeof(WideNode)); }   // raw 80-byte nodes
+int cw_node_bytes() { return (int)sizeof(WideNode); }
+void cw_nodes(Walk* w, void* out) { std::memcpy(out, w->wide.nodes.data(), w->wide.nodes.size() * sizeof(WideNode)); }   // raw nodes (sizeof(WideNode) bytes each, cw_node_bytes)
 void cw_info(Walk* w, int64_t* n_nodes, int32_t* depth) { *n_nodes = (int64_t)w->wide.nodes.size(); *depth = w->wide.max_depth; }
 void cw_slot_prim(Walk* w, int32_t* out) { memcpy(out, w->wide.slot_prim.data(), 4 * w->wide.slot_prim.size()); }
 

@@ -50,7 +50,7 @@ class Walk:
 
     def nodes(self):
         n, _ = self.info()
-        out = np.zeros((n, 80), np.uint8)
+        out = np.zeros((n, int(lib().cw_node_bytes())), np.uint8)
         lib().cw_nodes(self.h, C.c_void_p(out.ctypes.data))
         return out
 

@@ -321,10 +321,14 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
                                            : (__popc(__ballot_sync(kFull, must)) >= wait_mode || !__any_sync(kFull, did_node)));
       if (pm && (trigger || __popc(pm) >= tri_min)) {
         bool coop = false;
+        uint2 pv = make_uint2(0u, 0u);            // (prim_base, valid) of the node the lane's pending primitives belong to
         if (ANY) {
           // Cooperative test: the pending (ray, primitive) pairs of the whole warp are dealt out one per lane, so the
           // long watertight test runs with up to 32 lanes instead of the handful that happen to hold a group.
           const int c = pending ? __popc(tgroup.y) : 0;
+          // tgroup = (node, primitive bits in the node's nibble format): the owner re-reads the node's (prim_base, valid)
+          // word pair (L1: the node was fetched a few steps ago; issued here so that the load flies during the reservation)
+          if (pending) pv = load_node_prims(A.nodes, tgroup.x);
           // every pending lane reserves its slice of the warp's pair table with one shared-memory atomic (measured 1.3 %
           // faster than a five-step shuffle scan of the counts; the order of the pairs does not matter)
           if (lane == 0) sts32(s_cnt, 0u);
@@ -336,16 +340,15 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           const int incl = (int)excl + c;
           if (P >= coop_min && P <= kPairCap) {
             coop = true;
-            // tgroup = (node, primitive bits in the node's nibble format): the owner re-reads the node's (prim_base, valid)
-            // word (L1: the node was fetched a few steps ago) and turns each bit into its record index
+            // the owner turns each primitive bit into its record index (lowest bit first: the bit below it IS the mask of the
+            // records before it, so the only slow-pipe operation per primitive is the population count)
             if (pending) {
-              const uint2 pv = load_node_prims(A.nodes, tgroup.x);
               const uint32_t tag = pv.x | ((uint32_t)lane << kOwnerShift);
               uint32_t m = tgroup.y;
               uint32_t pa = s_pair + (uint32_t)(incl - c) * 4u;
               while (m) {
-                const uint32_t k = 31u - (uint32_t)__clz(m); m &= ~(1u << k);
-                sts32(pa, tag + (uint32_t)__popc(pv.y & ((1u << k) - 1u))); pa += 4u;
+                const uint32_t low = m & (0u - m); m ^= low;
+                sts32(pa, tag + (uint32_t)__popc(pv.y & (low - 1u))); pa += 4u;
               }
               tgroup.y = 0u;
             }
@@ -386,12 +389,11 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           }
         }
         if (!coop) {
-          uint2 pv = make_uint2(0u, 0u);
-          if (pending) pv = load_node_prims(A.nodes, tgroup.x);
+          if (!ANY && pending) pv = load_node_prims(A.nodes, tgroup.x);
           while (pending && tgroup.y) {
-            const uint32_t k = 31u - (uint32_t)__clz(tgroup.y);
-            tgroup.y &= ~(1u << k);
-            const int slot = prim_slot(pv.x, pv.y, k);
+            const uint32_t low = tgroup.y & (0u - tgroup.y);
+            tgroup.y ^= low;
+            const int slot = prim_slot(pv.x, pv.y, low);
             if (COUNT) cnt.prims++;
             const float4* pp = A.prims + (size_t)slot * 3;
             const float4 a = DSRT_PRIM_LD(pp), b = DSRT_PRIM_LD(pp + 1);

@@ -48,8 +48,8 @@ DSRT_HD uint32_t drop_source(uint32_t prim_mask, uint32_t prim_base, uint32_t va
   }
   return prim_mask;
 }
-// record index of primitive bit k of a node (layout.h)
-DSRT_HD int prim_slot(uint32_t prim_base, uint32_t valid, uint32_t k) { return (int)(prim_base + (uint32_t)hd_popc(valid & ((1u << k) - 1u))); }
+// record index of the primitive whose (one-hot) bit in a node's primitive mask is `bit` (layout.h)
+DSRT_HD int prim_slot(uint32_t prim_base, uint32_t valid, uint32_t bit) { return (int)(prim_base + (uint32_t)hd_popc(valid & (bit - 1u))); }
 constexpr uint32_t kHitBits = 0x88888888u;        // node-group word: bit 4p+3 = pending internal child of priority p
 constexpr uint32_t kInnerBits = 0x11111111u;      //                  bit 4s   = slot s is an internal child
 struct TraceHit {
@@ -469,9 +469,9 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
       tgroup = make_uint2(0u, 0u);
     }
     while (tgroup.y) {
-      const uint32_t k = 31u - (uint32_t)hd_clz(tgroup.y);
-      tgroup.y &= ~(1u << k);
-      const int slot = prim_slot(prim_base, valid, k);
+      const uint32_t low = tgroup.y & (0u - tgroup.y);        // lowest pending primitive first
+      tgroup.y ^= low;
+      const int slot = prim_slot(prim_base, valid, low);
       if (COUNT) cnt->prims++;
       if (PARITY) {
         const double* p = A.prims64 + (size_t)slot * 12;

@@ -68,7 +68,7 @@ typedef struct {
   uint64_t camera_samples;    /* camera rays generated */
   uint64_t extend_rays;       /* closest-hit queries (BVHAccel::intersect(ray, isect) calls) */
   uint64_t shadow_rays;       /* any-hit queries (BVHAccel::intersect(ray) calls) */
-  /* fetch counters, only filled when dsrt_set_option("count_traversal", 1): wide-BVH nodes (80 B) and primitive
+  /* fetch counters, only filled when dsrt_set_option("count_traversal", 1): wide-BVH nodes (80 B of information each) and primitive
    * records (48 B) fetched by the extend (closest-hit) and connect (any-hit) kernels */
   uint64_t extend_nodes, extend_prims;
   uint64_t connect_nodes, connect_prims;

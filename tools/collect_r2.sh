@@ -25,3 +25,5 @@ cuobjdump -sass dsgpuraytracing_b200/libdsrt.so | sed -E 's/\s+\/\* 0x[0-9a-f]{1
 cuobjdump -sass dsgpuraytracing_b200/libdsrt.so | sed -E 's/\s+\/\* 0x[0-9a-f]{16} \*\///' | awk '/Function :/ {keep = ($0 ~ /k_traceILb0ELb0/)} keep && (/Function :/ || /^[ \t]+\/\*[0-9a-f][0-9a-f][0-9a-f][0-9a-f]\*\//)' > $P/r2_ktrace_closest_sass.txt
 python tools/sass_by_line.py /tmp/r2_src.csv /tmp/r2_dis.txt 'k_traceILb1ELb0' 2 60 > $P/r2_ktrace_connect_by_line.txt || true
 cat $P/r2_compaction_table.md; head -8 $P/r2_launch_shares.txt; head -12 $P/r2_ktrace_connect_by_line.txt
+# the same counters grouped by what the code does (both instantiations)
+(python tools/sass_categories.py /tmp/r2_src.csv /tmp/r2_dis.txt k_traceILb1ELb0 2; python tools/sass_categories.py /tmp/r2_src.csv /tmp/r2_dis.txt k_traceILb0ELb0 0) > $P/r2_ktrace_categories_raw.txt || true

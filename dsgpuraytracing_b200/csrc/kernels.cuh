@@ -39,6 +39,9 @@ constexpr int kTraceThreads = 128;        // 4 warps per CTA
 #ifndef DSRT_PREFETCH_AHEAD
 #define DSRT_PREFETCH_AHEAD 16384         // queue positions between a refill's loads and the L2 prefetches it issues (0 = off)
 #endif
+#ifndef DSRT_ROUND_CAP
+#define DSRT_ROUND_CAP 0                  // > 0: an owner contributes at most this many primitives to one cooperative round (the scatter loop's trip count is the maximum over the owners)
+#endif
 #ifndef DSRT_NODE_STEPS
 #define DSRT_NODE_STEPS 2                 // node steps a lane may take between two warp-wide primitive-test decisions (1 / 2 / 3: 6839 / 6893 / 6741 Mrays/s)
 #endif
@@ -325,7 +328,11 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
         if (ANY) {
           // Cooperative test: the pending (ray, primitive) pairs of the whole warp are dealt out one per lane, so the
           // long watertight test runs with up to 32 lanes instead of the handful that happen to hold a group.
+#if DSRT_ROUND_CAP > 0
+          const int c = pending ? min(__popc(tgroup.y), DSRT_ROUND_CAP) : 0;      // the rest waits for the next round
+#else
           const int c = pending ? __popc(tgroup.y) : 0;
+#endif
           // tgroup = (node, primitive bits in the node's nibble format): the owner re-reads the node's (prim_base, valid)
           // word pair (L1: the node was fetched a few steps ago; issued here so that the load flies during the reservation)
           if (pending) pv = load_node_prims(A.nodes, tgroup.x);
@@ -346,11 +353,16 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
               const uint32_t tag = pv.x | ((uint32_t)lane << kOwnerShift);
               uint32_t m = tgroup.y;
               uint32_t pa = s_pair + (uint32_t)(incl - c) * 4u;
+#if DSRT_ROUND_CAP > 0
+#pragma unroll 1
+              for (int i = 0; i < c; i++) {
+#else
               while (m) {
+#endif
                 const uint32_t low = m & (0u - m); m ^= low;
                 sts32(pa, tag + (uint32_t)__popc(pv.y & (low - 1u))); pa += 4u;
               }
-              tgroup.y = 0u;
+              tgroup.y = m;             // (0 unless DSRT_ROUND_CAP held primitives back)
             }
             __syncwarp();
             for (int base = 0; base < P; base += 32) {

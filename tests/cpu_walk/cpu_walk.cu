@@ -94,6 +94,20 @@ void cw_philox_raw(const uint32_t* ctr4, uint32_t k0, uint32_t k1, uint32_t* out
   out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
 }
 
+// the node-word helpers of traverse.cuh on raw inputs (tests/test_host.py checks them against a plain restatement)
+// dir: any direction with the wanted signs; out_nodes: the node indices next_child hands out for the group (child_base, hits & inner | inner >> 3), in order
+int cw_open_order(const float* dir, uint32_t child_base, uint32_t hits, uint32_t inner, int ordered, uint32_t* out_nodes) {
+  TraceRay r; r.ox = r.oy = r.oz = 0.f; r.dx = dir[0]; r.dy = dir[1]; r.dz = dir[2]; r.tmax = kInfF; r.src_slot = -1;
+  const NodeFrame fr = make_frame(r);
+  const uint32_t open = hits & inner;
+  uint2 g = make_uint2(child_base, (ordered ? order_children(open, fr) : open) | (inner >> 3));
+  int n = 0;
+  while (g.y & kHitBits) { bool more; out_nodes[n++] = ordered ? next_child<true>(g, fr, more) : next_child<false>(g, fr, more); }
+  return n;
+}
+uint32_t cw_drop_source(uint32_t prim_mask, uint32_t prim_base, uint32_t valid, int src) { return drop_source(prim_mask, prim_base, valid, src); }
+int cw_prim_slot(uint32_t prim_base, uint32_t valid, uint32_t bit) { return prim_slot(prim_base, valid, bit); }
+
 void cw_trace_brute(Walk* w, int64_t n, const float* o, const float* d, int32_t* prim_id, float* t) {
   const Accel A = accel_of(w, false);
   for (int64_t i = 0; i < n; i++) {

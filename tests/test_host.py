@@ -354,3 +354,41 @@ def test_untrusted_file_fields_are_errors_not_crashes(tmp_path):
         fp = str(tmp_path / "broken.dae"); open(fp, "w").write(broken)
         with pytest.raises(D.DsrtError, match="implausible|too short"):
             D.load_dae(fp, 8, 8)
+
+
+def test_node_word_helpers_match_a_plain_restatement():
+    """layout.h node words: the order in which next_child opens the hit internal children of a node (front to back for the
+    ray's octant, child index = child_base + rank among the internal slots), the record index of a primitive bit, and the
+    removal of a ray's source triangle -- product code (host build) against a few lines of Python."""
+    import ctypes as C
+    from tests.cpuwalk import lib
+    L = lib()
+    L.cw_drop_source.restype = C.c_uint32
+    rng = np.random.default_rng(11)
+    for trial in range(400):
+        n_inner = int(rng.integers(0, 9)); slots = rng.permutation(8)
+        inner_slots = sorted(int(x) for x in slots[:n_inner])
+        inner = sum(8 << (4 * s) for s in inner_slots)
+        valid = 0
+        for s in slots[n_inner:]:
+            c = int(rng.integers(0, 4))
+            valid |= ((1 << c) - 1) << (4 * int(s))
+        hit_slots = [s for s in range(8) if rng.random() < 0.6]
+        hits = sum(0xF << (4 * s) for s in hit_slots)
+        d = rng.normal(size=3).astype(np.float32); d[np.abs(d) < 1e-3] = 0.5
+        octant = int(d[0] < 0) | (int(d[1] < 0) << 1) | (int(d[2] < 0) << 2)
+        base = int(rng.integers(0, 1 << 20))
+        out = (C.c_uint32 * 8)()
+        for ordered in (1, 0):
+            n = L.cw_open_order(d.ctypes.data_as(C.c_void_p), C.c_uint32(base), C.c_uint32(hits), C.c_uint32(inner), ordered, out)
+            want = [s for s in inner_slots if s in hit_slots]
+            want.sort(key=(lambda s: -(s ^ (7 - octant))) if ordered else (lambda s: -s))
+            assert [out[i] for i in range(n)] == [base + inner_slots.index(s) for s in want], (trial, ordered)
+        # primitive bits -> records, and the source drop
+        bits = [b for b in range(32) if (valid >> b) & 1]
+        for rank, b in enumerate(bits):
+            assert L.cw_prim_slot(C.c_uint32(base), C.c_uint32(valid), C.c_uint32(1 << b)) == base + rank
+            mask = hits & valid
+            assert L.cw_drop_source(C.c_uint32(mask), C.c_uint32(base), C.c_uint32(valid), base + rank) == mask & ~(1 << b)
+        for src in (-1, -5, base - 1, base + len(bits), base + 40):
+            assert L.cw_drop_source(C.c_uint32(hits & valid), C.c_uint32(base), C.c_uint32(valid), src) == hits & valid

@@ -195,9 +195,13 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
   const uint32_t s_pair = s_blk0 + kRayBlock * kBlkPitch + (threadIdx.x >> 5) * (kPairCap * kPairBytes);       // any-hit kernel only from here on
   const uint32_t s_flag_warp = s_blk0 + kRayBlock * kBlkPitch + (kTraceThreads / 32) * (kPairCap * kPairBytes) + (threadIdx.x & ~31u);
   const uint32_t s_cnt = s_blk0 + kRayBlock * kBlkPitch + (kTraceThreads / 32) * (kPairCap * kPairBytes) + kTraceThreads + (threadIdx.x >> 5) * 4u;
+  const uint32_t n = *n_ptr;
+  // Short queues (the deep bounces: a few thousand rays for 4144 resident warps): a warp takes up to 32 rays at its first
+  // fetch, so warps beyond ceil(n / 32) can never be needed -- they leave before they touch the work counter (the deep
+  // iterations of a pool group are ~15 launches whose duration is mostly this start-up)
+  if ((blockIdx.x * (kTraceThreads / 32) + (threadIdx.x >> 5)) * 32u >= n) return;
   if (ANY && lane == 0) sts32(s_cnt, 0u);
   __syncwarp();
-  const uint32_t n = *n_ptr;
   TraceCounters cnt; cnt.nodes = 0; cnt.prims = 0;
 
   // per-lane traversal state (kept across refills)

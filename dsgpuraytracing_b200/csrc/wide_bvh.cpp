@@ -51,6 +51,7 @@ struct Collapse {
   std::vector<double> c_int; std::vector<uint8_t> split8;
   static constexpr double c_node = 1.0;
   double c_prim = 1.0;      // cost of one primitive test relative to one node visit (build_wide_bvh argument)
+  const std::vector<EndPlane>* end_planes = nullptr;      // axis-aligned area lights (wide_bvh.h)
 
   Collapse(const dsrt_bvh2& b, const std::vector<Box3>& pb) : b2(b), pbox(pb) {}
 
@@ -151,6 +152,23 @@ struct Collapse {
     }
   }
 
+  // is one of these children a flat box (no thickness along `axis`) in the plane of an area light, overlapping its rectangle?
+  bool flat_child_on_light(const int* kids, int nk, int axis, double& at, bool& from_low) const {
+    for (const EndPlane& P : *end_planes) {
+      if (P.axis != axis) continue;
+      for (int i = 0; i < nk; i++) {
+        const Box3& b = T[kids[i]].box;
+        // "flat": the reference's own Cornell quads come out of their COLLADA transform 1e-7 thick
+        const double tol = 1e-6 * std::max(1.0, std::fabs(P.coord));
+        if (std::fabs(b.lo[axis] - P.coord) > tol || std::fabs(b.hi[axis] - P.coord) > tol) continue;
+        bool overlap = true;      // (the reference's Cornell quads are 0.8 x 0.6 under a 0.6 x 0.8 light: overlap, not containment)
+        for (int k = 0; k < 3; k++) if (k != axis && (b.hi[k] < P.lo[k] || b.lo[k] > P.hi[k])) overlap = false;
+        if (overlap) { at = P.from_low ? b.lo[axis] : b.hi[axis]; from_low = P.from_low; return true; }
+      }
+    }
+    return false;
+  }
+
   // 3..4. one wide node: octant-ordered slots + quantisation.  Its internal children get the node indices
   // child_base, child_base+1, ... (in slot order; their binary nodes are returned in kids_out), the primitives of its
   // leaf children are appended to slot_prim.  Returns the number of internal children or a negative error code.
@@ -199,6 +217,20 @@ struct Collapse {
         if (std::ceil((nb.hi[k] - (double)org[k]) / scale[k] + 1.0 / 64) <= 255.0 || e >= 110) break;
         e++;
       }
+      // a child that lies flat in the plane of an area light (EndPlane, wide_bvh.h): lower the origin by a fraction of a
+      // quantum so that the plane sits 3/128 quantum past a grid line on the side the shadow rays arrive from (the margin
+      // every plane gets is 1/64 = 2/128).  Taken only if the rounded float origin still puts it there and the box still fits.
+      double flat_at; bool from_low;
+      if (end_planes && flat_child_on_light(kids, nk, k, flat_at, from_low)) {
+        const double want = from_low ? 3.0 / 128 : 1.0 - 3.0 / 128;
+        const double x0 = (flat_at - (nb.lo[k] - scale[k])) / scale[k];
+        double d = want - (x0 - std::floor(x0));
+        if (d < 0) d += 1.0;
+        const float org_a = round_down(nb.lo[k] - scale[k] * (1.0 + d));
+        const double xa = (flat_at - (double)org_a) / scale[k], fa = xa - std::floor(xa);
+        if (std::fabs(fa - want) <= 1.0 / 256 && (double)org_a <= nb.lo[k] - scale[k] &&
+            std::ceil((nb.hi[k] - (double)org_a) / scale[k] + 1.0 / 64) <= 255.0) org[k] = org_a;
+      }
       ebits[k] = (uint8_t)(e + 127 + 15);     // stored with the node test's 2^15 folded in (layout.h)
     }
     w.ox = org[0]; w.oy = org[1]; w.oz = org[2]; w.ex = ebits[0]; w.ey = ebits[1]; w.ez = ebits[2];
@@ -238,7 +270,26 @@ struct Collapse {
 
 }  // namespace
 
-int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err, double prim_cost) {
+// area lights (type 3) whose direction is a coordinate axis and whose edges span the other two: light.cpp:71-92
+std::vector<EndPlane> light_end_planes(int n_lights, const int32_t* light_type, const double* light_param) {
+  std::vector<EndPlane> out;
+  for (int i = 0; i < n_lights; i++) {
+    if (light_type[i] != 3) continue;
+    const double* p = light_param + 28 * (size_t)i;
+    const double *pos = p + 3, *dir = p + 6, *dx = p + 9, *dy = p + 12;
+    int axis = -1;
+    for (int k = 0; k < 3; k++) if (std::fabs(dir[k]) > 0 && dir[(k + 1) % 3] == 0 && dir[(k + 2) % 3] == 0) axis = k;
+    if (axis < 0 || dx[axis] != 0 || dy[axis] != 0) continue;
+    EndPlane e; e.axis = axis; e.from_low = dir[axis] < 0; e.coord = pos[axis];
+    for (int k = 0; k < 3; k++) { const double h = 0.5 * (std::fabs(dx[k]) + std::fabs(dy[k])); e.lo[k] = pos[k] - h; e.hi[k] = pos[k] + h; }
+    if (!(std::isfinite(e.coord) && std::isfinite(e.lo[0] + e.lo[1] + e.lo[2] + e.hi[0] + e.hi[1] + e.hi[2]))) continue;
+    out.push_back(e);
+  }
+  return out;
+}
+
+int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err, double prim_cost,
+                   const std::vector<EndPlane>* end_planes) {
   out.nodes.clear(); out.slot_prim.clear(); out.max_depth = 0;
   if (b2.n_nodes <= 0 || n_prims <= 0) {
     // empty scene: a single node with no children
@@ -254,6 +305,7 @@ int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_pri
   const double t0 = now();
   Collapse C(b2, pbox);
   C.c_prim = prim_cost;
+  C.end_planes = end_planes && !end_planes->empty() ? end_planes : nullptr;
   std::vector<BNode>& T = C.T;
   // 1. working copy; leaves of more than one primitive are refined (each leaf's new nodes live in its own block of T)
   T.resize((size_t)b2.n_nodes);

@@ -25,7 +25,22 @@ int flatten_lights(int n_lights, const int32_t* light_type, const double* light_
 void build_env_tables(int w, int h, const float* rgb, std::vector<float>& pThetaPhi, std::vector<float>& pTheta,
                       std::vector<float>& pPhiGivenTheta);
 
+// A rectangle on which any-hit rays END: an area light whose plane is perpendicular to a coordinate axis.  Shadow rays stop
+// 0.1 % short of their light sample (pathtracer.cpp:486-504), so geometry that lies IN the light's plane -- the emissive quad
+// every Cornell scene of the reference puts under its area light -- passes the box test of almost every shadow ray unless the
+// quantised plane that faces the arriving rays is within 0.001 x distance of the true plane.  A wide node that holds such a
+// flat child therefore shifts its quantisation grid by a fraction of a quantum so that this one plane falls just past a grid
+// line (wide_bvh.cpp, step 4); every box stays conservative, only where the rounding slack goes changes.
+struct EndPlane {
+  int axis;             // the light's plane is coord along this axis
+  bool from_low;        // rays that carry radiance arrive from the low side (the light faces -axis)
+  double coord;
+  double lo[3], hi[3];  // extent of the rectangle (lo[axis] == hi[axis] == coord)
+};
+std::vector<EndPlane> light_end_planes(int n_lights, const int32_t* light_type, const double* light_param);
+
 // prim_cost: SAH cost of one primitive test relative to one wide-node visit in the collapse (1.0 measured best on B200)
-int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err, double prim_cost = 1.0);
+int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err, double prim_cost = 1.0,
+                   const std::vector<EndPlane>* end_planes = nullptr);
 
 }  // namespace dsrt

@@ -127,6 +127,10 @@ int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t
  * "max_ctas_per_sm" (caps the persistent grid; 0 = what fits), "smem_carveout_pct" (shared-memory carve-out of the
  * traversal kernels, -1 = driver default, which measured best), "collapse_prim_cost_pct" (SAH cost of a primitive test
  * relative to a wide-node visit in the collapse, percent; default 100; applies at the next dsrt_build_accel),
+ * "light_aligned_grid" (0/1, default 1; applies at the next dsrt_build_accel: a wide node that holds a flat child in the
+ * plane of an axis-aligned area light shifts its quantisation grid by a fraction of a quantum so that the plane facing the
+ * arriving shadow rays is tight -- they stop 0.1 % short of the light, src/pathtracer.cpp:486-504, and then miss the box of
+ * the emissive quad under the light instead of testing its triangles; results are unchanged, boxes stay conservative),
  * "skip_null_shadow" (0/1, default 0: the reference traces every shadow ray before it evaluates the BSDF and the cosine,
  * src/pathtracer.cpp:497-519; 1 = shadow rays whose contribution is exactly zero -- light behind the surface, non-diffuse
  * BSDF, emitter facing away -- keep their queue slot but are not traced; the image is identical, dsrt_stats.null_shadow_rays

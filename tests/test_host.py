@@ -392,3 +392,38 @@ def test_node_word_helpers_match_a_plain_restatement():
             assert L.cw_drop_source(C.c_uint32(mask), C.c_uint32(base), C.c_uint32(valid), base + rank) == mask & ~(1 << b)
         for src in (-1, -5, base - 1, base + len(bits), base + 40):
             assert L.cw_drop_source(C.c_uint32(hits & valid), C.c_uint32(base), C.c_uint32(valid), src) == hits & valid
+
+
+@pytest.mark.parametrize("name", ["CBspheres_lambertian", "CBbunny"])
+def test_light_aligned_grid_same_image_fewer_primitive_tests(name, golden, monkeypatch):
+    """wide_bvh.h EndPlane: a node holding the emissive quad under an axis-aligned area light shifts its quantisation grid so
+    that the quad's light-facing plane lies 3/128 quantum past a grid line.  Shadow rays (which stop at 0.999 x distance,
+    pathtracer.cpp:486-504) then miss the quad's box.  Same paths, same image, same segment counts -- fewer primitive tests;
+    and every quantised box still encloses its exact box with the 1/64-quantum margin (checked on the node itself)."""
+    g = golden(name); depth = CONFIGS[name]["depth"]; cam = g["small_camera"]
+    w1 = Walk(g, g, 4, camera=cam)
+    rgb1, c1 = w1.render(2, depth, seed=5)
+    monkeypatch.setenv("CW_NO_LIGHT_GRID", "1")
+    w0 = Walk(g, g, 4, camera=cam)
+    rgb0, c0 = w0.render(2, depth, seed=5)
+    assert np.array_equal(rgb0, rgb1) and list(c0[:3]) == list(c1[:3])
+    assert int(c1[4]) < 0.9 * int(c0[4]), (c0, c1)          # primitive tests
+    assert int(c1[3]) <= int(c0[3])                          # node visits
+    # the node that holds the light quad: its low plane along the light's axis is within 1/16 quantum below the quad
+    lt = np.asarray(g["light_type"]); lp = np.asarray(g["light_param"]).reshape(-1, 28)
+    area = lp[lt == 3][0]; axis = int(np.argmax(np.abs(area[6:9]))); coord = area[3 + axis]
+    assert area[6 + axis] < 0                                # faces -axis: rays arrive from the low side
+    found = 0
+    for raw in w1.nodes():
+        b = raw.tobytes()
+        org = np.frombuffer(b[:12], np.float32).astype(np.float64); scale = np.frombuffer(b[16:28], np.float32).astype(np.float64) / 2 ** 15
+        valid = int(np.frombuffer(b[36:40], np.uint32)[0]); inner = int(np.frombuffer(b[44:48], np.uint32)[0])
+        q = np.frombuffer(b[48:96], np.uint8).reshape(6, 8).astype(np.float64)
+        for s in range(8):
+            if not ((valid >> (4 * s)) & 0xF or (inner >> (4 * s + 3)) & 1):
+                continue
+            lo = org[axis] + q[axis, s] * scale[axis]; hi = org[axis] + q[3 + axis, s] * scale[axis]
+            if hi - lo <= 1.0001 * scale[axis] and lo < coord < hi and (coord - lo) < scale[axis] / 16:
+                assert (coord - lo) >= scale[axis] / 64
+                found += 1
+    assert found >= 1

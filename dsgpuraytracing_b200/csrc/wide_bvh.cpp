@@ -23,6 +23,7 @@
 #include <cstring>
 #include <deque>
 #include <future>
+#include <unordered_map>
 
 #include "wide_bvh.h"
 
@@ -136,6 +137,7 @@ struct Collapse {
   struct Kid { int bnode; bool leaf; };
   void collect(int n, std::vector<Kid>& kids) const {
     kids.clear();
+    if (!regrouped.empty()) { const auto it = regrouped.find(n); if (it != regrouped.end()) { kids = it->second; return; } }
     struct Item { int n, i; };
     Item st[64]; int sp = 0;
     if (T[n].l < 0) { kids.push_back({n, true}); return; }           // the root itself is a (<= 3 primitive) leaf
@@ -149,6 +151,68 @@ struct Collapse {
       const int l2 = resolve(T[it.n].l), r2 = resolve(T[it.n].r);
       const int k = dp[it.n].split[i];
       st[sp++] = {r2, i - k}; st[sp++] = {l2, k};
+    }
+  }
+
+  // 2b. regrouping at the top of the tree.  The dynamic programme can only cut the binary tree it is given, and the reference's
+  // binned SAH leaves scene-sized triangles (the Cornell walls) in a subtree whose box is the whole scene: that subtree becomes
+  // an internal child every ray has to open.  For a wide node N with children K and an internal child C that covers a large
+  // part of N, the SAH cost of any arrangement of the items I = (K \ C) + children(C) into direct children and new internal
+  // nodes G_j differs only in sum_j area(G_j) (each item's own term area(item) * cost(item) appears in every arrangement): the
+  // current arrangement pays area(C).  Greedy agglomeration (cheapest increase of the summed group area first, <= 8 members per
+  // group) until <= 8 slots are left; taken when the groups' summed area is < 0.9 area(C).  Groups become synthetic nodes of T
+  // whose children are listed explicitly (`regrouped`); only nodes whose box is >= 1/64 of the root's area are looked at.
+  std::unordered_map<int, std::vector<Kid>> regrouped;
+  int n_regrouped = 0;
+  void regroup_top(int root) {
+    const double root_area = T[root].box.half_area();
+    if (!(root_area > 0)) return;
+    std::deque<int> q; q.push_back(root);
+    int budget = 4096;
+    std::vector<Kid> kids, sub;
+    struct Grp { Box3 box; std::vector<Kid> members; int range; };
+    auto area = [](const Box3& b) { const double a = b.half_area(); return a >= 0 ? a : 0.0; };
+    while (!q.empty() && budget-- > 0) {
+      const int n = q.front(); q.pop_front();
+      if (area(T[n].box) < root_area / 64) continue;
+      for (int round = 0; round < 8; round++) {
+        collect(n, kids);
+        int ci = -1; double ca = 0.3 * area(T[n].box);
+        for (size_t i = 0; i < kids.size(); i++) if (!kids[i].leaf && area(T[kids[i].bnode].box) > ca) { ca = area(T[kids[i].bnode].box); ci = (int)i; }
+        if (ci < 0) break;
+        collect(kids[ci].bnode, sub);
+        std::vector<Grp> g;
+        for (size_t i = 0; i < kids.size(); i++) if ((int)i != ci) g.push_back({T[kids[i].bnode].box, {kids[i]}, T[kids[i].bnode].range});
+        for (const Kid& k : sub) g.push_back({T[k.bnode].box, {k}, T[k.bnode].range});
+        bool ok = true;
+        while (g.size() > 8 && ok) {
+          int bi = -1, bj = -1; double bd = std::numeric_limits<double>::infinity();
+          for (size_t i = 0; i < g.size(); i++) for (size_t j = i + 1; j < g.size(); j++) {
+            if (g[i].members.size() + g[j].members.size() > 8) continue;
+            Box3 u = g[i].box; u.grow(g[j].box);
+            const double d = area(u) - (g[i].members.size() > 1 ? area(g[i].box) : 0.0) - (g[j].members.size() > 1 ? area(g[j].box) : 0.0);
+            if (d < bd) { bd = d; bi = (int)i; bj = (int)j; }
+          }
+          if (bi < 0) { ok = false; break; }
+          g[bi].box.grow(g[bj].box); g[bi].range += g[bj].range;
+          g[bi].members.insert(g[bi].members.end(), g[bj].members.begin(), g[bj].members.end());
+          g.erase(g.begin() + bj);
+        }
+        if (!ok) break;
+        double cost = 0; for (const Grp& x : g) if (x.members.size() > 1) cost += area(x.box);
+        if (!(cost < 0.9 * ca)) break;
+        std::vector<Kid> nk;
+        for (const Grp& x : g) {
+          if (x.members.size() == 1) { nk.push_back(x.members[0]); continue; }
+          BNode b; b.box = x.box; b.start = -1; b.range = x.range; b.l = b.r = -1;      // children: regrouped[id], never l / r
+          const int id = (int)T.size(); T.push_back(b);
+          regrouped[id] = x.members;
+          nk.push_back({id, false});
+        }
+        regrouped[n] = nk; n_regrouped++;
+      }
+      collect(n, kids);
+      for (const Kid& k : kids) if (!k.leaf) q.push_back(k.bnode);
     }
   }
 
@@ -289,7 +353,7 @@ std::vector<EndPlane> light_end_planes(int n_lights, const int32_t* light_type, 
 }
 
 int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err, double prim_cost,
-                   const std::vector<EndPlane>* end_planes) {
+                   const std::vector<EndPlane>* end_planes, bool regroup_top) {
   out.nodes.clear(); out.slot_prim.clear(); out.max_depth = 0;
   if (b2.n_nodes <= 0 || n_prims <= 0) {
     // empty scene: a single node with no children
@@ -344,6 +408,7 @@ int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_pri
   C.dp.resize(NT); C.c_int.assign(NT, 0.0); C.split8.assign(NT, 0);
   C.dp_parallel(root, std::max(1 << 14, n_prims / (4 * host_threads())));
 
+  if (regroup_top) C.regroup_top(root);
   const double t2 = now();
   // 3..4. emission.  The top of the tree is emitted breadth-first by one thread until kTopJobs subtrees are pending;
   // every pending subtree is then emitted (breadth-first within itself) as an independent task into its own block and

@@ -39,8 +39,9 @@ struct EndPlane {
 };
 std::vector<EndPlane> light_end_planes(int n_lights, const int32_t* light_type, const double* light_param);
 
+// regroup_top: children of the top wide nodes are regrouped where that lowers the SAH cost (wide_bvh.cpp, step 2b)
 // prim_cost: SAH cost of one primitive test relative to one wide-node visit in the collapse (1.0 measured best on B200)
 int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err, double prim_cost = 1.0,
-                   const std::vector<EndPlane>* end_planes = nullptr);
+                   const std::vector<EndPlane>* end_planes = nullptr, bool regroup_top = true);
 
 }  // namespace dsrt

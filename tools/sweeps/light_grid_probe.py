@@ -1,6 +1,7 @@
-"""Effect of the light-aligned quantisation grid (wide_bvh.h EndPlane) on the traversal counters, measured with the CPU walk of the
-product's own host-device code (tests/cpu_walk): primitive tests and node visits per path segment with the option off / on, 2 spp at
-192x108 (stand-ins) or the fixtures' small camera.  python tools/sweeps/light_grid_probe.py"""
+"""Effect of the two round-2 host-side tree refinements -- the light-aligned quantisation grid (wide_bvh.h EndPlane) and the regrouping
+of the top wide nodes (wide_bvh.cpp step 2b) -- on the traversal counters, measured with the CPU walk of the product's own host-device
+code (tests/cpu_walk): node visits and primitive tests per path segment with both off / grid only / both on, 2 spp at 192x108
+(stand-ins) or the fixtures' small camera.  python tools/sweeps/light_grid_probe.py"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -11,22 +12,27 @@ from tests.scenes import CONFIGS
 
 def run(arr, bvh, cam, depth):
     out = []
-    for off in (True, False):
-        if off: os.environ["CW_NO_LIGHT_GRID"] = "1"
-        else: os.environ.pop("CW_NO_LIGHT_GRID", None)
-        rgb, c = Walk(arr, bvh, 4, camera=cam).render(2, depth, seed=3)
-        out.append((rgb, c))
-    (r0, c0), (r1, c1) = out
-    seg = float(c0[1] + c0[2])
-    return np.array_equal(r0, r1) and list(c0[:3]) == list(c1[:3]), c0[3] / seg, c1[3] / seg, c0[4] / seg, c1[4] / seg
+    for env in ({"CW_NO_LIGHT_GRID": "1", "CW_NO_REGROUP": "1"}, {"CW_NO_REGROUP": "1"}, {}):
+        for k in ("CW_NO_LIGHT_GRID", "CW_NO_REGROUP"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        w = Walk(arr, bvh, 4, camera=cam)
+        rgb, c = w.render(2, depth, seed=3)
+        out.append((rgb, c, w.info()))
+    seg = float(out[0][1][1] + out[0][1][2])
+    same = all(np.array_equal(out[0][0], o[0]) and list(out[0][1][:3]) == list(o[1][:3]) for o in out[1:])
+    return same, [o[1][3] / seg for o in out], [o[1][4] / seg for o in out], [o[2][1] for o in out]
 
-print("| scene | image + segment counts identical | node visits / segment off -> on | primitive tests / segment off -> on |")
-print("|---|---|---|---|")
-for name, mk in (("c2 CBdragon stand-in", S.cbdragon_standin), ("c3 CBlucy (glass) stand-in", S.cblucy_standin)):
-    sc, cam = mk(192, 108)
-    same, n0, n1, p0, p1 = run(sc, D.build_bvh2(sc), cam, 8)
-    print(f"| {name} | {same} | {n0:.3f} -> {n1:.3f} | {p0:.3f} -> {p1:.3f} ({100 * (p1 / p0 - 1):+.1f} %) |")
+print("| scene | image + segment counts identical | node visits / segment: off -> grid -> grid + regroup | primitive tests / segment | wide levels |")
+print("|---|---|---|---|---|")
+rows = [(n, mk(192, 108), 8) for n, mk in (("c2 CBdragon stand-in", S.cbdragon_standin), ("c3 CBlucy (glass) stand-in", S.cblucy_standin))]
+for name, (sc, cam), depth in rows:
+    same, n, p, lv = run(sc, D.build_bvh2(sc), cam, depth)
+    print(f"| {name} | {same} | {n[0]:.3f} -> {n[1]:.3f} -> {n[2]:.3f} ({100 * (n[2] / n[0] - 1):+.1f} %) | {p[0]:.3f} -> {p[1]:.3f} -> {p[2]:.3f} ({100 * (p[2] / p[0] - 1):+.1f} %) | {lv[0]} -> {lv[2]} |")
 for name in ("CBspheres_lambertian", "CBspheres", "CBgems", "CBcoil", "CBbunny", "bunny"):
     g = dict(np.load(os.path.join(os.path.dirname(__file__), "..", "..", "tests", "golden", name + ".npz")))
-    same, n0, n1, p0, p1 = run(g, g, g["small_camera"], CONFIGS[name]["depth"])
-    print(f"| {name} | {same} | {n0:.3f} -> {n1:.3f} | {p0:.3f} -> {p1:.3f} ({100 * (p1 / p0 - 1):+.1f} %) |")
+    same, n, p, lv = run(g, g, g["small_camera"], CONFIGS[name]["depth"])
+    print(f"| {name} | {same} | {n[0]:.3f} -> {n[1]:.3f} -> {n[2]:.3f} ({100 * (n[2] / n[0] - 1):+.1f} %) | {p[0]:.3f} -> {p[1]:.3f} -> {p[2]:.3f} ({100 * (p[2] / p[0] - 1):+.1f} %) | {lv[0]} -> {lv[2]} |")
+sc, cam = S.triangle_soup(1 << 17, W=192, H=108)
+same, n, p, lv = run(sc, D.build_bvh2(sc), cam, 8)
+print(f"| 128 Ki-triangle soup | {same} | {n[0]:.3f} -> {n[1]:.3f} -> {n[2]:.3f} ({100 * (n[2] / n[0] - 1):+.1f} %) | {p[0]:.3f} -> {p[1]:.3f} -> {p[2]:.3f} ({100 * (p[2] / p[0] - 1):+.1f} %) | {lv[0]} -> {lv[2]} |")

@@ -71,7 +71,7 @@ struct dsrt_ctx {
   Camera cam{};
   int ns_aa = 1, ns_area_light = 4, max_depth = 1;
   uint32_t seed = 0;
-  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 8, opt_refill = 18, opt_refill_hi = 26, opt_refill_patience = 6, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_max_ctas = 0, opt_carveout = -1, opt_prim_cost = 100, opt_mem_budget_mb = 0, opt_device_build = 0, opt_light_phase = 1, opt_regroup = 1;
+  int64_t opt_count = 0, opt_batch_spp = 0, opt_stage_timing = 0, opt_skip_null = 0, opt_tri_min = 8, opt_refill = 18, opt_refill_hi = 26, opt_refill_patience = 6, opt_wait_mode = 0, opt_pool_batches = 8, opt_coop_min = 6, opt_max_ctas = 0, opt_carveout = -1, opt_prim_cost = 100, opt_mem_budget_mb = 0, opt_device_build = 0, opt_light_phase = 1, opt_regroup = 0, opt_flat_slots = 1;
   WideBVH wide;
   std::vector<PrimRecord> recs; std::vector<ShadeRecord> shd; std::vector<PrimRecord64> r64; std::vector<Light> lights;
   int env_w = 0, env_h = 0;
@@ -401,6 +401,7 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
   else if (n == "pool_batches") ctx->opt_pool_batches = std::max<int64_t>(1, value);
   else if (n == "coop_min_pairs") ctx->opt_coop_min = value;
   else if (n == "max_ctas_per_sm") ctx->opt_max_ctas = value;
+  else if (n == "drop_coplanar_mates") { ctx->opt_flat_slots = value != 0; ctx->have_accel = false; }
   else if (n == "regroup_top") { ctx->opt_regroup = value != 0; ctx->have_accel = false; }
   else if (n == "light_aligned_grid") { ctx->opt_light_phase = value != 0; ctx->have_accel = false; }   // takes effect at the next dsrt_build_accel
   else if (n == "collapse_prim_cost_pct") { ctx->opt_prim_cost = std::max<int64_t>(1, value); ctx->have_accel = false; }   // takes effect at the next dsrt_build_accel
@@ -532,6 +533,7 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
   const std::vector<EndPlane> ends = ctx->opt_light_phase ? light_end_planes((int)ctx->light_type.size(), ctx->light_type.data(), ctx->light_param.data()) : std::vector<EndPlane>();
   int rc = build_wide_bvh(b, pbox, ctx->n_prims, ctx->wide, err, (double)ctx->opt_prim_cost / 100.0, &ends, ctx->opt_regroup != 0);
   if (rc) return fail(ctx, rc, err);
+  if (ctx->opt_flat_slots) mark_flat_slots(s, ctx->wide);
   }
   if (ctx->wide.max_depth > kStackEntries) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel: wide BVH deeper than the traversal stack");
   if (ctx->wide.slot_prim.size() >= ((size_t)1 << kOwnerShift)) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel: more than 2^27 primitives");

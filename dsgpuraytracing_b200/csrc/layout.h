@@ -36,7 +36,9 @@ struct alignas(DSRT_NODE96 ? 32 : 16) WideNode {
   uint8_t ex, ey, ez, imask;
 #if DSRT_NODE96
   float sx, sy, sz;              // 2^15 * 2^(e-127) per axis: the floats the exponent bytes encode
-  uint32_t pad;
+  uint32_t flat;                 // nibble s = 0xf when leaf slot s holds two or three COPLANAR triangles (the halves of a wall
+                                 // quad): a ray that starts on one of them cannot hit the others, so drop_source (traverse.cuh)
+                                 // takes the whole slot out of the hit mask; set by mark_flat_slots (wide_bvh.cpp), 0 otherwise
 #endif
   uint32_t prim_base;            // (prim_base, valid) are re-read as one 64-bit word when a lane turns hit bits into records
   uint32_t valid;

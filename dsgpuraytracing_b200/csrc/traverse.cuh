@@ -38,13 +38,30 @@ DSRT_HD bool leaves_sphere(int src, int slot) { return src < -1 && slot == -(src
 // without this every secondary ray would fetch and test its own source once.  prim_mask / valid are in the node's nibble
 // format (layout.h): record prim_base + r is the r-th set bit of `valid`.  The source lies in this node for about one node
 // visit per ray, so the bit is looked up in a (rare) branch instead of with straight-line code on every visit.
-DSRT_HD uint32_t drop_source(uint32_t prim_mask, uint32_t prim_base, uint32_t valid, int src) {
+// The node's `flat` word (layout.h) extends this to the source's coplanar slot mates -- the other half of a wall quad, which
+// every ray leaving a Cornell wall would otherwise fetch and test (0.85 of the 3.1 primitive tests per shadow ray on the bench
+// scene): a ray that starts in a triangle's plane meets that plane at t = 0 only.  The word is read in the rare branch.
+DSRT_HD uint32_t load_node_flat(const uint4* __restrict__ nodes, uint32_t node) {
+#if DSRT_NODE96
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(nodes + (size_t)node * kNodeQuads + 1) + 3;
+#ifdef __CUDA_ARCH__
+  return __ldg(p);
+#else
+  return *p;
+#endif
+#else
+  return 0u;
+#endif
+}
+DSRT_HD uint32_t drop_source(uint32_t prim_mask, uint32_t prim_base, uint32_t valid, int src, const uint4* __restrict__ nodes = nullptr, uint32_t node = 0u) {
   const uint32_t rel = (uint32_t)src - prim_base;     // wraps to a huge value for src < prim_base (incl. -1 and sphere codes)
   if (rel < 24u && rel < (uint32_t)hd_popc(valid)) {      // (a node holds at most 24 primitives: the first test is the cheap one)
     uint32_t v = valid;
 #pragma unroll 1
     for (uint32_t i = 0; i < rel; i++) v &= v - 1u;
-    prim_mask &= ~(v & (0u - v));
+    const uint32_t bit = v & (0u - v);
+    const uint32_t flat = nodes ? load_node_flat(nodes, node) : 0u;
+    prim_mask &= ~(bit | (flat & (0xfu << ((31u - (uint32_t)hd_clz(bit)) & 0x1cu))));
   }
   return prim_mask;
 }
@@ -429,10 +446,10 @@ DSRT_HD uint32_t next_child(uint2& ngroup, const NodeFrame& fr, bool& more) {
 }
 // node test results -> (children to open, primitives to test).  n1 = (prim_base, valid, child_base, inner), layout.h
 template <bool ORDERED>
-DSRT_HD void split_hits(uint32_t m, const uint4 n1, const NodeFrame& fr, int src_slot, uint32_t node, uint2& ngroup, uint2& tgroup) {
+DSRT_HD void split_hits(uint32_t m, const uint4 n1, const NodeFrame& fr, int src_slot, const uint4* __restrict__ nodes, uint32_t node, uint2& ngroup, uint2& tgroup) {
   const uint32_t open = m & n1.w;
   ngroup = make_uint2(n1.z, (ORDERED ? order_children(open, fr) : open) | (n1.w >> 3));
-  tgroup = make_uint2(node, drop_source(m & n1.y, n1.x, n1.y, src_slot));
+  tgroup = make_uint2(node, drop_source(m & n1.y, n1.x, n1.y, src_slot, nodes, node));
 }
 
 template <bool ANY, bool PARITY, bool COUNT>
@@ -463,7 +480,7 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
       const NodeRegs nd = load_node(A.nodes, node);
       if (COUNT) cnt->nodes++;
       const uint32_t m = test_children<PARITY, SAT>(ray, fr, nd, tbest, A.pad, A.one_bits);
-      split_hits<ORDERED>(m, nd.n1, fr, ray.src_slot, node, ngroup, tgroup);
+      split_hits<ORDERED>(m, nd.n1, fr, ray.src_slot, A.nodes, node, ngroup, tgroup);
       prim_base = nd.n1.x; valid = nd.n1.y;
     } else {
       tgroup = make_uint2(0u, 0u);

@@ -480,6 +480,49 @@ int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_pri
   return DSRT_OK;
 }
 
+// Sets WideNode::flat (layout.h): leaf slots whose two or three primitives are triangles in one plane.  "In one plane": every
+// vertex within 1e-6 of the slot's extent of the plane of the slot's largest triangle (the reference's own wall quads come out
+// of their COLLADA transforms 1e-7 off).  A ray leaving one of them then skips its slot mates (drop_source, traverse.cuh).
+void mark_flat_slots(const dsrt_scene& sc, WideBVH& wide) {
+#if DSRT_NODE96
+  parallel_for(wide.nodes.size(), (size_t)1 << 14, [&](size_t n0, size_t n1) {
+    for (size_t n = n0; n < n1; n++) {
+      WideNode& w = wide.nodes[n];
+      w.flat = 0;
+      uint32_t rank = 0;
+      for (int s = 0; s < 8; s++) {
+        const int c = __builtin_popcount((w.valid >> (4 * s)) & 0xfu);
+        const uint32_t first = w.prim_base + rank; rank += (uint32_t)c;
+        if (c < 2) continue;
+        const double* best = nullptr; double best_n2 = 0, nx = 0, ny = 0, nz = 0, ext = 0; bool tris = true;
+        for (int i = 0; i < c; i++) {
+          const int p = wide.slot_prim[first + i];
+          if (sc.prim_type[p] != 1) { tris = false; break; }
+          const double* v = sc.tri_pos + 9 * (size_t)p;
+          const double ax = v[3] - v[0], ay = v[4] - v[1], az = v[5] - v[2], bx = v[6] - v[0], by = v[7] - v[1], bz = v[8] - v[2];
+          const double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx, n2 = cx * cx + cy * cy + cz * cz;
+          ext = std::max(ext, std::sqrt(std::max(ax * ax + ay * ay + az * az, bx * bx + by * by + bz * bz)));
+          if (n2 > best_n2) { best_n2 = n2; best = v; nx = cx; ny = cy; nz = cz; }
+        }
+        if (!tris || !best || !(best_n2 > 0) || !std::isfinite(best_n2)) continue;
+        const double inv = 1.0 / std::sqrt(best_n2);
+        double dev = 0;
+        for (int i = 0; i < c; i++) {
+          const double* v = sc.tri_pos + 9 * (size_t)wide.slot_prim[first + i];
+          for (int k = 0; k < 3; k++) {
+            dev = std::max(dev, std::fabs(((v[3 * k] - best[0]) * nx + (v[3 * k + 1] - best[1]) * ny + (v[3 * k + 2] - best[2]) * nz) * inv));
+            ext = std::max(ext, std::sqrt((v[3 * k] - best[0]) * (v[3 * k] - best[0]) + (v[3 * k + 1] - best[1]) * (v[3 * k + 1] - best[1]) + (v[3 * k + 2] - best[2]) * (v[3 * k + 2] - best[2])));
+          }
+        }
+        if (dev <= 1e-6 * ext) w.flat |= 0xfu << (4 * s);
+      }
+    }
+  });
+#else
+  (void)sc; (void)wide;
+#endif
+}
+
 void flatten_records(const dsrt_scene& sc, const WideBVH& wide, std::vector<PrimRecord>& recs, std::vector<ShadeRecord>& shd) {
   const size_t n = wide.slot_prim.size();
   recs.resize(n ? n : 1); shd.resize(n ? n : 1);

@@ -16,6 +16,8 @@ struct WideBVH {
 
 // primitive / shading records in leaf-contiguous slot order (layout.h)
 void flatten_records(const dsrt_scene& sc, const WideBVH& wide, std::vector<PrimRecord>& recs, std::vector<ShadeRecord>& shd);
+// marks the leaf slots that hold coplanar triangles (WideNode::flat, layout.h); after build_wide_bvh
+void mark_flat_slots(const dsrt_scene& sc, WideBVH& wide);
 // fp64 records of the parity kernel (same slot order); built on demand by dsrt_primary_hits(mode 1)
 void flatten_records64(const dsrt_scene& sc, const WideBVH& wide, std::vector<PrimRecord64>& r64);
 // float light table; returns the number of light samples per path vertex (pathtracer.cpp:474)
@@ -39,9 +41,10 @@ struct EndPlane {
 };
 std::vector<EndPlane> light_end_planes(int n_lights, const int32_t* light_type, const double* light_param);
 
-// regroup_top: children of the top wide nodes are regrouped where that lowers the SAH cost (wide_bvh.cpp, step 2b)
+// regroup_top: children of the top wide nodes are regrouped where that lowers the SAH cost (wide_bvh.cpp, step 2b); fewer node
+// visits per ray, but not fewer node steps per WARP on B200 (include/dsrt.h "regroup_top"), hence off by default
 // prim_cost: SAH cost of one primitive test relative to one wide-node visit in the collapse (1.0 measured best on B200)
 int build_wide_bvh(const dsrt_bvh2& b2, const std::vector<Box3>& pbox, int n_prims, WideBVH& out, std::string& err, double prim_cost = 1.0,
-                   const std::vector<EndPlane>* end_planes = nullptr, bool regroup_top = true);
+                   const std::vector<EndPlane>* end_planes = nullptr, bool regroup_top = false);
 
 }  // namespace dsrt

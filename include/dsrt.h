@@ -127,11 +127,16 @@ int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t
  * "max_ctas_per_sm" (caps the persistent grid; 0 = what fits), "smem_carveout_pct" (shared-memory carve-out of the
  * traversal kernels, -1 = driver default, which measured best), "collapse_prim_cost_pct" (SAH cost of a primitive test
  * relative to a wide-node visit in the collapse, percent; default 100; applies at the next dsrt_build_accel),
- * "regroup_top" (0/1, default 1; applies at the next dsrt_build_accel: where an internal child of one of the top wide nodes
+ * "drop_coplanar_mates" (0/1, default 1; applies at the next dsrt_build_accel: leaf slots whose two or three triangles lie
+ * in one plane -- the halves of a wall quad -- are marked in the node, and a ray that starts on one of them skips the others
+ * like it skips its source: it meets their plane at t = 0 only),
+ * "regroup_top" (0/1, default 0; applies at the next dsrt_build_accel: where an internal child of one of the top wide nodes
  * covers most of its parent -- the reference's binned SAH leaves the scene-sized wall triangles of a Cornell box in a subtree
  * whose box is the whole scene, which every ray then has to open -- its children and its siblings are regrouped so that the
  * summed area of the internal nodes drops: walls become direct children of the root, the mesh gets a node of its own; hits are
- * unchanged, node visits per segment fall by 9-26 % on the Cornell scenes),
+ * unchanged, node visits per segment fall by 9-26 % on the Cornell scenes; measured on B200 the closest-hit stage gains 1-8 %
+ * and the any-hit stage loses 2 %, -1.2 % / -0.2 % per frame on the two 1080p stand-ins: the rays that cross the mesh get one
+ * level more and a warp walks the union of its lanes' nodes, so the visits saved on the short rays do not shorten it),
  * "light_aligned_grid" (0/1, default 1; applies at the next dsrt_build_accel: a wide node that holds a flat child in the
  * plane of an axis-aligned area light shifts its quantisation grid by a fraction of a quantum so that the plane facing the
  * arriving shadow rays is tight -- they stop 0.1 % short of the light, src/pathtracer.cpp:486-504, and then miss the box of

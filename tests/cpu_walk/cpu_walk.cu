@@ -45,7 +45,8 @@ Walk* cw_create(const dsrt_scene* s, const dsrt_bvh2* b, int ns_area_light, int 
   if (env_w > 0) { w->env_w = env_w; w->env_h = env_h; w->env_rgb.assign(env_rgb, env_rgb + (size_t)env_w * env_h * 3); build_env_tables(env_w, env_h, w->env_rgb.data(), w->env_tp, w->env_t, w->env_pgt); }
   std::vector<Box3> pbox; primitive_boxes(s, pbox);
   const std::vector<EndPlane> ends = light_end_planes(s->n_lights, s->light_type, s->light_param);
-  if (build_wide_bvh(*b, pbox, s->n_prims, w->wide, w->err, 1.0, std::getenv("CW_NO_LIGHT_GRID") ? nullptr : &ends, std::getenv("CW_NO_REGROUP") == nullptr)) { fprintf(stderr, "cw_create: %s\n", w->err.c_str()); delete w; return nullptr; }
+  if (build_wide_bvh(*b, pbox, s->n_prims, w->wide, w->err, 1.0, std::getenv("CW_NO_LIGHT_GRID") ? nullptr : &ends, std::getenv("CW_REGROUP") != nullptr)) { fprintf(stderr, "cw_create: %s\n", w->err.c_str()); delete w; return nullptr; }
+  if (!std::getenv("CW_NO_FLAT_SLOTS")) mark_flat_slots(*s, w->wide);
   flatten_records(*s, w->wide, w->recs, w->shd); flatten_records64(*s, w->wide, w->r64);
   w->n_light_samples = flatten_lights(s->n_lights, s->light_type, s->light_param, ns_area_light, env_w > 0, w->lights);
   w->bsdfs.resize(s->n_bsdf);

@@ -436,12 +436,48 @@ def test_regrouped_top_nodes_same_image_fewer_node_visits(name, golden, monkeypa
     children of the root and gives the mesh its own node.  Same paths, same image, same segment counts, >= 10 % fewer node visits;
     every primitive still appears exactly once."""
     g = golden(name); depth = CONFIGS[name]["depth"]; cam = g["small_camera"]
+    w0 = Walk(g, g, 4, camera=cam)
+    rgb0, c0 = w0.render(2, depth, seed=5)
+    monkeypatch.setenv("CW_REGROUP", "1")                     # the option is off by default (see include/dsrt.h)
     w1 = Walk(g, g, 4, camera=cam)
     rgb1, c1 = w1.render(2, depth, seed=5)
     assert sorted(w1.slot_prim().tolist()) == list(range(w1.n_prims))
-    monkeypatch.setenv("CW_NO_REGROUP", "1")
-    w0 = Walk(g, g, 4, camera=cam)
-    rgb0, c0 = w0.render(2, depth, seed=5)
     assert np.array_equal(rgb0, rgb1) and list(c0[:3]) == list(c1[:3])
     assert int(c1[3]) < 0.9 * int(c0[3]), (c0, c1)
     assert w1.info()[1] <= w0.info()[1] + 1                  # at most one more level of wide nodes
+
+
+@pytest.mark.parametrize("name", ["CBspheres_lambertian", "CBbunny", "CBgems"])
+def test_coplanar_slot_mates_are_dropped_with_the_source(name, golden, monkeypatch):
+    """layout.h WideNode::flat: a ray leaving one half of a wall quad does not fetch the other half (it meets that plane at t = 0
+    only).  Same image, same segment counts, fewer primitive tests; the marked slots are exactly pairs / triples of triangles whose
+    vertices lie in one plane, and the mesh's curved leaves are not marked."""
+    g = golden(name); depth = CONFIGS[name]["depth"]; cam = g["small_camera"]
+    w1 = Walk(g, g, 4, camera=cam)
+    rgb1, c1 = w1.render(2, depth, seed=5)
+    monkeypatch.setenv("CW_NO_FLAT_SLOTS", "1")
+    w0 = Walk(g, g, 4, camera=cam)
+    rgb0, c0 = w0.render(2, depth, seed=5)
+    assert list(c0[:4]) == list(c1[:4])
+    assert np.allclose(rgb0, rgb1, rtol=0, atol=1e-6) and (np.abs(rgb0 - rgb1).max(axis=2) > 0).mean() < 1e-3
+    assert int(c1[4]) < 0.9 * int(c0[4]), (c0, c1)
+    sp = w1.slot_prim(); tri = np.asarray(g["tri_pos"]).reshape(-1, 3, 3); marked = 0; unmarked_multi = 0
+    for raw, raw0 in zip(w1.nodes(), w0.nodes()):
+        b = raw.tobytes()
+        flat = int(np.frombuffer(b[28:32], np.uint32)[0]); base, valid = (int(x) for x in np.frombuffer(b[32:40], np.uint32))
+        assert int(np.frombuffer(raw0.tobytes()[28:32], np.uint32)[0]) == 0
+        rank = 0
+        for s in range(8):
+            c = bin((valid >> (4 * s)) & 0xF).count("1"); prims = sp[base + rank: base + rank + c]; rank += c
+            f = (flat >> (4 * s)) & 0xF
+            assert f in (0, 0xF)
+            if c >= 2 and all(g["prim_type"][p] == 1 for p in prims):
+                P = tri[prims].reshape(-1, 3); nrm = max((np.cross(t[1] - t[0], t[2] - t[0]) for t in tri[prims]), key=np.linalg.norm)
+                dev = np.abs((P - P[0]) @ (nrm / np.linalg.norm(nrm))).max(); ext = np.linalg.norm(P - P[0], axis=1).max()
+                if f:
+                    assert dev <= 2e-6 * ext; marked += 1
+                else:
+                    assert dev > 0.5e-6 * ext; unmarked_multi += 1
+            else:
+                assert f == 0
+    assert marked >= 3                                       # wall quads (and the light quad) that share a leaf slot

@@ -12,8 +12,8 @@ from tests.scenes import CONFIGS
 
 def run(arr, bvh, cam, depth):
     out = []
-    for env in ({"CW_NO_LIGHT_GRID": "1", "CW_NO_REGROUP": "1"}, {"CW_NO_REGROUP": "1"}, {}):
-        for k in ("CW_NO_LIGHT_GRID", "CW_NO_REGROUP"):
+    for env in ({"CW_NO_LIGHT_GRID": "1"}, {}, {"CW_REGROUP": "1"}):
+        for k in ("CW_NO_LIGHT_GRID", "CW_REGROUP"):
             os.environ.pop(k, None)
         os.environ.update(env)
         w = Walk(arr, bvh, 4, camera=cam)

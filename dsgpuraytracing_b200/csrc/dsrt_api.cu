@@ -401,9 +401,10 @@ int dsrt_set_option(dsrt_ctx* ctx, const char* name, int64_t value) {
   else if (n == "pool_batches") ctx->opt_pool_batches = std::max<int64_t>(1, value);
   else if (n == "coop_min_pairs") ctx->opt_coop_min = value;
   else if (n == "max_ctas_per_sm") ctx->opt_max_ctas = value;
-  else if (n == "drop_coplanar_mates") { ctx->opt_flat_slots = value != 0; ctx->have_accel = false; }
-  else if (n == "regroup_top") { ctx->opt_regroup = value != 0; ctx->have_accel = false; }
-  else if (n == "light_aligned_grid") { ctx->opt_light_phase = value != 0; ctx->have_accel = false; }   // takes effect at the next dsrt_build_accel
+  // the three tree options take effect at the next dsrt_build_accel (a changed value invalidates the current structure)
+  else if (n == "drop_coplanar_mates") { if (ctx->opt_flat_slots != (value != 0)) ctx->have_accel = false; ctx->opt_flat_slots = value != 0; }
+  else if (n == "regroup_top") { if (ctx->opt_regroup != (value != 0)) ctx->have_accel = false; ctx->opt_regroup = value != 0; }
+  else if (n == "light_aligned_grid") { if (ctx->opt_light_phase != (value != 0)) ctx->have_accel = false; ctx->opt_light_phase = value != 0; }
   else if (n == "collapse_prim_cost_pct") { ctx->opt_prim_cost = std::max<int64_t>(1, value); ctx->have_accel = false; }   // takes effect at the next dsrt_build_accel
   else if (n == "device_build") { ctx->opt_device_build = value; ctx->have_accel = false; }   // takes effect at the next dsrt_build_accel
   else if (n == "wavefront_budget_mb") ctx->opt_mem_budget_mb = value;   // 0: 80 % of the free device memory; > 0: additional cap (tests)

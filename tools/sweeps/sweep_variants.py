@@ -23,15 +23,24 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     scene = os.environ.get("SWEEP_SCENE", "c2")        # c2 (bench scene) | soupN (config 5, N Mi triangles, 3840x2160, 1 light sample)
     if scene.startswith("soup"):
         sc, cam = S.triangle_soup(int(scene[4:]) << 20); nl = 1
+    elif scene == "c3":
+        sc, cam = S.cblucy_standin(1920, 1080); nl = 4
     else:
         V, F = S.torus_knot(); V = V.astype(np.float32).astype(np.float64)
         sc = S.cb_mesh_scene(V, F); cam = S.cam_dragon(1920, 1080); nl = 4
     core = D.Core(0); core.set_params(spp, nl, 8, 0); core.load(sc, camera=cam, device_build=bool(int(os.environ.get("SWEEP_DEVICE_BUILD", "0")))); core.set_option("stage_timing", 1)
+    tree_defaults = {"light_aligned_grid": 1, "drop_coplanar_mates": 1, "regroup_top": 0}      # take effect at dsrt_build_accel
+    tree_now = dict(tree_defaults)
     defaults = {"max_ctas_per_sm": 0, "postpone_min_lanes": 8, "refill_busy_lanes": 18, "coop_min_pairs": 6, "postpone_wait_mode": 0, "pool_batches": 8, "batch_spp": 0, "smem_carveout_pct": -1, "refill_hi_lanes": 26, "refill_patience": 6}
     for o in OPTS:
         try:
-            for k, v in {**defaults, **o}.items():
+            for k, v in {**defaults, **{k: v for k, v in o.items() if k not in tree_defaults}}.items():
                 core.set_option(k, v)
+            tree = {k: {**tree_defaults, **o}[k] for k in tree_defaults}
+            if tree != tree_now:
+                for k, v in tree.items():
+                    core.set_option(k, v)
+                core.build_accel(); tree_now = tree
         except D.DsrtError as e:
             print(os.path.basename(os.environ.get("DSRT_LIB", "libdsrt.so")), o, "unsupported:", str(e)[:60]); continue
         core.render(); rgb, st = core.render()

@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
           const NodeRegs nd = load_node(A.nodes, node);
           if (COUNT) cnt.nodes++;
           const uint32_t m = test_children<false, kSat>(ray, fr, nd, tbest, 0.f, A.one_bits);
-          split_hits<kOrdered>(m, nd.n1, fr, ray.src_slot, A.nodes, node, ngroup, tgroup);
+          split_hits<kOrdered>(m, nd.n1, nd.flat, fr, ray.src_slot, node, ngroup, tgroup);
           did_node = true;
         }
       }

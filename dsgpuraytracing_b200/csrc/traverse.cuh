@@ -40,27 +40,15 @@ DSRT_HD bool leaves_sphere(int src, int slot) { return src < -1 && slot == -(src
 // visit per ray, so the bit is looked up in a (rare) branch instead of with straight-line code on every visit.
 // The node's `flat` word (layout.h) extends this to the source's coplanar slot mates -- the other half of a wall quad, which
 // every ray leaving a Cornell wall would otherwise fetch and test (0.85 of the 3.1 primitive tests per shadow ray on the bench
-// scene): a ray that starts in a triangle's plane meets that plane at t = 0 only.  The word is read in the rare branch.
-DSRT_HD uint32_t load_node_flat(const uint4* __restrict__ nodes, uint32_t node) {
-#if DSRT_NODE96
-  const uint32_t* p = reinterpret_cast<const uint32_t*>(nodes + (size_t)node * kNodeQuads + 1) + 3;
-#ifdef __CUDA_ARCH__
-  return __ldg(p);
-#else
-  return *p;
-#endif
-#else
-  return 0u;
-#endif
-}
-DSRT_HD uint32_t drop_source(uint32_t prim_mask, uint32_t prim_base, uint32_t valid, int src, const uint4* __restrict__ nodes = nullptr, uint32_t node = 0u) {
+// scene): a ray that starts in a triangle's plane meets that plane at t = 0 only.  The word arrives with the node's first
+// 256-bit load (NodeRegs::flat), so the branch needs no memory access.
+DSRT_HD uint32_t drop_source(uint32_t prim_mask, uint32_t prim_base, uint32_t valid, int src, uint32_t flat = 0u) {
   const uint32_t rel = (uint32_t)src - prim_base;     // wraps to a huge value for src < prim_base (incl. -1 and sphere codes)
   if (rel < 24u && rel < (uint32_t)hd_popc(valid)) {      // (a node holds at most 24 primitives: the first test is the cheap one)
     uint32_t v = valid;
 #pragma unroll 1
     for (uint32_t i = 0; i < rel; i++) v &= v - 1u;
     const uint32_t bit = v & (0u - v);
-    const uint32_t flat = nodes ? load_node_flat(nodes, node) : 0u;
     prim_mask &= ~(bit | (flat & (0xfu << ((31u - (uint32_t)hd_clz(bit)) & 0x1cu))));
   }
   return prim_mask;
@@ -242,6 +230,7 @@ struct NodeRegs {
   uint4 n1;            // prim_base, valid, child_base, inner
   uint4 n2, n3, n4;    // quantised planes: (qlox, qloy) (qloz, qhix) (qhiy, qhiz), 8 bytes each
   float sx, sy, sz;    // plane scales 2^15 * 2^(e-127)
+  uint32_t flat;       // leaf slots of coplanar triangles (layout.h); arrives with the first 256-bit load
 };
 DSRT_HD NodeRegs load_node(const uint4* __restrict__ nodes, uint32_t node) {
   NodeRegs n;
@@ -255,16 +244,17 @@ DSRT_HD NodeRegs load_node(const uint4* __restrict__ nodes, uint32_t node) {
                : "=r"(n.n1.x), "=r"(n.n1.y), "=r"(n.n1.z), "=r"(n.n1.w), "=r"(n.n2.x), "=r"(n.n2.y), "=r"(n.n2.z), "=r"(n.n2.w) : "l"(np + 2));
   asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(n.n3.x), "=r"(n.n3.y), "=r"(n.n3.z), "=r"(n.n3.w), "=r"(n.n4.x), "=r"(n.n4.y), "=r"(n.n4.z), "=r"(n.n4.w) : "l"(np + 4));
-  n.sx = __uint_as_float(sx); n.sy = __uint_as_float(sy); n.sz = __uint_as_float(sz);
+  n.sx = __uint_as_float(sx); n.sy = __uint_as_float(sy); n.sz = __uint_as_float(sz); n.flat = pad;
 #else
   const uint4 s4 = np[1];
   n.n0 = np[0]; n.n1 = np[2]; n.n2 = np[3]; n.n3 = np[4]; n.n4 = np[5];
-  n.sx = hd_u2f(s4.x); n.sy = hd_u2f(s4.y); n.sz = hd_u2f(s4.z);
+  n.sx = hd_u2f(s4.x); n.sy = hd_u2f(s4.y); n.sz = hd_u2f(s4.z); n.flat = s4.w;
 #endif
 #else
   n.n0 = hd_ldg(np); n.n1 = hd_ldg(np + 1); n.n2 = hd_ldg(np + 2); n.n3 = hd_ldg(np + 3); n.n4 = hd_ldg(np + 4);
   // the node stores its exponent bytes biased up by 15 (layout.h): a byte moved into the exponent field IS 2^15 * 2^(e-127)
   n.sx = hd_u2f((n.n0.w << 23) & 0x7f800000u); n.sy = hd_u2f((n.n0.w << 15) & 0x7f800000u); n.sz = hd_u2f((n.n0.w << 7) & 0x7f800000u);
+  n.flat = 0u;
 #endif
   return n;
 }
@@ -446,10 +436,10 @@ DSRT_HD uint32_t next_child(uint2& ngroup, const NodeFrame& fr, bool& more) {
 }
 // node test results -> (children to open, primitives to test).  n1 = (prim_base, valid, child_base, inner), layout.h
 template <bool ORDERED>
-DSRT_HD void split_hits(uint32_t m, const uint4 n1, const NodeFrame& fr, int src_slot, const uint4* __restrict__ nodes, uint32_t node, uint2& ngroup, uint2& tgroup) {
+DSRT_HD void split_hits(uint32_t m, const uint4 n1, uint32_t flat, const NodeFrame& fr, int src_slot, uint32_t node, uint2& ngroup, uint2& tgroup) {
   const uint32_t open = m & n1.w;
   ngroup = make_uint2(n1.z, (ORDERED ? order_children(open, fr) : open) | (n1.w >> 3));
-  tgroup = make_uint2(node, drop_source(m & n1.y, n1.x, n1.y, src_slot, nodes, node));
+  tgroup = make_uint2(node, drop_source(m & n1.y, n1.x, n1.y, src_slot, flat));
 }
 
 template <bool ANY, bool PARITY, bool COUNT>
@@ -480,7 +470,7 @@ DSRT_HD void trace_ray(const Accel& A, const TraceRay& ray, const Ray64* ray64, 
       const NodeRegs nd = load_node(A.nodes, node);
       if (COUNT) cnt->nodes++;
       const uint32_t m = test_children<PARITY, SAT>(ray, fr, nd, tbest, A.pad, A.one_bits);
-      split_hits<ORDERED>(m, nd.n1, fr, ray.src_slot, A.nodes, node, ngroup, tgroup);
+      split_hits<ORDERED>(m, nd.n1, nd.flat, fr, ray.src_slot, node, ngroup, tgroup);
       prim_base = nd.n1.x; valid = nd.n1.y;
     } else {
       tgroup = make_uint2(0u, 0u);

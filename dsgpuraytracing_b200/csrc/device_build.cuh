@@ -16,6 +16,7 @@
 //   k_db_collapse  one tree level per launch: a wide node takes the two children of its binary root and keeps replacing the
 //                  child of largest surface area by its two children until it has 8 (a subtree of <= 3 primitives whose box
 //                  is tight stays whole as one leaf child); octant-ordered slots and outward quantisation exactly as wide_bvh.cpp
+//   k_db_mark_flat leaf slots of coplanar triangles (WideNode::flat)
 //   k_db_flatten   48-byte primitive / shading records in slot order
 #pragma once
 #include <cuda_runtime.h>
@@ -183,10 +184,15 @@ __device__ __forceinline__ bool db_is_leaf_child(const DbKid& k, const DbTree& T
   return db_area(k) * (float)k.count <= DSRT_DB_GROUP_ALPHA * sum;
 }
 
+// axis-aligned area lights (wide_bvh.h EndPlane), by value to the collapse kernel: a node holding a flat child in such a plane
+// shifts its quantisation grid exactly like wide_bvh.cpp emit_node does
+constexpr int kDbMaxEndPlanes = 4;
+struct DbEndPlanes { int n; int axis[kDbMaxEndPlanes]; int from_low[kDbMaxEndPlanes]; double coord[kDbMaxEndPlanes]; double lo[kDbMaxEndPlanes][3], hi[kDbMaxEndPlanes][3]; };
+
 // items: (binary reference, wide node index).  counters: [0] wide nodes allocated, [1] primitive slots allocated, [2] items of
 // the next level, [3] error flag
 __global__ void k_db_collapse(DbTree T, const int2* __restrict__ items, int n_items, int2* next_items, unsigned int* counters,
-                              WideNode* nodes, int32_t* slot_prim, unsigned int node_cap) {
+                              WideNode* nodes, int32_t* slot_prim, unsigned int node_cap, DbEndPlanes ends) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_items) return;
   const int2 it = items[t];
@@ -245,6 +251,29 @@ __global__ void k_db_collapse(DbTree T, const int2* __restrict__ items, int n_it
       if (ceil((nhi[k] - (double)org[k]) / scale[k] + 1.0 / 64) <= 255.0 || e >= 110) break;
       e++;
     }
+    // light-aligned grid (wide_bvh.cpp emit_node): a flat child in the plane of an area light gets its light-facing plane
+    // 3/128 quantum past a grid line
+    for (int p = 0; p < ends.n; p++) {
+      if (ends.axis[p] != k) continue;
+      const double tol = 1e-6 * fmax(1.0, fabs(ends.coord[p]));
+      bool found = false; double at = 0;
+      for (int i = 0; i < nk && !found; i++) {
+        const float* b = kids[i].b;
+        if (fabs((double)b[k] - ends.coord[p]) > tol || fabs((double)b[3 + k] - ends.coord[p]) > tol) continue;
+        bool overlap = true;
+        for (int a = 0; a < 3; a++) if (a != k && ((double)b[3 + a] < ends.lo[p][a] || (double)b[a] > ends.hi[p][a])) overlap = false;
+        if (overlap) { found = true; at = ends.from_low[p] ? (double)b[k] : (double)b[3 + k]; }
+      }
+      if (!found) continue;
+      const double want = ends.from_low[p] ? 3.0 / 128 : 1.0 - 3.0 / 128;
+      const double x0 = (at - (nlo[k] - scale[k])) / scale[k];
+      double d = want - (x0 - floor(x0));
+      if (d < 0) d += 1.0;
+      const float org_a = __double2float_rd(nlo[k] - scale[k] * (1.0 + d));
+      const double xa = (at - (double)org_a) / scale[k], fa = xa - floor(xa);
+      if (fabs(fa - want) <= 1.0 / 256 && (double)org_a <= nlo[k] - scale[k] && ceil((nhi[k] - (double)org_a) / scale[k] + 1.0 / 64) <= 255.0) org[k] = org_a;
+      break;
+    }
     (&w.ex)[k] = (uint8_t)(e + 127 + 15);
 #if DSRT_NODE96
     (&w.sx)[k] = __uint_as_float((uint32_t)(e + 127 + 15) << 23);
@@ -281,6 +310,44 @@ __global__ void k_db_collapse(DbTree T, const int2* __restrict__ items, int n_it
     }
   }
   nodes[it.y] = w;
+}
+
+// WideNode::flat (layout.h), as mark_flat_slots (wide_bvh.cpp) sets it: leaf slots whose 2-3 triangles lie in one plane
+__global__ void k_db_mark_flat(DbScene sc, WideNode* nodes, int n_nodes, const int32_t* __restrict__ slot_prim) {
+#if DSRT_NODE96
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_nodes) return;
+  const uint32_t valid = nodes[n].valid, prim_base = nodes[n].prim_base;
+  uint32_t flat = 0, rank = 0;
+  for (int s = 0; s < 8; s++) {
+    const int c = __popc((valid >> (4 * s)) & 0xfu);
+    const uint32_t first = prim_base + rank; rank += (uint32_t)c;
+    if (c < 2) continue;
+    const double* best = nullptr; double best_n2 = 0, nx = 0, ny = 0, nz = 0, ext = 0; bool tris = true;
+    for (int i = 0; i < c; i++) {
+      const int p = slot_prim[first + i];
+      if (sc.prim_type[p] != 1) { tris = false; break; }
+      const double* v = sc.tri_pos + 9 * (size_t)p;
+      const double ax = v[3] - v[0], ay = v[4] - v[1], az = v[5] - v[2], bx = v[6] - v[0], by = v[7] - v[1], bz = v[8] - v[2];
+      const double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx, n2 = cx * cx + cy * cy + cz * cz;
+      ext = fmax(ext, sqrt(fmax(ax * ax + ay * ay + az * az, bx * bx + by * by + bz * bz)));
+      if (n2 > best_n2) { best_n2 = n2; best = v; nx = cx; ny = cy; nz = cz; }
+    }
+    if (!tris || !best || !(best_n2 > 0) || !isfinite(best_n2)) continue;
+    const double inv = 1.0 / sqrt(best_n2);
+    double dev = 0;
+    for (int i = 0; i < c; i++) {
+      const double* v = sc.tri_pos + 9 * (size_t)slot_prim[first + i];
+      for (int k = 0; k < 3; k++) {
+        const double dx = v[3 * k] - best[0], dy = v[3 * k + 1] - best[1], dz = v[3 * k + 2] - best[2];
+        dev = fmax(dev, fabs((dx * nx + dy * ny + dz * nz) * inv));
+        ext = fmax(ext, sqrt(dx * dx + dy * dy + dz * dz));
+      }
+    }
+    if (dev <= 1e-6 * ext) flat |= 0xfu << (4 * s);
+  }
+  nodes[n].flat = flat;
+#endif
 }
 
 __global__ void k_db_flatten(DbScene sc, int n_slots, const int32_t* __restrict__ slot_prim, PrimRecord* recs, ShadeRecord* shd) {

@@ -469,11 +469,20 @@ static int build_wide_bvh_device(dsrt_ctx* ctx, DevState& D, float scene_box[6])
   DbTree T; T.left = d_left; T.right = d_right; T.first = d_first; T.last = d_last; T.ibox = d_ibox; T.pbox = d_pbox; T.sorted = d_sorted;
   CK(cudaStreamSynchronize(st));
   const double t1 = now();
+  DbEndPlanes ends; std::memset(&ends, 0, sizeof(ends));
+  if (ctx->opt_light_phase) {
+    for (const EndPlane& e : light_end_planes((int)ctx->light_type.size(), ctx->light_type.data(), ctx->light_param.data())) {
+      if (ends.n == kDbMaxEndPlanes) break;
+      const int i = ends.n++;
+      ends.axis[i] = e.axis; ends.from_low[i] = e.from_low ? 1 : 0; ends.coord[i] = e.coord;
+      for (int k = 0; k < 3; k++) { ends.lo[i][k] = e.lo[k]; ends.hi[i][k] = e.hi[k]; }
+    }
+  }
   unsigned n_items = 1; int levels = 0, cur = 0;
   while (n_items > 0) {
     levels++;
     if (levels > kStackEntries) return fail(ctx, DSRT_ERR_LIMIT, "dsrt_build_accel(device_build): wide BVH deeper than the traversal stack");
-    k_db_collapse<<<(n_items + 127) / 128, 128, 0, st>>>(T, d_items[cur], (int)n_items, d_items[cur ^ 1], d_cnt, d_nodes, d_slot, node_cap);
+    k_db_collapse<<<(n_items + 127) / 128, 128, 0, st>>>(T, d_items[cur], (int)n_items, d_items[cur ^ 1], d_cnt, d_nodes, d_slot, node_cap, ends);
     unsigned int h[4];
     CK(cudaMemcpyAsync(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -497,6 +506,7 @@ static int build_wide_bvh_device(dsrt_ctx* ctx, DevState& D, float scene_box[6])
   CK(cudaMalloc(&D.d_prims, n_slots * sizeof(PrimRecord))); CK(cudaMalloc(&D.d_shade, n_slots * sizeof(ShadeRecord)));
   k_db_flatten<<<(unsigned)((n_slots + B - 1) / B), B, 0, st>>>(sc, (int)n_slots, d_slot, (PrimRecord*)D.d_prims, (ShadeRecord*)D.d_shade);
   CK(cudaGetLastError());
+  if (ctx->opt_flat_slots) { k_db_mark_flat<<<(unsigned)((n_wide + B - 1) / B), B, 0, st>>>(sc, d_nodes, (int)n_wide, d_slot); CK(cudaGetLastError()); }
   ctx->wide.nodes.resize(n_wide); ctx->wide.slot_prim.resize(n_slots); ctx->wide.max_depth = levels;
   ctx->recs.clear(); ctx->recs.shrink_to_fit(); ctx->shd.clear(); ctx->shd.shrink_to_fit(); ctx->recs_on_device = true;
   CK(cudaMemcpyAsync(ctx->wide.nodes.data(), d_nodes, n_wide * sizeof(WideNode), cudaMemcpyDeviceToHost, st));

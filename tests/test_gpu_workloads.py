@@ -373,6 +373,40 @@ def test_device_built_bvh_on_the_measured_scenes(core):
     core.set_option("device_build", 0)
 
 
+# ---- options that shape the wide BVH without changing a hit ("light_aligned_grid", "drop_coplanar_mates", "regroup_top") -----------
+@pytest.mark.gpu
+@pytest.mark.parametrize("device_build", [False, True])
+@pytest.mark.parametrize("name", ["CBbunny", "CBspheres"])
+def test_tree_options_change_the_fetch_counts_not_the_image(name, device_build, golden):
+    """include/dsrt.h: the emissive quad under the area light and the other half of the wall quad a ray starts on drop out of
+    the shadow rays' way (defaults), walls become direct children of the root (opt-in).  Same seed, same paths: the frames are
+    equal up to the order of the float atomics, the segment counts are equal, the primitive tests per segment fall; the host
+    builder and the device-side builder (its own grid code + k_db_mark_flat) both honour the options."""
+    g = golden(name); cfg = CONFIGS[name]
+    c = D.Core(0)
+    try:
+        c.set_params(4, cfg["nl"], cfg["depth"], 9)
+        c.set_option("count_traversal", 1)
+        out = {}
+        for key, opts in (("off", (0, 0, 0)), ("defaults", (1, 1, 0)), ("regroup", (1, 1, 1))):
+            for o, v in zip(("light_aligned_grid", "drop_coplanar_mates", "regroup_top"), opts):
+                c.set_option(o, v)
+            c.load(g, camera=g["small_camera"], device_build=device_build)
+            rgb, st = c.render()
+            out[key] = (np.array(rgb, copy=True), st.extend_rays, st.shadow_rays, st.prims_tested / st.segments, st.nodes_visited / st.segments)
+        ref = out["off"]
+        for key in ("defaults", "regroup"):
+            rgb, ext, sh, pps, nps = out[key]
+            assert (ext, sh) == (ref[1], ref[2])
+            d = np.abs(rgb - ref[0])
+            assert (d.max(axis=2) > 1e-5 * max(1.0, float(ref[0].max()))).mean() <= 1e-3, (key, d.max())
+            assert pps < (0.95 if device_build else 0.85) * ref[3], (key, pps, ref[3])
+        if not device_build:
+            assert out["regroup"][4] <= out["defaults"][4]            # node visits per segment (the device tree has no regrouping)
+    finally:
+        c.close()
+
+
 # ---- a failed call must not leave a half-updated context usable (ADVICE r1) ------------------------------------------------------
 @pytest.mark.gpu
 def test_failed_scene_or_bvh_calls_invalidate_the_context(golden):

@@ -12,7 +12,10 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "image_io.h"
 #include "pathtracer.h"
@@ -28,6 +31,7 @@ static void usage(const char* bin) {
   printf("  -g <INT>  number of GPUs (default 1)\n  -o <FILE> output PNG (default \"Screen Shot GPU <time>.png\")\n");
   printf("  -e <FILE> lat-long environment map (.exr or .pfm)\n");
   printf("  -T        import meshes the half-edge builder rejects (non-manifold ...) as plain indexed triangles\n");
+  printf("  -O <NAME=INT> option of the GPU core (include/dsrt.h dsrt_set_option: skip_null_shadow, regroup_top, wavefront_budget_mb, ...); repeatable\n");
   printf("  -S <INT>  Philox seed (default 0)\n  -r <FILE> also dump the linear float RGB buffer\n  -j        one JSON line of run statistics\n");
 }
 
@@ -37,8 +41,9 @@ int main(int argc, char** argv) {
   unsigned seed = 0;
   bool useCPU = false, json = false;
   std::string camFileName, outName, rawName, envName;
+  std::vector<std::pair<std::string, long long>> coreOptions;
   int opt;
-  while ((opt = getopt(argc, argv, "s:l:t:m:f:w:h:g:o:S:r:e:vcTj")) != -1) {
+  while ((opt = getopt(argc, argv, "s:l:t:m:f:w:h:g:o:O:S:r:e:vcTj")) != -1) {
     switch (opt) {
       case 's': ns_aa = (size_t)atoi(optarg); break;
       case 'l': ns_area_light = (size_t)atoi(optarg); break;
@@ -49,6 +54,12 @@ int main(int argc, char** argv) {
       case 'f': camFileName = optarg; break;
       case 'g': n_gpus = atoi(optarg); break;
       case 'o': outName = optarg; break;
+      case 'O': {
+        const char* eq = strchr(optarg, '=');
+        if (!eq || eq == optarg) { fprintf(stderr, "-O expects NAME=INT\n"); return 1; }
+        coreOptions.emplace_back(std::string(optarg, (size_t)(eq - optarg)), atoll(eq + 1));
+        break;
+      }
       case 'S': seed = (unsigned)strtoul(optarg, nullptr, 10); break;
       case 'r': rawName = optarg; break;
       case 'e': envName = optarg; break;
@@ -70,6 +81,7 @@ int main(int argc, char** argv) {
   if (!envName.empty() && !load_envmap(envName, envmap, err)) { fprintf(stderr, "error: %s\n", err.c_str()); return 1; }
   PathTracer pathtracer(ns_aa, max_ray_depth, ns_area_light, 1, 1, 1, num_threads, envName.empty() ? nullptr : &envmap);
   pathtracer.set_gpus(n_gpus); pathtracer.set_seed(seed);
+  for (const auto& o : coreOptions) pathtracer.set_option(o.first, o.second);
   pathtracer.set_camera(&camera);
   pathtracer.set_scene(&scene);
   pathtracer.set_frame_size((size_t)screenW, (size_t)screenH);

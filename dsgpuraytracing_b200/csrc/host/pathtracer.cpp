@@ -104,6 +104,8 @@ void PathTracer::start_raytracing() {
     std::vector<int> devs(n_gpus); for (int i = 0; i < n_gpus; i++) devs[i] = i;
     int rc = n_gpus > 1 ? dsrt_create_multi(n_gpus, devs.data(), &ctx) : dsrt_create(0, &ctx);
     if (rc) { fail("dsrt_create"); if (ctx) { dsrt_destroy(ctx); ctx = nullptr; } state = READY; return; }
+    for (const auto& o : options)
+      if (dsrt_set_option(ctx, o.first.c_str(), o.second)) { fail("dsrt_set_option(" + o.first + ")"); dsrt_destroy(ctx); ctx = nullptr; state = READY; return; }
   }
   if (!accel_uploaded) {
     dsrt_scene sc{};

@@ -56,6 +56,9 @@ class PathTracer {
   // extensions of this port
   void set_gpus(int n) { n_gpus = n < 1 ? 1 : n; }
   void set_seed(uint32_t s) { seed = s; }
+  // dsrt_set_option passthrough (include/dsrt.h: "skip_null_shadow", "regroup_top", "wavefront_budget_mb", ...); applied when the
+  // GPU context is created, before the scene is handed over
+  void set_option(const std::string& name, int64_t value) { options.emplace_back(name, value); }
   const std::string& last_error() const { return error; }
   const dsrt_stats& stats() const { return last_stats; }
 
@@ -80,6 +83,7 @@ class PathTracer {
   bool accel_uploaded = false;
   int n_gpus = 1;
   uint32_t seed = 0;
+  std::vector<std::pair<std::string, int64_t>> options;
   std::string error;
   dsrt_stats last_stats{};
 };

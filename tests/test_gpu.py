@@ -269,6 +269,15 @@ def test_cli_binary(tmp_path):
     assert ok, info
     r = subprocess.run([exe, "-c", O.ref_scene_path("CBspheres_lambertian.dae")], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    # -O NAME=INT hands options to the GPU core: skipped null shadow rays are not counted as traced, an unknown name is an error
+    base = ["-s", "2", "-l", "4", "-m", "5", "-w", "96", "-h", "72", "-S", "5", "-j", "-o", str(png), O.ref_scene_path("CBspheres_lambertian.dae")]
+    r = subprocess.run([exe, "-O", "skip_null_shadow=1", "-O", "regroup_top=1"] + base, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r0 = subprocess.run([exe] + base, capture_output=True, text=True, timeout=120)
+    j1 = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1]); j0 = json.loads([l for l in r0.stdout.splitlines() if l.startswith("{")][-1])
+    assert j1["extend_rays"] == j0["extend_rays"] and j1["shadow_rays"] <= j0["shadow_rays"]
+    r = subprocess.run([exe, "-O", "no_such_option=1"] + base, capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "dsrt_set_option" in r.stderr
 
 
 def test_multi_device_context_matches_single(golden):

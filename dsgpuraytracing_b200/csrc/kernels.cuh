@@ -43,7 +43,9 @@ constexpr int kTraceThreads = 128;        // 4 warps per CTA
 #define DSRT_ROUND_CAP 0                  // > 0: an owner contributes at most this many primitives to one cooperative round (the scatter loop's trip count is the maximum over the owners)
 #endif
 #ifndef DSRT_NODE_STEPS
-#define DSRT_NODE_STEPS 2                 // node steps a lane may take between two warp-wide primitive-test decisions (1 / 2 / 3: 6839 / 6893 / 6741 Mrays/s)
+#define DSRT_NODE_STEPS 4                 // node steps a lane may take between two warp-wide primitive-test decisions.  2 was best (1 / 2 / 3: 6839 / 6893 /
+                                          // 6741 Mrays/s) while a shadow ray tested 4.3 primitives; with 2.25 (light-aligned grid, coplanar mates, layout.h) the
+                                          // decisions are the smaller part: 2 / 3 / 4 = 7886 / 7935 / 7995 on the bench scene, soups +1.4-2.4 % (r2c37-r2c39)
 #endif
 // Per-lane ray block in shared memory (value-major): what a lane needs to test ANOTHER lane's ray against a triangle.  Shared
 // memory is the scarce resource of this kernel -- every KB taken here is L1 taken from the node / primitive fetches (7 CTAs per

@@ -34,7 +34,7 @@ constexpr int kTraceThreads = 128;        // 4 warps per CTA
 #define DSRT_TRACE_MIN_CTAS 7             // resident CTAs per SM the traversal kernels are compiled for (register cap 72; measured best of 6, 7, 8)
 #endif
 #ifndef DSRT_NODE_STEPS_CLOSEST
-#define DSRT_NODE_STEPS_CLOSEST 2         // the same for the closest-hit kernel
+#define DSRT_NODE_STEPS_CLOSEST 3         // the same for the closest-hit kernel (2 / 3 / 4: bench scene 7 997 / 8 006 / 7 985, 8 Mi soup 1 248 / 1 260 / 1 262, r2c41)
 #endif
 #ifndef DSRT_PREFETCH_AHEAD
 #define DSRT_PREFETCH_AHEAD 16384         // queue positions between a refill's loads and the L2 prefetches it issues (0 = off)

@@ -130,7 +130,7 @@ int dsrt_set_params(dsrt_ctx* ctx, int32_t ns_aa, int32_t ns_area_light, int32_t
  * "drop_coplanar_mates" (0/1, default 1; applies at the next dsrt_build_accel: leaf slots whose two or three triangles lie
  * in one plane -- the halves of a wall quad -- are marked in the node, and a ray that starts on one of them skips the others
  * like it skips its source: it meets their plane at t = 0 only),
- * "regroup_top" (0/1, default 0; applies at the next dsrt_build_accel: where an internal child of one of the top wide nodes
+ * "regroup_top" (0/1, default 0; host builder only; applies at the next dsrt_build_accel: where an internal child of one of the top wide nodes
  * covers most of its parent -- the reference's binned SAH leaves the scene-sized wall triangles of a Cornell box in a subtree
  * whose box is the whole scene, which every ray then has to open -- its children and its siblings are regrouped so that the
  * summed area of the internal nodes drops: walls become direct children of the root, the mesh gets a node of its own; hits are

@@ -481,3 +481,25 @@ def test_coplanar_slot_mates_are_dropped_with_the_source(name, golden, monkeypat
             else:
                 assert f == 0
     assert marked >= 3                                       # wall quads (and the light quad) that share a leaf slot
+
+
+def test_light_aligned_grid_ignores_lights_it_cannot_use(golden, monkeypatch):
+    """wide_bvh.cpp light_end_planes: only area lights whose direction is a coordinate axis and whose edges span the other two
+    define a plane the grid can be aligned to; a tilted light, a non-finite one or a point light leave every node exactly as
+    the option-off build has it (and nothing crashes)."""
+    g = dict(golden("CBspheres_lambertian"))
+    lp = np.array(g["light_param"], np.float64).reshape(-1, 28).copy()
+    variants = []
+    t = lp.copy(); t[0, 6:9] = [0.0, -0.8, 0.6]; variants.append(("tilted", g["light_type"], t))
+    t = lp.copy(); t[0, 3:6] = [0.0, np.nan, 0.0]; variants.append(("nan", g["light_type"], t))
+    t = lp.copy(); variants.append(("point", np.full_like(g["light_type"], 2), t))
+    t = lp.copy(); t[0, 9:12] = [0.6, 0.1, 0.0]; variants.append(("edge leaves the plane", g["light_type"], t))
+    for name, lt, p in variants:
+        arr = dict(g); arr["light_type"] = lt; arr["light_param"] = p
+        monkeypatch.delenv("CW_NO_LIGHT_GRID", raising=False)
+        on = Walk(arr, g, 4).nodes()
+        monkeypatch.setenv("CW_NO_LIGHT_GRID", "1")
+        off = Walk(arr, g, 4).nodes()
+        assert np.array_equal(on, off), name
+    monkeypatch.delenv("CW_NO_LIGHT_GRID", raising=False)
+    assert not np.array_equal(Walk(g, g, 4).nodes(), off)       # the scene's own light does move the grid

@@ -50,7 +50,10 @@ namespace {
 struct BuildNode { Box3 box; int start, range, left, right; };
 
 struct Builder {
-  static constexpr int kBuckets = 32;
+#ifndef DSRT_SAH_BUCKETS
+#define DSRT_SAH_BUCKETS 32          // the reference's bucket count (bvh.cpp:21-202); other values are for experiments only (the topology then differs)
+#endif
+  static constexpr int kBuckets = DSRT_SAH_BUCKETS;
   static constexpr int kMaxLeaf = 4;
   static constexpr int kParallelMin = 1 << 16;     // spawn a task for subtrees at least this large
   static constexpr int kParallelBin = 1 << 21;     // bin nodes at least this large with all threads

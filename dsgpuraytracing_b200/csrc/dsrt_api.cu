@@ -543,6 +543,8 @@ int dsrt_build_accel(dsrt_ctx* ctx) {
   std::string err;
   const std::vector<EndPlane> ends = ctx->opt_light_phase ? light_end_planes((int)ctx->light_type.size(), ctx->light_type.data(), ctx->light_param.data()) : std::vector<EndPlane>();
   int rc = build_wide_bvh(b, pbox, ctx->n_prims, ctx->wide, err, (double)ctx->opt_prim_cost / 100.0, &ends, ctx->opt_regroup != 0);
+  if (!rc && ctx->opt_regroup && ctx->wide.max_depth > kStackEntries)      // regrouping may add levels: never at the price of a scene that no longer fits the stack
+    rc = build_wide_bvh(b, pbox, ctx->n_prims, ctx->wide, err, (double)ctx->opt_prim_cost / 100.0, &ends, false);
   if (rc) return fail(ctx, rc, err);
   if (ctx->opt_flat_slots) mark_flat_slots(s, ctx->wide);
   }

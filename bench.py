@@ -411,7 +411,9 @@ def run_ours(a):
                 "other_roofline": {"bound": "hbm" if l2_regime else "l2", "peak": hbm_peak if l2_regime else l2_gbs,
                                    "frac": achieved / (hbm_peak if l2_regime else l2_gbs), "peak_source": hbm_src if l2_regime else "live L2 probe",
                                    "hbm_read_gbs_same_probe": hbm_read_gbs},
-                "note": "the kernel is instruction-issue / ALU-pipe bound (profiles/r2_ktrace_summary.md); DRAM only sees the ray queues"}
+                "note": "the kernel is instruction-issue / ALU-pipe bound (profiles/r2_ktrace_summary.md); DRAM only sees the ray queues; bytes_per_segment "
+                        "comes from this run's exact node / primitive fetch counters, so a tree that needs fewer fetches lowers 'achieved' together with the time "
+                        "(bench scene: 666 B/segment before the light-aligned grid and the coplanar-mate drop, DESIGN.md section 3 and 4.1)"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

@@ -163,7 +163,8 @@ __global__ void k_generate_centres(PathState ps, RenderParams rp, int n_paths) {
 //  * cooperative any-hit test (ANY): the pending (ray, primitive) pairs of the whole warp are written to a per-warp table
 //    (slices reserved with one shared-memory atomic per lane) and dealt out one per lane; the per-ray data the test needs
 //    (origin, watertight basis, tmax, source) lives in a per-lane shared-memory block, a hit sets the owner's flag;
-//  * a ray never fetches the triangle it starts on: its bit is dropped from the leaf hit mask (drop_source, traverse.cuh).
+//  * a ray never fetches the triangle it starts on, nor that triangle's coplanar slot mates (the other half of a wall quad):
+//    their bits are dropped from the leaf hit mask (drop_source, traverse.cuh; WideNode::flat, layout.h).
 
 // shared-memory accesses of k_trace by 32-bit shared-window address (no generic-address arithmetic in the hot loop)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(kTraceThreads, DSRT_TRACE_MIN_CTAS) k_trace(Ac
   TraceRay ray; NodeFrame fr;
   float tbest = 0.f; TraceHit hit;
   constexpr bool kSat = ANY ? (DSRT_SAT_SLAB != 0) : (DSRT_SAT_CLOSEST != 0);      // saturating node test (traverse.cuh)
-  constexpr bool kOrdered = !ANY || (DSRT_ANY_ORDERED != 0);                       // children opened front to back
+  constexpr bool kOrdered = !ANY || (DSRT_ANY_ORDERED != 0);                       // children opened front to back (closest hit) / in slot order (any hit, traverse.cuh DSRT_ANY_ORDERED)
   float t_unit = 1.f;                              // closest hit: the distance the frame is currently scaled to
   uint32_t spa = s_stack;                          // address of the first free stack entry (== s_stack: empty)
   uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
